@@ -1,0 +1,169 @@
+/*
+ * dfine_b200.h -- C-ABI of the B200-native decoder hot path of D-FINE-seg.
+ *
+ * One shared library (libdfine_b200.so, hand-written CUDA for sm_100a) exports
+ * exactly these entry points.  Every argument is a plain pointer, integer or
+ * float: no torch / C++ types cross the boundary.  Citations are relative to the
+ * reference tree (uc-vision/D-FINE-seg).
+ *
+ * Conventions
+ *   - All device pointers are owned by the caller (PyTorch caching allocator on
+ *     the reference side).  The library never allocates or frees device memory,
+ *     never synchronises the device, and launches only on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream).
+ *   - Small per-level tables (`lvl_hw`, `lvl_start`, `lvl_npts`) are HOST
+ *     pointers; they are copied by value into the kernel parameters.
+ *   - Return value: 0 = success; <0 = argument error (DFINE_E_*);
+ *     >0 = a cudaError_t raised by the launch.  dfine_last_error() returns a
+ *     thread-local human readable message for the last non-zero return.
+ *   - There is no CPU fallback: a NULL / host data pointer is an error.
+ */
+#ifndef DFINE_B200_H_
+#define DFINE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFINE_B200_VERSION 100 /* major*100 + minor */
+
+/* element types of value / grad_out / raw Linear outputs / GEMM operands */
+#define DFINE_F32 0
+#define DFINE_BF16 1
+
+/* argument errors */
+#define DFINE_E_NULL (-1)        /* required pointer is NULL */
+#define DFINE_E_SHAPE (-2)       /* non-positive / inconsistent size */
+#define DFINE_E_UNSUPPORTED (-3) /* head_dim / n_levels / n_points / dtype not built */
+#define DFINE_E_ALIGN (-4)       /* pointer or stride not 16-byte aligned */
+
+#define DFINE_MAX_LEVELS 4
+#define DFINE_MAX_POINTS 32 /* sum(num_points_list) per head */
+
+/* flags for dfine_msda_fwd / dfine_msda_bwd */
+#define DFINE_MSDA_FUSED_INPUTS 1 /* sampling inputs are raw Linear outputs + ref boxes */
+
+int dfine_version(void);
+const char* dfine_last_error(void);
+
+/* --------------------------------------------------------------------------
+ * K1  multi-scale deformable attention, forward.
+ *
+ * Replaces  deformable_attention_core_func_v2   src/d_fine/arch/utils.py:191-264
+ * (bound as MSDeformableAttention.ms_deformable_attn_core, dfine_decoder.py:90-92,
+ *  called at dfine_decoder.py:174-176) and, with DFINE_MSDA_FUSED_INPUTS, also the
+ * softmax + sampling-location arithmetic of MSDeformableAttention.forward
+ * (dfine_decoder.py:144-166, reference_points last-dim 4 branch).
+ *
+ * value      element (b, l, h, k) lives at value[b*v_stride_b + l*v_stride_l + h*c + k]
+ *            (strides in ELEMENTS).  This is the zero-copy layout behind the tuple of
+ *            views that TransformerDecoder.value_op returns (dfine_decoder.py:416-426):
+ *            memory [B, L, H*c] => v_stride_b = L*H*c, v_stride_l = H*c.
+ * lvl_hw     host int32 [n_lvl][2] = (h_l, w_l)          (value_spatial_shapes)
+ * lvl_start  host int32 [n_lvl]    = first flattened pixel of level l
+ * lvl_npts   host int32 [n_lvl]    = num_points_list; P = sum
+ * plain mode (flags == 0):
+ *   samp     float32 [B, Lq, H, P, 2]  sampling_locations in [0,1] (x, y)
+ *   attn     float32 [B, Lq, H, P]     soft-maxed attention weights
+ *   ref_boxes, pts_scale: ignored (may be NULL)
+ * fused mode (flags & DFINE_MSDA_FUSED_INPUTS):
+ *   samp     samp_dtype [B, Lq, H, P, 2] raw output of the sampling_offsets Linear
+ *   attn     samp_dtype [B, Lq, H, P]    raw output of the attention_weights Linear
+ *   ref_boxes float32 [B, Lq, 4]  (cx, cy, w, h)
+ *   pts_scale float32 [P]         buffer num_points_scale (dfine_decoder.py:74-77)
+ *   offset_scale                  MSDeformableAttention.offset_scale (0.5)
+ * out        out_dtype [B, Lq, H*c]   contiguous
+ * idx_debug  optional int32 [B, Lq, H, P, 4]: flattened pixel index (lvl_start +
+ *            y*w + x) of the nw, ne, sw, se corners, -1 where the corner is out of
+ *            bounds (zero padding).  NULL to skip.
+ * -------------------------------------------------------------------------- */
+int dfine_msda_fwd(const void* value, int64_t v_stride_b, int64_t v_stride_l,
+                   const int32_t* lvl_hw, const int32_t* lvl_start, const int32_t* lvl_npts,
+                   int n_lvl, const void* samp, const void* attn, const float* ref_boxes,
+                   const float* pts_scale, float offset_scale, void* out, int32_t* idx_debug,
+                   int B, int Lq, int H, int c, int value_dtype, int samp_dtype, int out_dtype,
+                   int flags, void* stream);
+
+/* --------------------------------------------------------------------------
+ * K2  multi-scale deformable attention, backward.
+ *
+ * Replaces the autograd graph of arch/utils.py:191-264 (aten::grid_sampler_2d_backward,
+ * cat/mul/sum backward) and, in fused mode, softmax backward + the location
+ * arithmetic backward of dfine_decoder.py:144-166.
+ *
+ * grad_out    go_dtype [B, Lq, H*c] contiguous
+ * grad_value  float32  [B, L, H, c] contiguous (L = sum h_l*w_l).  The library
+ *             zero-fills it on `stream` before accumulating.
+ * grad_samp   float32  [B, Lq, H, P, 2]  d/d sampling_locations (plain) or
+ *             d/d raw offsets (fused)
+ * grad_attn   float32  [B, Lq, H, P]     d/d attention weights (plain) or
+ *             d/d raw logits (fused)
+ * No gradient is produced for ref_boxes: the reference detaches them
+ * (dfine_decoder.py:465, :514).
+ * -------------------------------------------------------------------------- */
+int dfine_msda_bwd(const void* value, int64_t v_stride_b, int64_t v_stride_l,
+                   const int32_t* lvl_hw, const int32_t* lvl_start, const int32_t* lvl_npts,
+                   int n_lvl, const void* samp, const void* attn, const float* ref_boxes,
+                   const float* pts_scale, float offset_scale, const void* grad_out,
+                   float* grad_value, float* grad_samp, float* grad_attn, int B, int Lq, int H,
+                   int c, int value_dtype, int samp_dtype, int go_dtype, int flags,
+                   void* stream);
+
+/* Packs fp32 grad_value [n] to bf16 (AMP: the gradient of a bf16 `memory`). */
+int dfine_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+
+/* --------------------------------------------------------------------------
+ * K3  FDR: weighting function, Integral and distance2bbox.
+ *
+ * dfine_fdr_project   replaces weighting_function   arch/utils.py:145-188
+ *   up, reg_scale: device float32 [1];  project: device float32 [reg_max+1]
+ * dfine_fdr_fwd       replaces Integral.forward     dfine_decoder.py:291-295
+ *                     + distance2bbox               arch/utils.py:119-142
+ *                     + box_xyxy_to_cxcywh          arch/utils.py:70-73
+ *   corners   c_dtype [N, 4*(reg_max+1)]  pred_corners
+ *   ref_init  float32 [N, 4]              ref_points_initial (cx, cy, w, h)
+ *   project   float32 [reg_max+1]         W(n) table (deploy mode caches it,
+ *                                         dfine_decoder.py:428-429)
+ *   reg_scale device float32 [1]
+ *   dist      float32 [N, 4]  optional output of Integral (NULL to skip)
+ *   boxes     float32 [N, 4]  optional cxcywh output (NULL to skip; then ref_init
+ *                             may be NULL too)
+ * dfine_fdr_bwd       gradient w.r.t. corners only (ref_init is detached,
+ *                     up / reg_scale have requires_grad=False, dfine_decoder.py:597-598)
+ *   grad_boxes float32 [N,4] or NULL;  grad_dist float32 [N,4] or NULL (added)
+ *   grad_corners float32 [N, 4*(reg_max+1)]
+ * -------------------------------------------------------------------------- */
+int dfine_fdr_project(const float* up, const float* reg_scale, float* project, int reg_max,
+                      void* stream);
+int dfine_fdr_fwd(const void* corners, int c_dtype, const float* ref_init, const float* project,
+                  const float* reg_scale, float* dist, float* boxes, int64_t N, int reg_max,
+                  void* stream);
+int dfine_fdr_bwd(const void* corners, int c_dtype, const float* ref_init, const float* project,
+                  const float* reg_scale, const float* grad_boxes, const float* grad_dist,
+                  float* grad_corners, int64_t N, int reg_max, void* stream);
+
+/* --------------------------------------------------------------------------
+ * K4  mask assembly: prototype x coefficient contraction on tcgen05 tensor cores.
+ *
+ * Replaces torch.einsum("bqc,bchw->bqhw") in DFINETransformer._mask_logits_from_h
+ * (dfine_decoder.py:937-940) and the eval-mode sigmoid (dfine_decoder.py:1041).
+ *
+ * coef   bf16 [B, M, K]   mask_embed (row-major, K contiguous)
+ * proto  bf16 [B, K, N]   mask_feat flattened over (h, w), N contiguous
+ * out    out_dtype [B, M, N]
+ * K must be a multiple of 64, N a multiple of 8; M is arbitrary.
+ * `tensormaps` is caller-owned HOST scratch of DFINE_MASK_TMAP_BYTES bytes (the
+ * library encodes its TMA descriptors there; they are passed to the kernel by
+ * value, so the scratch may be reused as soon as the call returns).
+ * -------------------------------------------------------------------------- */
+#define DFINE_MASK_TMAP_BYTES 512
+int dfine_mask_gemm_fwd(const void* coef, const void* proto, void* out, int B, int M, int K,
+                        int N, int out_dtype, int apply_sigmoid, void* tensormaps,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFINE_B200_H_ */

@@ -1,0 +1,193 @@
+"""ctypes/numpy front end of oracle/dfine_oracle.c -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module.  The product package (d-fine-seg_b200/dfine_b200) never
+does.  See the header of dfine_oracle.c for what is restated and how it is pinned.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libdfine_oracle.so")
+_lib = None
+
+_f32p = ctypes.POINTER(ctypes.c_float)
+_i32p = ctypes.POINTER(ctypes.c_int32)
+
+
+def build(force: bool = False) -> str:
+    """Compile dfine_oracle.c with the committed Makefile (gcc, -ffp-contract=off)."""
+    src = os.path.join(_HERE, "dfine_oracle.c")
+    stale = (not os.path.exists(_LIB_PATH)) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src)
+    if force or stale:
+        subprocess.run(["make", "-C", _HERE, "-s", "-B"], check=True)
+    return _LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(_LIB_PATH)
+    return _lib
+
+
+def _f(a: np.ndarray):
+    assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_f32p)
+
+
+def _i(a: np.ndarray):
+    assert a.dtype == np.int32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_i32p)
+
+
+def _c32(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+
+
+def level_tables(spatial_shapes: Sequence[Sequence[int]], num_points: Sequence[int]):
+    """(lvl_hw [n,2], lvl_start [n], lvl_npts [n]) as int32 arrays."""
+    hw = np.ascontiguousarray(np.asarray(spatial_shapes, dtype=np.int32).reshape(-1, 2))
+    sizes = hw[:, 0].astype(np.int64) * hw[:, 1]
+    start = np.ascontiguousarray(np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int32))
+    npts = np.ascontiguousarray(np.asarray(num_points, dtype=np.int32))
+    assert len(npts) == len(hw)
+    return hw, start, npts
+
+
+def msda_fwd(value, spatial_shapes, num_points, loc, attn, want_idx: bool = False):
+    """value [B,L,H,c]; loc [B,Lq,H,P,2]; attn [B,Lq,H,P] -> out [B,Lq,H*c] (, idx, wts)."""
+    value, loc, attn = _c32(value), _c32(loc), _c32(attn)
+    B, L, H, c = value.shape
+    Lq, P = loc.shape[1], loc.shape[3]
+    hw, start, npts = level_tables(spatial_shapes, num_points)
+    assert int(npts.sum()) == P and int((hw[:, 0] * hw[:, 1]).sum()) == L
+    out = np.empty((B, Lq, H * c), np.float32)
+    idx = np.empty((B, Lq, H, P, 4), np.int32) if want_idx else None
+    wts = np.empty((B, Lq, H, P, 4), np.float32) if want_idx else None
+    rc = lib().oracle_msda_fwd(_f(value), B, L, H, c, len(npts), _i(hw), _i(start), _i(npts),
+                               _f(loc), _f(attn), Lq, _f(out),
+                               _i(idx) if want_idx else None, _f(wts) if want_idx else None)
+    assert rc == 0, rc
+    return (out, idx, wts) if want_idx else out
+
+
+def msda_bwd(value, spatial_shapes, num_points, loc, attn, grad_out):
+    """-> grad_value [B,L,H,c], grad_loc [B,Lq,H,P,2], grad_attn [B,Lq,H,P]."""
+    value, loc, attn, grad_out = _c32(value), _c32(loc), _c32(attn), _c32(grad_out)
+    B, L, H, c = value.shape
+    Lq, P = loc.shape[1], loc.shape[3]
+    hw, start, npts = level_tables(spatial_shapes, num_points)
+    gv = np.empty_like(value)
+    gl = np.empty_like(loc)
+    ga = np.empty_like(attn)
+    rc = lib().oracle_msda_bwd(_f(value), B, L, H, c, len(npts), _i(hw), _i(start), _i(npts),
+                               _f(loc), _f(attn), Lq, _f(grad_out), _f(gv), _f(gl), _f(ga))
+    assert rc == 0, rc
+    return gv, gl, ga
+
+
+def msda_locations(raw, ref_boxes, pts_scale, offset_scale: float = 0.5):
+    raw, ref_boxes, pts_scale = _c32(raw), _c32(ref_boxes), _c32(pts_scale)
+    B, Lq, H, P, _ = raw.shape
+    out = np.empty_like(raw)
+    lib().oracle_msda_locations(_f(raw), _f(ref_boxes.reshape(B, Lq, 4)), _f(pts_scale),
+                                ctypes.c_float(offset_scale), B, Lq, H, P, _f(out))
+    return out
+
+
+def msda_locations_bwd(grad_loc, ref_boxes, pts_scale, offset_scale: float = 0.5):
+    grad_loc, ref_boxes, pts_scale = _c32(grad_loc), _c32(ref_boxes), _c32(pts_scale)
+    B, Lq, H, P, _ = grad_loc.shape
+    out = np.empty_like(grad_loc)
+    lib().oracle_msda_locations_bwd(_f(grad_loc), _f(ref_boxes.reshape(B, Lq, 4)), _f(pts_scale),
+                                    ctypes.c_float(offset_scale), B, Lq, H, P, _f(out))
+    return out
+
+
+def softmax(x):
+    x = _c32(x)
+    n = x.shape[-1]
+    y = np.empty_like(x)
+    lib().oracle_softmax(_f(x), ctypes.c_size_t(x.size // n), n, _f(y))
+    return y
+
+
+def softmax_bwd(y, gy):
+    y, gy = _c32(y), _c32(gy)
+    n = y.shape[-1]
+    gx = np.empty_like(y)
+    lib().oracle_softmax_bwd(_f(y), _f(gy), ctypes.c_size_t(y.size // n), n, _f(gx))
+    return gx
+
+
+def msda_fused_fwd(value, spatial_shapes, num_points, raw_offsets, raw_logits, ref_boxes,
+                   pts_scale, offset_scale: float = 0.5):
+    """MSDeformableAttention.forward minus the two Linears (dfine_decoder.py:144-176)."""
+    loc = msda_locations(raw_offsets, ref_boxes, pts_scale, offset_scale)
+    attn = softmax(raw_logits)
+    return msda_fwd(value, spatial_shapes, num_points, loc, attn)
+
+
+def msda_fused_bwd(value, spatial_shapes, num_points, raw_offsets, raw_logits, ref_boxes,
+                   pts_scale, grad_out, offset_scale: float = 0.5):
+    loc = msda_locations(raw_offsets, ref_boxes, pts_scale, offset_scale)
+    attn = softmax(raw_logits)
+    gv, gl, ga = msda_bwd(value, spatial_shapes, num_points, loc, attn, grad_out)
+    return gv, msda_locations_bwd(gl, ref_boxes, pts_scale, offset_scale), softmax_bwd(attn, ga)
+
+
+def fdr_project(up: float, reg_scale: float, reg_max: int = 32) -> np.ndarray:
+    out = np.empty(reg_max + 1, np.float32)
+    rc = lib().oracle_fdr_project(ctypes.c_float(up), ctypes.c_float(reg_scale), reg_max, _f(out))
+    assert rc == 0, rc
+    return out
+
+
+def fdr_fwd(corners, ref_init, project, reg_scale: float, reg_max: int = 32
+            ) -> Tuple[np.ndarray, np.ndarray]:
+    """-> (dist [...,4], boxes [...,4])."""
+    corners, ref_init, project = _c32(corners), _c32(ref_init), _c32(project)
+    lead = corners.shape[:-1]
+    N = int(np.prod(lead)) if lead else 1
+    dist = np.empty((N, 4), np.float32)
+    boxes = np.empty((N, 4), np.float32)
+    rc = lib().oracle_fdr_fwd(_f(corners), _f(ref_init), _f(project), ctypes.c_float(reg_scale),
+                              _f(dist), _f(boxes), ctypes.c_size_t(N), reg_max)
+    assert rc == 0, rc
+    return dist.reshape(*lead, 4), boxes.reshape(*lead, 4)
+
+
+def fdr_bwd(corners, ref_init, project, reg_scale: float, grad_boxes: Optional[np.ndarray],
+            grad_dist: Optional[np.ndarray] = None, reg_max: int = 32) -> np.ndarray:
+    corners, ref_init, project = _c32(corners), _c32(ref_init), _c32(project)
+    N = corners.size // (4 * (reg_max + 1))
+    gb = _c32(grad_boxes) if grad_boxes is not None else None
+    gd = _c32(grad_dist) if grad_dist is not None else None
+    gc = np.empty_like(corners)
+    rc = lib().oracle_fdr_bwd(_f(corners), _f(ref_init), _f(project), ctypes.c_float(reg_scale),
+                              _f(gb) if gb is not None else None,
+                              _f(gd) if gd is not None else None, _f(gc),
+                              ctypes.c_size_t(N), reg_max)
+    assert rc == 0, rc
+    return gc
+
+
+def mask_gemm(coef, proto, apply_sigmoid: bool = False) -> np.ndarray:
+    """coef [B,M,K], proto [B,K,N] (or [B,K,h,w]) -> [B,M,N] (or [B,M,h,w])."""
+    coef, proto = _c32(coef), _c32(proto)
+    B, M, K = coef.shape
+    tail = proto.shape[2:]
+    N = int(np.prod(tail))
+    out = np.empty((B, M, N), np.float32)
+    rc = lib().oracle_mask_gemm(_f(coef), _f(proto.reshape(B, K, N)), _f(out), B, M, K, N,
+                                int(apply_sigmoid))
+    assert rc == 0, rc
+    return out.reshape(B, M, *tail)

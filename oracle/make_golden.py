@@ -1,0 +1,269 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (TEST INFRASTRUCTURE).
+
+Run in the build container only (the reference tree is not shipped to the GPU box):
+
+    python oracle/make_golden.py [--ref /root/reference] [--out tests/golden]
+
+Every fixture holds the seeded inputs AND the outputs the reference produced for them
+(torch CPU, float32), so the tests never need the reference or a particular RNG.
+Tensors that feed both the fp32 and the bf16 kernels are rounded to bf16-representable
+values first, so one fixture serves both element types with identical inputs.
+
+Reference entry points exercised (all imported, nothing restated here):
+  src/d_fine/arch/utils.py:191   deformable_attention_core_func_v2
+  src/d_fine/arch/dfine_decoder.py:49   MSDeformableAttention (forward :119-178)
+  src/d_fine/arch/dfine_decoder.py:416  TransformerDecoder.value_op
+  src/d_fine/arch/utils.py:145   weighting_function
+  src/d_fine/arch/dfine_decoder.py:274  Integral
+  src/d_fine/arch/utils.py:119   distance2bbox
+  src/d_fine/arch/dfine_decoder.py:937  DFINETransformer._mask_logits_from_h
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+
+def bf16r(t: torch.Tensor) -> torch.Tensor:
+    """Round to the nearest bf16-representable float32."""
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def make_boxes(g: torch.Generator, B: int, Lq: int) -> torch.Tensor:
+    """Object-like cxcywh boxes plus ~10 % border / oversize boxes."""
+    cxy = torch.rand(B, Lq, 2, generator=g) * 0.9 + 0.05
+    wh = torch.exp(torch.rand(B, Lq, 2, generator=g) * (np.log(0.6) - np.log(0.02)) + np.log(0.02))
+    big = torch.rand(B, Lq, 1, generator=g) < 0.10
+    wh_big = torch.rand(B, Lq, 2, generator=g) * 0.6 + 0.6
+    cxy_edge = torch.rand(B, Lq, 2, generator=g) * 1.2 - 0.1
+    wh = torch.where(big, wh_big, wh)
+    cxy = torch.where(big, cxy_edge, cxy)
+    return torch.cat([cxy, wh], -1)
+
+
+def ref_value_views(TransformerDecoder, memory: torch.Tensor, H: int, shapes):
+    stub = types.SimpleNamespace(num_head=H)
+    return TransformerDecoder.value_op(stub, memory, None, None, None, shapes)
+
+
+def case_core(ref, name, seed, B, Lq, H, c, shapes, npts, loc_override=None, attn_override=None):
+    """deformable_attention_core_func_v2 forward + all three gradients."""
+    g = torch.Generator().manual_seed(seed)
+    L = sum(h * w for h, w in shapes)
+    P = sum(npts)
+    memory = bf16r(torch.randn(B, L, H * c, generator=g)).requires_grad_(True)
+    if loc_override is None:
+        boxes = make_boxes(g, B, Lq)
+        off = torch.randn(B, Lq, H, P, 2, generator=g) * 0.6
+        loc = boxes[:, :, None, None, :2] + off * boxes[:, :, None, None, 2:] * 0.5
+    else:
+        loc = loc_override
+    loc = loc.clone().requires_grad_(True)
+    if attn_override is None:
+        attn = torch.softmax(torch.randn(B, Lq, H, P, generator=g) * 1.5, -1)
+    else:
+        attn = attn_override
+    attn = attn.clone().requires_grad_(True)
+    grad_out = bf16r(torch.randn(B, Lq, H * c, generator=g))
+
+    value = ref_value_views(ref.TransformerDecoder, memory, H, shapes)
+    out = ref.core(value, shapes, loc, attn, npts)
+    assert out.shape == (B, Lq, H * c)
+    out.backward(grad_out)
+    return name, dict(
+        memory_bf16=memory.detach().to(torch.bfloat16).view(torch.int16).numpy(),
+        loc=loc.detach().numpy(), attn=attn.detach().numpy(),
+        grad_out_bf16=grad_out.to(torch.bfloat16).view(torch.int16).numpy(),
+        shapes=np.asarray(shapes, np.int32), npts=np.asarray(npts, np.int32),
+        H=np.int32(H), c=np.int32(c),
+        out=out.detach().contiguous().numpy(),
+        grad_memory=memory.grad.numpy(), grad_loc=loc.grad.numpy(), grad_attn=attn.grad.numpy(),
+    )
+
+
+def case_edge(ref):
+    """Engineered positions: pixel centres, half-pixel borders, far outside, NaN / inf."""
+    shapes, npts, H, c = [[5, 7], [3, 4]], [4, 4], 2, 16
+    vals = []
+    for (h, w) in shapes:
+        xs = [(k + 0.5) / w for k in range(-1, w + 1)] + [0.0, 1.0, -1.0 / w, 1.0 + 1.0 / w,
+                                                          0.5 / w * 0.999999, 1e-8, 1 - 1e-8]
+        ys = [(k + 0.5) / h for k in range(-1, h + 1)] + [0.0, 1.0, 0.5, 0.25]
+        vals.append((xs, ys))
+    pts = []
+    for xs, ys in vals:
+        lv = [(x, y) for x in xs for y in ys]
+        pts.append(lv)
+    n = max(len(p) for p in pts)
+    Lq = (n + 3) // 4 + 2
+    loc = torch.full((1, Lq, H, 8, 2), 0.5)
+    for lvl, lv in enumerate(pts):
+        for i, (x, y) in enumerate(lv):
+            q, p = divmod(i, 4)
+            loc[0, q, :, lvl * 4 + p, 0] = x
+            loc[0, q, :, lvl * 4 + p, 1] = y
+    special = torch.tensor([[float("nan"), 0.5], [0.5, float("inf")], [-float("inf"), 0.5],
+                            [1e30, 0.5], [0.5, -1e30], [3.0, 3.0], [-2.0, 0.5], [0.5, 2.5]])
+    loc[0, Lq - 2, 0, :, :] = special
+    loc[0, Lq - 1, 1, :, :] = special.flip(0)
+    g = torch.Generator().manual_seed(77)
+    attn = torch.softmax(torch.randn(1, Lq, H, 8, generator=g), -1)
+    attn[0, 0, 0] = 0.0
+    attn[0, 0, 0, 3] = 1.0  # one-hot attention
+    # Only the forward is pinned for the NaN/inf rows: autograd through NaN positions
+    # yields NaN gradients in the reference, checked separately by the finite mask.
+    return case_core(ref, "core_edge", 5, 1, Lq, H, c, shapes, npts, loc_override=loc,
+                     attn_override=attn)
+
+
+def case_probe(ref):
+    """Which pixels does aten::grid_sampler_2d touch?  One sample per (image, head):
+    the non-zeros of grad_input are the in-bounds corners, their values the weights."""
+    h, w = 6, 9
+    g = torch.Generator().manual_seed(9)
+    xs = [(k + 0.5) / w for k in range(-2, w + 2)] + [k / w for k in range(-1, w + 2)]
+    ys = [(k + 0.5) / h for k in range(-2, h + 2)] + [k / h for k in range(-1, h + 2)]
+    eng = torch.tensor([(x, y) for x in xs for y in ys], dtype=torch.float32)
+    rnd = torch.rand(400, 2, generator=g) * 1.3 - 0.15
+    loc = torch.cat([eng, rnd], 0)
+    n = loc.shape[0]
+    inp = torch.ones(n, 1, h, w, requires_grad=True)
+    grid = (2 * loc - 1).reshape(n, 1, 1, 2)
+    out = torch.nn.functional.grid_sample(inp, grid, mode="bilinear", padding_mode="zeros",
+                                          align_corners=False)
+    out.sum().backward()
+    return "aten_corner_probe", dict(loc=loc.numpy(), hw=np.asarray([h, w], np.int32),
+                                     grad_input=inp.grad.reshape(n, h * w).numpy(),
+                                     out=out.detach().reshape(n).numpy())
+
+
+def case_module(ref, name, seed, B, Lq, C, H, shapes, npts):
+    """MSDeformableAttention.forward with trained-like Linear weights; grads wrt
+    query, memory and the four Linear parameters.  Also records the raw Linear
+    outputs so that the fused kernel can be checked without the module."""
+    torch.manual_seed(seed)
+    g = torch.Generator().manual_seed(seed)
+    m = ref.MSDeformableAttention(C, H, len(shapes), npts)
+    with torch.no_grad():
+        m.sampling_offsets.weight.copy_(bf16r(torch.randn(m.sampling_offsets.weight.shape, generator=g) * 0.02))
+        m.attention_weights.weight.copy_(bf16r(torch.randn(m.attention_weights.weight.shape, generator=g) * 0.05))
+        m.attention_weights.bias.copy_(bf16r(torch.randn(m.attention_weights.bias.shape, generator=g) * 0.1))
+        m.sampling_offsets.bias.copy_(bf16r(m.sampling_offsets.bias))
+    L = sum(h * w for h, w in shapes)
+    P = sum(npts)
+    memory = bf16r(torch.randn(B, L, C, generator=g)).requires_grad_(True)
+    query = bf16r(torch.randn(B, Lq, C, generator=g)).requires_grad_(True)
+    ref_pts = make_boxes(g, B, Lq).unsqueeze(2)  # [B, Lq, 1, 4]
+    grad_out = bf16r(torch.randn(B, Lq, C, generator=g))
+    value = ref_value_views(ref.TransformerDecoder, memory, H, shapes)
+    assert not value[0].is_contiguous()
+    out = m(query, ref_pts, value, shapes)
+    out.backward(grad_out)
+    with torch.no_grad():
+        raw_off = m.sampling_offsets(query).reshape(B, Lq, H, P, 2)
+        raw_logit = m.attention_weights(query).reshape(B, Lq, H, P)
+    return name, dict(
+        memory_bf16=memory.detach().to(torch.bfloat16).view(torch.int16).numpy(),
+        query=query.detach().numpy(), ref_points=ref_pts.numpy(),
+        grad_out_bf16=grad_out.to(torch.bfloat16).view(torch.int16).numpy(),
+        shapes=np.asarray(shapes, np.int32), npts=np.asarray(npts, np.int32), H=np.int32(H),
+        so_w=m.sampling_offsets.weight.detach().numpy(), so_b=m.sampling_offsets.bias.detach().numpy(),
+        aw_w=m.attention_weights.weight.detach().numpy(), aw_b=m.attention_weights.bias.detach().numpy(),
+        num_points_scale=m.num_points_scale.numpy(), offset_scale=np.float32(m.offset_scale),
+        raw_off=raw_off.numpy(), raw_logit=raw_logit.numpy(),
+        out=out.detach().contiguous().numpy(), grad_memory=memory.grad.numpy(),
+        grad_query=query.grad.numpy(),
+        g_so_w=m.sampling_offsets.weight.grad.numpy(), g_so_b=m.sampling_offsets.bias.grad.numpy(),
+        g_aw_w=m.attention_weights.weight.grad.numpy(), g_aw_b=m.attention_weights.bias.grad.numpy(),
+        state_dict_keys=np.asarray(sorted(m.state_dict().keys())),
+    )
+
+
+def case_fdr(ref):
+    g = torch.Generator().manual_seed(21)
+    out = {}
+    for tag, (up, rs) in {"m": (0.5, 4.0), "x": (0.5, 8.0), "odd": (-0.37, 5.5)}.items():
+        upt, rst = torch.tensor([up]), torch.tensor([rs])
+        out[f"project_{tag}"] = ref.weighting_function(32, upt, rst).numpy()
+        out[f"project_deploy_{tag}"] = ref.weighting_function(32, upt, rst, deploy=True).numpy()
+        out[f"up_rs_{tag}"] = np.asarray([up, rs], np.float32)
+    reg_max, N = 32, 96
+    corners = (torch.randn(2, N // 2, 4 * (reg_max + 1), generator=g) * 3.0)
+    corners[0, 0] = 0.0            # uniform distribution
+    corners[0, 1, :33] = 80.0      # overflow-prone logits
+    corners[0, 2, 5] = 60.0        # one-hot
+    corners = bf16r(corners).requires_grad_(True)
+    ref_init = make_boxes(g, 2, N // 2)
+    project = ref.weighting_function(reg_max, torch.tensor([0.5]), torch.tensor([4.0]))
+    integral = ref.Integral(reg_max)
+    dist = integral(corners, project)
+    boxes = ref.distance2bbox(ref_init, dist, torch.tensor([4.0]))
+    gb = torch.randn(boxes.shape, generator=g)
+    gd = torch.randn(dist.shape, generator=g)
+    (boxes * gb).sum().backward(retain_graph=True)
+    g_from_boxes = corners.grad.clone()
+    corners.grad = None
+    ((boxes * gb).sum() + (dist * gd).sum()).backward()
+    out.update(corners=corners.detach().numpy(), ref_init=ref_init.numpy(),
+               project=project.numpy(), reg_scale=np.float32(4.0), dist=dist.detach().numpy(),
+               boxes=boxes.detach().numpy(), grad_boxes=gb.numpy(), grad_dist=gd.numpy(),
+               grad_corners_from_boxes=g_from_boxes.numpy(),
+               grad_corners_from_both=corners.grad.numpy())
+    return "fdr", out
+
+
+def case_mask(ref):
+    g = torch.Generator().manual_seed(31)
+    B, Q, C, Hm, Wm = 2, 37, 64, 12, 20
+    h = bf16r(torch.randn(B, Q, C, generator=g))
+    feat = bf16r(torch.randn(B, C, Hm, Wm, generator=g))
+    stub = types.SimpleNamespace(mask_head=torch.nn.Identity())
+    logits = ref.DFINETransformer._mask_logits_from_h(stub, h, feat)
+    return "mask", dict(coef=h.numpy(), proto=feat.numpy(), logits=logits.numpy(),
+                        probs=torch.sigmoid(logits).numpy())
+
+
+def load_reference(path: str):
+    sys.path.insert(0, path)
+    from src.d_fine.arch import dfine_decoder as dd  # noqa: E402
+    from src.d_fine.arch import utils as au  # noqa: E402
+    return types.SimpleNamespace(
+        core=au.deformable_attention_core_func_v2, weighting_function=au.weighting_function,
+        distance2bbox=au.distance2bbox, MSDeformableAttention=dd.MSDeformableAttention,
+        Integral=dd.Integral, TransformerDecoder=dd.TransformerDecoder,
+        DFINETransformer=dd.DFINETransformer)
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--ref", default="/root/reference")
+    ap.add_argument("--out", default=os.path.join(os.path.dirname(__file__), "..", "tests", "golden"))
+    a = ap.parse_args()
+    torch.set_num_threads(1)
+    torch.use_deterministic_algorithms(True)
+    ref = load_reference(a.ref)
+    os.makedirs(a.out, exist_ok=True)
+    cases = [
+        case_core(ref, "core_m_small", 1, 2, 40, 8, 32, [[12, 16], [6, 8], [3, 4]], [3, 6, 3]),
+        case_core(ref, "core_n_small", 2, 1, 30, 8, 16, [[10, 10], [5, 5]], [6, 6]),
+        case_core(ref, "core_x444", 3, 1, 20, 8, 32, [[16, 16], [8, 8], [4, 4]], [4, 4, 4]),
+        case_edge(ref),
+        case_probe(ref),
+        case_module(ref, "module_m_small", 11, 2, 33, 256, 8, [[12, 16], [6, 8], [3, 4]], [3, 6, 3]),
+        case_module(ref, "module_n_small", 12, 1, 21, 128, 8, [[10, 12], [5, 6]], [6, 6]),
+        case_fdr(ref),
+        case_mask(ref),
+    ]
+    for name, arrs in cases:
+        p = os.path.join(a.out, name + ".npz")
+        np.savez_compressed(p, **arrs)
+        print(f"{name}: {os.path.getsize(p) / 1024:.0f} KiB")
+
+
+if __name__ == "__main__":
+    main()

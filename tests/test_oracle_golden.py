@@ -1,0 +1,120 @@
+"""Pins the CPU oracle (oracle/dfine_oracle.c) to outputs of the unmodified reference.
+
+The fixtures under tests/golden/ were produced by oracle/make_golden.py, which imports
+the reference (src/d_fine/arch/{utils,dfine_decoder}.py) and runs it on seeded inputs.
+"""
+import numpy as np
+import pytest
+
+from oracle import cpu_oracle as O
+from util import FP32_RTOL, assert_close, bf16_bits_to_f32, golden
+
+CORE_CASES = ["core_m_small", "core_n_small", "core_x444", "core_edge"]
+
+
+def _core_inputs(g):
+    H, c = int(g["H"]), int(g["c"])
+    mem = bf16_bits_to_f32(g["memory_bf16"])
+    B, L, C = mem.shape
+    return mem.reshape(B, L, H, c), bf16_bits_to_f32(g["grad_out_bf16"])
+
+
+@pytest.mark.parametrize("name", CORE_CASES)
+def test_core_forward_matches_reference(name):
+    # reference: deformable_attention_core_func_v2, arch/utils.py:191-264
+    g = golden(name)
+    value, _ = _core_inputs(g)
+    out = O.msda_fwd(value, g["shapes"], g["npts"], g["loc"], g["attn"])
+    assert_close(out, g["out"], FP32_RTOL, "out")
+
+
+@pytest.mark.parametrize("name", CORE_CASES)
+def test_core_backward_matches_reference(name):
+    g = golden(name)
+    value, go = _core_inputs(g)
+    gv, gl, ga = O.msda_bwd(value, g["shapes"], g["npts"], g["loc"], g["attn"], go)
+    assert_close(gv.reshape(g["grad_memory"].shape), g["grad_memory"], FP32_RTOL, "grad_value")
+    assert_close(gl, g["grad_loc"], FP32_RTOL, "grad_loc")
+    assert_close(ga, g["grad_attn"], FP32_RTOL, "grad_attn")
+
+
+def test_corner_indices_match_aten_probe():
+    """The pixels aten::grid_sampler_2d touches (non-zeros of grad_input for an all-ones
+    map, one sample per image) must be exactly the oracle's in-bounds corners, with the
+    same weights.  Zero-weight corners are invisible to the probe and are skipped."""
+    g = golden("aten_corner_probe")
+    h, w = [int(v) for v in g["hw"]]
+    loc = g["loc"]
+    n = loc.shape[0]
+    value = np.ones((1, h * w, 1, 1), np.float32)
+    attn = np.ones((1, n, 1, 1), np.float32)
+    out, idx, wts = O.msda_fwd(value, [[h, w]], [1], loc.reshape(1, n, 1, 1, 2), attn, want_idx=True)
+    idx, wts = idx.reshape(n, 4), wts.reshape(n, 4)
+    dense = np.zeros((n, h * w), np.float32)
+    for j in range(4):
+        ok = idx[:, j] >= 0
+        np.add.at(dense, (np.nonzero(ok)[0], idx[ok, j]), wts[ok, j])
+    ref = g["grad_input"]
+    assert np.array_equal(dense != 0, ref != 0), "touched-pixel sets differ from ATen"
+    assert np.abs(dense - ref).max() <= 1e-6
+    assert_close(out.reshape(n), g["out"], FP32_RTOL, "probe out")
+
+
+@pytest.mark.parametrize("name", ["module_m_small", "module_n_small"])
+def test_fused_module_matches_reference(name):
+    # reference: MSDeformableAttention.forward, dfine_decoder.py:119-178
+    g = golden(name)
+    H = int(g["H"])
+    mem = bf16_bits_to_f32(g["memory_bf16"])
+    B, L, C = mem.shape
+    value = mem.reshape(B, L, H, C // H)
+    out = O.msda_fused_fwd(value, g["shapes"], g["npts"], g["raw_off"], g["raw_logit"],
+                           g["ref_points"], g["num_points_scale"], float(g["offset_scale"]))
+    assert_close(out, g["out"], FP32_RTOL, "module out")
+    go = bf16_bits_to_f32(g["grad_out_bf16"])
+    gv, g_off, g_logit = O.msda_fused_bwd(value, g["shapes"], g["npts"], g["raw_off"],
+                                          g["raw_logit"], g["ref_points"],
+                                          g["num_points_scale"], go, float(g["offset_scale"]))
+    assert_close(gv.reshape(B, L, C), g["grad_memory"], FP32_RTOL, "grad_memory")
+    # push the raw-output gradients through the two Linears (plain matmuls) and compare
+    # with the parameter / query gradients autograd produced in the reference
+    q = g["query"].reshape(-1, C).astype(np.float64)
+    g_off2 = g_off.reshape(q.shape[0], -1).astype(np.float64)
+    g_log2 = g_logit.reshape(q.shape[0], -1).astype(np.float64)
+    assert_close(g_off2.T @ q, g["g_so_w"], 2e-5, "grad sampling_offsets.weight")
+    assert_close(g_off2.sum(0), g["g_so_b"], 2e-5, "grad sampling_offsets.bias")
+    assert_close(g_log2.T @ q, g["g_aw_w"], 2e-5, "grad attention_weights.weight")
+    assert_close(g_log2.sum(0), g["g_aw_b"], 2e-5, "grad attention_weights.bias")
+    gq = g_off2 @ g["so_w"].astype(np.float64) + g_log2 @ g["aw_w"].astype(np.float64)
+    assert_close(gq.reshape(g["grad_query"].shape), g["grad_query"], 2e-5, "grad_query")
+
+
+@pytest.mark.parametrize("tag", ["m", "x", "odd"])
+def test_weighting_function(tag):
+    # reference: weighting_function, arch/utils.py:145-188 (both deploy modes)
+    g = golden("fdr")
+    up, rs = [float(v) for v in g[f"up_rs_{tag}"]]
+    proj = O.fdr_project(up, rs, 32)
+    assert_close(proj, g[f"project_{tag}"], FP32_RTOL, "project")
+    assert_close(proj, g[f"project_deploy_{tag}"], FP32_RTOL, "project deploy")
+    assert proj[16] == 0.0 and proj.shape == (33,)
+
+
+def test_fdr_forward_backward():
+    # reference: Integral.forward dfine_decoder.py:291-295, distance2bbox arch/utils.py:119-142
+    g = golden("fdr")
+    dist, boxes = O.fdr_fwd(g["corners"], g["ref_init"], g["project"], float(g["reg_scale"]))
+    assert_close(dist, g["dist"], FP32_RTOL, "dist")
+    assert_close(boxes, g["boxes"], FP32_RTOL, "boxes")
+    gc = O.fdr_bwd(g["corners"], g["ref_init"], g["project"], float(g["reg_scale"]), g["grad_boxes"])
+    assert_close(gc.reshape(g["corners"].shape), g["grad_corners_from_boxes"], FP32_RTOL, "gc boxes")
+    gc = O.fdr_bwd(g["corners"], g["ref_init"], g["project"], float(g["reg_scale"]),
+                   g["grad_boxes"], g["grad_dist"])
+    assert_close(gc.reshape(g["corners"].shape), g["grad_corners_from_both"], FP32_RTOL, "gc both")
+
+
+def test_mask_assembly():
+    # reference: DFINETransformer._mask_logits_from_h, dfine_decoder.py:937-940 (+ :1041)
+    g = golden("mask")
+    assert_close(O.mask_gemm(g["coef"], g["proto"]), g["logits"], FP32_RTOL, "logits")
+    assert_close(O.mask_gemm(g["coef"], g["proto"], True), g["probs"], FP32_RTOL, "probs")
