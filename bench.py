@@ -1,0 +1,471 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native D-FINE-seg decoder hot path.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun)
+    python bench.py --impl reference ...                      (CPU arm: the reference's torch path)
+
+A "step" is one pass of the hot path over one batch of synthetic input at BASELINE.json's
+config 3 (D-FINE-m, 640x640, batch 32 per GPU, bf16 autocast, Lq = 300 + 200 denoising
+queries): for each of the 4 decoder layers MSDeformableAttention forward (2 Linears + fused
+sampling kernel) and the FDR box decode, then the backward of all of it (gradients to
+`memory`, the queries, the Linear parameters and pred_corners).  `value` is whole-job
+images/s with inputs resident in HBM; `e2e` is the same step with every input copied from
+pinned host memory and the decoded boxes read back inside the timed region.
+
+The reference arm and `cpu_baseline` time oracle/torch_port.py -- the reference's own
+PyTorch (ATen grid_sample) call sequence -- on the host cores; they are the only places this
+file touches oracle/.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "d-fine-seg_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+METRIC = "D-FINE-m 640x640 train imgs/s through the decoder hot path (MSDeformAttn fwd+bwd + FDR)"
+UNIT = "imgs/s"
+
+WORKLOADS = {
+    # BASELINE.json configs[2]: D-FINE-m detection training, 640x640, batch 32 / GPU
+    "dfine_m_train_640_b32": dict(B=32, Lq=500, C=256, H=8, shapes=[[80, 80], [40, 40], [20, 20]],
+                                  npts=[3, 6, 3], layers=4, reg_max=32, up=0.5, reg_scale=4.0),
+}
+DEFAULT_WORKLOAD = "dfine_m_train_640_b32"
+
+
+# ------------------------------------------------------------------------------------------
+# synthetic inputs: object-like boxes + 10 % border / oversize boxes,
+# "trained-like" Linear weights on top of the reference's directional bias init
+# ------------------------------------------------------------------------------------------
+def make_inputs(wl: dict, B: int, seed: int, device: str):
+    g = torch.Generator().manual_seed(seed)
+    Lq, C, H, layers = wl["Lq"], wl["C"], wl["H"], wl["layers"]
+    L = sum(h * w for h, w in wl["shapes"])
+    P = sum(wl["npts"])
+
+    def boxes():
+        cxy = torch.rand(B, Lq, 2, generator=g) * 0.9 + 0.05
+        wh = torch.exp(torch.rand(B, Lq, 2, generator=g) * 3.4 - 3.9)  # logU(0.02, 0.6)
+        big = torch.rand(B, Lq, 1, generator=g) < 0.10
+        wh = torch.where(big, torch.rand(B, Lq, 2, generator=g) * 0.6 + 0.6, wh)
+        cxy = torch.where(big, torch.rand(B, Lq, 2, generator=g) * 1.2 - 0.1, cxy)
+        return torch.cat([cxy, wh], -1)
+
+    inp = dict(
+        memory=torch.randn(B, L, C, generator=g),
+        queries=[torch.randn(B, Lq, C, generator=g) for _ in range(layers)],
+        refs=[boxes().unsqueeze(2) for _ in range(layers)],
+        corners=[torch.randn(B, Lq, 4 * (wl["reg_max"] + 1), generator=g) * 2 for _ in range(layers)],
+        ref_init=boxes(),
+        grad_outs=[torch.randn(B, Lq, C, generator=g) for _ in range(layers)],
+        grad_boxes=[torch.randn(B, Lq, 4, generator=g) for _ in range(layers)],
+    )
+    lin = []
+    for _ in range(layers):
+        lin.append(dict(so_w=torch.randn(H * P * 2, C, generator=g) * 0.02,
+                        aw_w=torch.randn(H * P, C, generator=g) * 0.02,
+                        aw_b=torch.randn(H * P, generator=g) * 0.1))
+    inp["lin"] = lin
+    return inp
+
+
+def algorithmic_bytes(wl: dict, B: int):
+    """SURVEY.md section 8(d), per decoder layer, bf16 value / fp32 out / fp32 grad_value."""
+    L = sum(h * w for h, w in wl["shapes"])
+    P = sum(wl["npts"])
+    blc, samples, bqc = B * L * wl["C"], B * wl["Lq"] * wl["H"] * P, B * wl["Lq"] * wl["C"]
+    e_v, e_o, e_g = 2, 4, 4
+    fwd = blc * e_v + samples * 12 + bqc * e_o
+    bwd = bqc * e_o + blc * e_v + samples * 12 + blc * e_g + samples * 12
+    return fwd, bwd
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+class HotPath:
+    """The patched decoder hot path over one batch, driven through the package's public API."""
+
+    def __init__(self, wl: dict, inp: dict, device: torch.device):
+        import dfine_b200
+        self.api = dfine_b200
+        self.wl, self.dev = wl, device
+        self.mods = []
+        for lw in inp["lin"]:
+            m = dfine_b200.MSDeformableAttention(wl["C"], wl["H"], len(wl["shapes"]), wl["npts"])
+            with torch.no_grad():
+                m.sampling_offsets.weight.copy_(lw["so_w"])
+                m.attention_weights.weight.copy_(lw["aw_w"])
+                m.attention_weights.bias.copy_(lw["aw_b"])
+            self.mods.append(m.to(device))
+        self.up = torch.tensor([wl["up"]], device=device)
+        self.reg_scale = torch.tensor([wl["reg_scale"]], device=device)
+        self.host = None
+        self.d = None
+
+    def load_device(self, inp: dict):
+        dev = self.dev
+        self.d = dict(
+            memory=inp["memory"].to(dev, torch.bfloat16),
+            queries=[q.to(dev) for q in inp["queries"]],
+            refs=[r.to(dev) for r in inp["refs"]],
+            corners=[c.to(dev, torch.bfloat16) for c in inp["corners"]],
+            ref_init=inp["ref_init"].to(dev),
+            grad_outs=[g.to(dev) for g in inp["grad_outs"]],
+            grad_boxes=[g.to(dev) for g in inp["grad_boxes"]],
+        )
+
+    def pin_host(self, inp: dict):
+        def pin(t, dt=None):
+            t = t.to(dt) if dt is not None else t
+            return t.contiguous().pin_memory()
+        self.host = dict(
+            memory=pin(inp["memory"], torch.bfloat16),
+            queries=[pin(q) for q in inp["queries"]],
+            refs=[pin(r) for r in inp["refs"]],
+            corners=[pin(c, torch.bfloat16) for c in inp["corners"]],
+            ref_init=pin(inp["ref_init"]),
+            grad_outs=[pin(g) for g in inp["grad_outs"]],
+            grad_boxes=[pin(g) for g in inp["grad_boxes"]],
+        )
+        self.h2d_bytes = sum(t.numel() * t.element_size() for v in self.host.values()
+                             for t in (v if isinstance(v, list) else [v]))
+        L = len(inp["queries"])
+        self.boxes_host = torch.empty((L, *inp["grad_boxes"][0].shape), dtype=torch.float32).pin_memory()
+        self.d2h_bytes = self.boxes_host.numel() * 4
+
+    def step(self, d: dict):
+        wl = self.wl
+        mem = d["memory"].detach().requires_grad_(True)
+        queries = [q.detach().requires_grad_(True) for q in d["queries"]]
+        corners = [c.detach().requires_grad_(True) for c in d["corners"]]
+        for m in self.mods:
+            m.zero_grad(set_to_none=True)
+        outs, boxes = [], []
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            project = self.api.fdr_project(self.up, self.reg_scale, wl["reg_max"])
+            # TransformerDecoder.value_op: per-level strided views of `memory` (zero copy)
+            B, L, C = mem.shape
+            value = mem.reshape(B, L, wl["H"], C // wl["H"]).permute(0, 2, 3, 1).split(
+                [h * w for h, w in wl["shapes"]], dim=-1)
+            for i, m in enumerate(self.mods):
+                outs.append(m(queries[i], d["refs"][i], value, wl["shapes"]))
+                boxes.append(self.api.fdr_decode(corners[i], d["ref_init"], project, self.reg_scale,
+                                                 wl["reg_max"]))
+        torch.autograd.backward(outs + boxes, d["grad_outs"] + d["grad_boxes"])
+        return boxes, mem.grad
+
+    def step_e2e(self):
+        dev = self.dev
+        d = {k: ([t.to(dev, non_blocking=True) for t in v] if isinstance(v, list)
+                 else v.to(dev, non_blocking=True)) for k, v in self.host.items()}
+        boxes, _ = self.step(d)
+        self.boxes_host.copy_(torch.stack(boxes), non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return self.boxes_host
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-i", str(gpu_index), "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.f.name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def rank_seed(rank: int) -> int:
+    """Per-rank synthetic batch (the reference seeds 42 + rank, src/dl/train.py:131)."""
+    return 42 + rank
+
+
+def max_over_ranks(ms: float, device, dist_on: bool) -> float:
+    """Step time of the job = the slowest rank's device time."""
+    if not dist_on:
+        return ms
+    import torch.distributed as dist
+    t = torch.tensor([ms], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def job_throughput(images_per_gpu: int, world: int, steps: int, ms: float) -> float:
+    """Whole-job images/s: every rank processes its own shard of the batch (weak scaling)."""
+    return images_per_gpu * world * steps / (ms / 1e3)
+
+
+def time_steps(fn, steps: int, warmup: int, device, dist_on: bool):
+    import torch.distributed as dist
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize(device)
+    if dist_on:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    s = torch.cuda.Event(enable_timing=True)
+    e = torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(steps):
+        fn()
+    e.record()
+    torch.cuda.synchronize(device)
+    if dist_on:
+        dist.barrier()
+    return max_over_ranks(s.elapsed_time(e), device, dist_on)
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm: the reference's torch path (oracle/torch_port.py), bounded sample
+# ------------------------------------------------------------------------------------------
+def cpu_reference_run(wl: dict, sample_b: int, steps: int, warmup: int, seed: int = 42):
+    from oracle import torch_port as TP  # the only use of oracle/ in this file
+    inp = make_inputs(wl, sample_b, seed, "cpu")
+    H, P = wl["H"], sum(wl["npts"])
+    nps = torch.tensor([1.0 / n for n in wl["npts"] for _ in range(n)])
+    ang = torch.arange(H, dtype=torch.float32) * (2.0 * torch.pi / H)
+    dirs = torch.stack([ang.cos(), ang.sin()], -1)
+    dirs = dirs / dirs.abs().max(-1, keepdim=True).values
+    rank = torch.cat([torch.arange(1, n + 1) for n in wl["npts"]]).float()
+    so_b = (dirs[:, None, :] * rank[None, :, None]).reshape(-1)
+    up, rs = torch.tensor([wl["up"]]), torch.tensor([wl["reg_scale"]])
+
+    lins = [(*(t.detach().requires_grad_(True) for t in (lw["so_w"], so_b, lw["aw_w"], lw["aw_b"])), nps)
+            for lw in inp["lin"]]
+
+    def step():
+        for t in (x for lin in lins for x in lin[:4]):
+            t.grad = None
+        TP.hot_path_step(inp["memory"], inp["queries"], inp["refs"], lins, wl["shapes"], wl["npts"], H,
+                         inp["corners"], inp["ref_init"], up, rs, inp["grad_outs"], inp["grad_boxes"],
+                         train=True)
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return sample_b * steps / dt, dt / steps * 1e3
+
+
+def run_reference_arm(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = torch.get_num_threads()
+    sample_b = args.cpu_sample
+    v, ms = cpu_reference_run(wl, sample_b, args.steps, args.warmup)
+    sample = (f"{sample_b} of {wl['B']} images per step, {args.steps} steps, fp32, torch "
+              f"{torch.__version__} CPU, reference call sequence restated in oracle/torch_port.py")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "sample_images_per_step": sample_b, "device": "cpu"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-sample", type=int, default=4, help="images per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager", action="store_true", help="skip the eager-PyTorch GPU bar")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        run_reference_arm(args, wl)
+        return
+
+    import dfine_b200
+    from dfine_b200 import ops
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    dist_on = world > 1
+    if dist_on:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    dfine_b200._lib.lib()  # fail loudly if the extension is missing
+
+    inp = make_inputs(wl, wl["B"], rank_seed(rank), "cpu")
+    hp = HotPath(wl, inp, device)
+    hp.load_device(inp)
+    hp.pin_host(inp)
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    # ---- device-resident timing (value) with per-kernel CUDA-event brackets ----
+    ops.enable_kernel_timers(False)
+    for _ in range(args.warmup):
+        hp.step(hp.d)
+    ops.enable_kernel_timers(True)
+    l0 = ops.LAUNCHES["count"]
+    ms = time_steps(lambda: hp.step(hp.d), args.steps, 0, device, dist_on)
+    launches = ops.LAUNCHES["count"] - l0
+    timers = ops.kernel_timers()
+    kernel_ms = {k: sum(s.elapsed_time(e) for s, e in v) / len(v) for k, v in timers.items()}
+    kernel_calls = {k: len(v) // args.steps for k, v in timers.items()}
+    ops.enable_kernel_timers(False)
+    # ---- end-to-end timing (host buffers, H2D + D2H inside the timed region) ----
+    ms_e2e = time_steps(hp.step_e2e, args.steps, args.warmup, device, dist_on)
+    clocks = sampler.stop() if sampler else None
+
+    value = job_throughput(wl["B"], world, args.steps, ms)
+    e2e = job_throughput(wl["B"], world, args.steps, ms_e2e)
+
+    if rank != 0:
+        if dist_on:
+            torch.distributed.destroy_process_group()
+        return
+
+    peak, peak_src = load_peaks()
+    fwd_b, bwd_b = algorithmic_bytes(wl, wl["B"])
+    dom = "msda_bwd" if kernel_ms.get("msda_bwd", 0) >= kernel_ms.get("msda_fwd", 0) else "msda_fwd"
+    dom_bytes = bwd_b if dom == "msda_bwd" else fwd_b
+    achieved = dom_bytes / (kernel_ms[dom] / 1e3) / 1e9
+    fb_ms = kernel_ms.get("msda_fwd", 0) + kernel_ms.get("msda_bwd", 0) + kernel_ms.get("cast_bf16", 0)
+    roofline = {
+        "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": kernel_ms[dom],
+        "msda_fwd_bwd": {"algorithmic_bytes": fwd_b + bwd_b, "ms": fb_ms,
+                         "achieved": (fwd_b + bwd_b) / (fb_ms / 1e3) / 1e9,
+                         "frac": (fwd_b + bwd_b) / (fb_ms / 1e3) / 1e9 / peak,
+                         "note": "fwd + (memset + bwd) + fp32->bf16 grad cast, per decoder layer"},
+        "kernel_ms": kernel_ms, "kernel_calls_per_step": kernel_calls,
+    }
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": args.workload, "images_per_gpu": wl["B"], "queries": wl["Lq"],
+                   "levels": wl["shapes"], "points": wl["npts"], "decoder_layers": wl["layers"],
+                   "value_dtype": "bf16", "accumulate": "f32",
+                   "l2_policy": "inputs_larger_than_l2 (memory 137.6 MB + 275 MB fp32 grad per layer)",
+                   "parallelism": f"dp{world} (batch-sharded, no data-path collective)"},
+        "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": hp.h2d_bytes, "d2h_bytes_per_step": hp.d2h_bytes},
+        "gpu_launches": launches, "roofline": roofline, "clocks": clocks,
+    }
+
+    if world == 1 and not args.no_eager:
+        # informational: the reference's eager PyTorch path on the same GPU (fp32 restatement
+        # under bf16 autocast), i.e. the bar a user of the reference sees today
+        try:
+            out["gpu_eager_reference"] = eager_gpu_bar(wl, inp, device, max(3, args.steps // 4))
+        except Exception as exc:  # noqa: BLE001
+            out["gpu_eager_reference"] = {"error": str(exc)[:200]}
+    if world == 1 and not args.no_cpu_baseline:
+        cores = torch.get_num_threads()
+        v, cms = cpu_reference_run(wl, args.cpu_sample, 2, 1)
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                               "ms_per_step": cms,
+                               "sample": f"{args.cpu_sample} of {wl['B']} images per step, 2 timed steps "
+                                         f"after 1 warm-up, fp32, oracle/torch_port.py on the host CPU"}
+    print(json.dumps(out))
+    if dist_on:
+        torch.distributed.destroy_process_group()
+
+
+def eager_gpu_bar(wl, inp, device, steps):
+    from oracle import torch_port as TP  # baseline leg
+    H = wl["H"]
+    nps = torch.tensor([1.0 / n for n in wl["npts"] for _ in range(n)], device=device)
+    import dfine_b200
+    ref_mod = dfine_b200.MSDeformableAttention(wl["C"], H, len(wl["shapes"]), wl["npts"])
+    so_b = ref_mod.sampling_offsets.bias.detach().to(device)
+    up = torch.tensor([wl["up"]], device=device)
+    rs = torch.tensor([wl["reg_scale"]], device=device)
+    mem = inp["memory"].to(device, torch.bfloat16)
+    d = dict(q=[q.to(device) for q in inp["queries"]], r=[r.to(device) for r in inp["refs"]],
+             c=[c.to(device, torch.bfloat16) for c in inp["corners"]], ri=inp["ref_init"].to(device),
+             go=[g.to(device) for g in inp["grad_outs"]], gb=[g.to(device) for g in inp["grad_boxes"]])
+    lins = [(*(t.to(device).requires_grad_(True) for t in (lw["so_w"], so_b, lw["aw_w"], lw["aw_b"])), nps)
+            for lw in inp["lin"]]
+
+    def step():
+        for t in (x for lin in lins for x in lin[:4]):
+            t.grad = None
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            TP.hot_path_step(mem, d["q"], d["r"], lins, wl["shapes"], wl["npts"], H, d["c"], d["ri"],
+                             up, rs, d["go"], d["gb"], train=True)
+
+    ms = time_steps(step, steps, 3, device, False)
+    return {"value": wl["B"] * steps / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / steps,
+            "what": "reference call sequence (F.grid_sample path) eager on the same GPU, bf16 autocast"}
+
+
+if __name__ == "__main__":
+    main()

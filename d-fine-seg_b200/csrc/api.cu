@@ -1,0 +1,356 @@
+// C-ABI entry points of libdfine_b200.so (declared in include/dfine_b200.h).
+// Argument validation, error plumbing and parameter packing only: the kernels live in
+// msda_fwd.cu, msda_bwd.cu, fdr.cu and mask_gemm.cu.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace dfine {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+
+int launch_fdr_project(const float*, const float*, float*, int, cudaStream_t);
+int launch_fdr(bool, const void*, int, const float*, const float*, const float*, float*, float*,
+               const float*, const float*, float*, long long, int, cudaStream_t);
+int launch_mask_gemm(const void*, const void*, void*, int, int, int, int, int, int, cudaStream_t);
+
+static int cuda_rc(int rc, const char* what) {
+  if (rc > 0) set_error("%s: CUDA error %d (%s)", what, rc, cudaGetErrorString((cudaError_t)rc));
+  return rc;
+}
+
+// No CPU fallback: data pointers must be device (or managed) memory.
+static int require_device(const void* p, const char* name, const char* fn) {
+  if (!p) {
+    set_error("%s: %s is NULL", fn, name);
+    return DFINE_E_NULL;
+  }
+  cudaPointerAttributes at;
+  const cudaError_t e = cudaPointerGetAttributes(&at, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("%s: cannot query %s (%s); a CUDA device is required, there is no CPU path", fn,
+              name, cudaGetErrorString(e));
+    return (int)e;
+  }
+  if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged) {
+    set_error("%s: %s is not device memory; there is no CPU path", fn, name);
+    return DFINE_E_NULL;
+  }
+  return 0;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int fill_msda(MsdaParams& p, const char* fn, const void* value, int64_t sb, int64_t sl,
+                     const int32_t* lvl_hw, const int32_t* lvl_start, const int32_t* lvl_npts,
+                     int n_lvl, const void* samp, const void* attn, const float* ref,
+                     const float* pts_scale, float offset_scale, int B, int Lq, int H, int c,
+                     int value_dtype, int samp_dtype, int flags) {
+  memset(&p, 0, sizeof p);
+  if (!lvl_hw || !lvl_start || !lvl_npts) {
+    set_error("%s: level tables must be host pointers, got NULL", fn);
+    return DFINE_E_NULL;
+  }
+  if (B <= 0 || Lq <= 0 || H <= 0 || c <= 0) {
+    set_error("%s: B, Lq, H, c must be positive (got %d, %d, %d, %d)", fn, B, Lq, H, c);
+    return DFINE_E_SHAPE;
+  }
+  if (n_lvl < 1 || n_lvl > kMaxLevels) {
+    set_error("%s: n_lvl %d outside [1, %d]", fn, n_lvl, kMaxLevels);
+    return DFINE_E_UNSUPPORTED;
+  }
+  if ((value_dtype != DFINE_F32 && value_dtype != DFINE_BF16) ||
+      (samp_dtype != DFINE_F32 && samp_dtype != DFINE_BF16)) {
+    set_error("%s: dtypes must be DFINE_F32 or DFINE_BF16", fn);
+    return DFINE_E_UNSUPPORTED;
+  }
+  p.fused = (flags & DFINE_MSDA_FUSED_INPUTS) ? 1 : 0;
+  if (!p.fused && samp_dtype != DFINE_F32) {
+    set_error("%s: plain mode takes float32 sampling_locations / attention_weights", fn);
+    return DFINE_E_UNSUPPORTED;
+  }
+  int P = 0;
+  long long L = 0;
+  for (int l = 0; l < n_lvl; ++l) {
+    const int h = lvl_hw[2 * l], w = lvl_hw[2 * l + 1];
+    if (h <= 0 || w <= 0 || lvl_npts[l] <= 0 || lvl_start[l] < 0) {
+      set_error("%s: level %d has invalid shape (%d, %d), start %d or points %d", fn, l, h, w,
+                lvl_start[l], lvl_npts[l]);
+      return DFINE_E_SHAPE;
+    }
+    p.lvl_h[l] = h;
+    p.lvl_w[l] = w;
+    p.lvl_start[l] = lvl_start[l];
+    P += lvl_npts[l];
+    p.lvl_pend[l] = P;
+    const long long end = (long long)lvl_start[l] + (long long)h * w;
+    if (end > L) L = end;
+  }
+  for (int l = n_lvl; l < kMaxLevels; ++l) p.lvl_pend[l] = 1 << 30;
+  if (P > kMaxPoints) {
+    set_error("%s: %d sampling points per head exceed the built maximum %d", fn, P, kMaxPoints);
+    return DFINE_E_UNSUPPORTED;
+  }
+  if (L > 0x7fffffffLL) {
+    set_error("%s: value length too large", fn);
+    return DFINE_E_SHAPE;
+  }
+  int rc;
+  if ((rc = require_device(value, "value", fn))) return rc;
+  if ((rc = require_device(samp, "samp", fn))) return rc;
+  if ((rc = require_device(attn, "attn", fn))) return rc;
+  if (p.fused) {
+    if ((rc = require_device(ref, "ref_boxes", fn))) return rc;
+    if ((rc = require_device(pts_scale, "pts_scale", fn))) return rc;
+    if (!aligned16(ref)) {
+      set_error("%s: ref_boxes must be 16-byte aligned", fn);
+      return DFINE_E_ALIGN;
+    }
+  }
+  const int esz = value_dtype == DFINE_BF16 ? 2 : 4;
+  if (!aligned16(value) || (sb * esz) % 16 || (sl * esz) % 16 || (c * esz) % 16) {
+    set_error("%s: value pointer / strides / head slice must be 16-byte aligned "
+              "(stride_b %lld, stride_l %lld elements, c %d)", fn, (long long)sb, (long long)sl, c);
+    return DFINE_E_ALIGN;
+  }
+  if (sl < (int64_t)H * c || sb < sl) {
+    set_error("%s: value strides (%lld, %lld) inconsistent with H*c = %d", fn, (long long)sb,
+              (long long)sl, H * c);
+    return DFINE_E_SHAPE;
+  }
+  if (!aligned16(samp) || !aligned16(attn)) {
+    set_error("%s: samp / attn must be 16-byte aligned", fn);
+    return DFINE_E_ALIGN;
+  }
+  p.value = value;
+  p.stride_b = sb;
+  p.stride_l = sl;
+  p.samp = samp;
+  p.attn = attn;
+  p.ref = ref;
+  p.pts_scale = pts_scale;
+  p.offset_scale = offset_scale;
+  p.B = B; p.Lq = Lq; p.H = H; p.c = c; p.n_lvl = n_lvl; p.P = P; p.L = (int)L;
+  p.samp_bf16 = samp_dtype == DFINE_BF16;
+  return 0;
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                     long long n) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src + i));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(src + i) + 1);
+    __nv_bfloat162 o[4] = {__floats2bfloat162_rn(a.x, a.y), __floats2bfloat162_rn(a.z, a.w),
+                           __floats2bfloat162_rn(b.x, b.y), __floats2bfloat162_rn(b.z, b.w)};
+    *reinterpret_cast<uint4*>(dst + i) = *reinterpret_cast<const uint4*>(o);
+  } else {
+    for (long long j = i; j < n; ++j) dst[j] = __float2bfloat16_rn(src[j]);
+  }
+}
+
+}  // namespace dfine
+
+using namespace dfine;
+
+extern "C" {
+
+int dfine_version(void) { return DFINE_B200_VERSION; }
+
+const char* dfine_last_error(void) { return g_err; }
+
+int dfine_msda_fwd(const void* value, int64_t v_stride_b, int64_t v_stride_l,
+                   const int32_t* lvl_hw, const int32_t* lvl_start, const int32_t* lvl_npts,
+                   int n_lvl, const void* samp, const void* attn, const float* ref_boxes,
+                   const float* pts_scale, float offset_scale, void* out, int32_t* idx_debug,
+                   int B, int Lq, int H, int c, int value_dtype, int samp_dtype, int out_dtype,
+                   int flags, void* stream) {
+  MsdaParams p;
+  int rc = fill_msda(p, "dfine_msda_fwd", value, v_stride_b, v_stride_l, lvl_hw, lvl_start,
+                     lvl_npts, n_lvl, samp, attn, ref_boxes, pts_scale, offset_scale, B, Lq, H, c,
+                     value_dtype, samp_dtype, flags);
+  if (rc) return rc;
+  if ((rc = require_device(out, "out", "dfine_msda_fwd"))) return rc;
+  if (out_dtype != DFINE_F32 && out_dtype != DFINE_BF16) {
+    set_error("dfine_msda_fwd: out_dtype must be DFINE_F32 or DFINE_BF16");
+    return DFINE_E_UNSUPPORTED;
+  }
+  if (!aligned16(out) || (idx_debug && !aligned16(idx_debug))) {
+    set_error("dfine_msda_fwd: out / idx_debug must be 16-byte aligned");
+    return DFINE_E_ALIGN;
+  }
+  p.out = out;
+  p.out_bf16 = out_dtype == DFINE_BF16;
+  p.idx_debug = idx_debug;
+  return cuda_rc(launch_msda_fwd(p, value_dtype, (cudaStream_t)stream), "dfine_msda_fwd");
+}
+
+int dfine_msda_bwd(const void* value, int64_t v_stride_b, int64_t v_stride_l,
+                   const int32_t* lvl_hw, const int32_t* lvl_start, const int32_t* lvl_npts,
+                   int n_lvl, const void* samp, const void* attn, const float* ref_boxes,
+                   const float* pts_scale, float offset_scale, const void* grad_out,
+                   float* grad_value, float* grad_samp, float* grad_attn, int B, int Lq, int H,
+                   int c, int value_dtype, int samp_dtype, int go_dtype, int flags,
+                   void* stream) {
+  MsdaParams p;
+  int rc = fill_msda(p, "dfine_msda_bwd", value, v_stride_b, v_stride_l, lvl_hw, lvl_start,
+                     lvl_npts, n_lvl, samp, attn, ref_boxes, pts_scale, offset_scale, B, Lq, H, c,
+                     value_dtype, samp_dtype, flags);
+  if (rc) return rc;
+  if ((rc = require_device(grad_out, "grad_out", "dfine_msda_bwd"))) return rc;
+  if ((rc = require_device(grad_value, "grad_value", "dfine_msda_bwd"))) return rc;
+  if ((rc = require_device(grad_samp, "grad_samp", "dfine_msda_bwd"))) return rc;
+  if ((rc = require_device(grad_attn, "grad_attn", "dfine_msda_bwd"))) return rc;
+  if (go_dtype != DFINE_F32 && go_dtype != DFINE_BF16) {
+    set_error("dfine_msda_bwd: go_dtype must be DFINE_F32 or DFINE_BF16");
+    return DFINE_E_UNSUPPORTED;
+  }
+  if (!aligned16(grad_out) || !aligned16(grad_value) || !aligned16(grad_samp) ||
+      !aligned16(grad_attn)) {
+    set_error("dfine_msda_bwd: gradient buffers must be 16-byte aligned");
+    return DFINE_E_ALIGN;
+  }
+  p.grad_out = grad_out;
+  p.go_bf16 = go_dtype == DFINE_BF16;
+  p.grad_value = grad_value;
+  p.grad_samp = grad_samp;
+  p.grad_attn = grad_attn;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t bytes = (size_t)B * p.L * H * c * sizeof(float);
+  cudaError_t e = cudaMemsetAsync(grad_value, 0, bytes, s);
+  if (e != cudaSuccess) return cuda_rc((int)e, "dfine_msda_bwd(memset)");
+  return cuda_rc(launch_msda_bwd(p, value_dtype, s), "dfine_msda_bwd");
+}
+
+int dfine_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  int rc;
+  if (n < 0) {
+    set_error("dfine_cast_f32_to_bf16: negative size");
+    return DFINE_E_SHAPE;
+  }
+  if (n == 0) return 0;
+  if ((rc = require_device(src, "src", "dfine_cast_f32_to_bf16"))) return rc;
+  if ((rc = require_device(dst, "dst", "dfine_cast_f32_to_bf16"))) return rc;
+  if (!aligned16(src) || !aligned16(dst)) {
+    set_error("dfine_cast_f32_to_bf16: pointers must be 16-byte aligned");
+    return DFINE_E_ALIGN;
+  }
+  const long long threads = (n + 7) / 8;
+  cast_f32_bf16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  return cuda_rc((int)cudaGetLastError(), "dfine_cast_f32_to_bf16");
+}
+
+int dfine_fdr_project(const float* up, const float* reg_scale, float* project, int reg_max,
+                      void* stream) {
+  int rc;
+  if (reg_max < 4 || (reg_max & 1) || reg_max > 255) {
+    set_error("dfine_fdr_project: reg_max must be even and in [4, 254] (got %d)", reg_max);
+    return DFINE_E_SHAPE;
+  }
+  if ((rc = require_device(up, "up", "dfine_fdr_project"))) return rc;
+  if ((rc = require_device(reg_scale, "reg_scale", "dfine_fdr_project"))) return rc;
+  if ((rc = require_device(project, "project", "dfine_fdr_project"))) return rc;
+  return cuda_rc(launch_fdr_project(up, reg_scale, project, reg_max, (cudaStream_t)stream),
+                 "dfine_fdr_project");
+}
+
+static int fdr_common(const char* fn, const void* corners, int c_dtype, const float* project,
+                      const float* reg_scale, int64_t N, int reg_max) {
+  int rc;
+  if (N < 0 || reg_max < 1) {
+    set_error("%s: N must be >= 0 and reg_max >= 1 (got %lld, %d)", fn, (long long)N, reg_max);
+    return DFINE_E_SHAPE;
+  }
+  if (c_dtype != DFINE_F32 && c_dtype != DFINE_BF16) {
+    set_error("%s: c_dtype must be DFINE_F32 or DFINE_BF16", fn);
+    return DFINE_E_UNSUPPORTED;
+  }
+  if (N == 0) return 0;
+  if ((rc = require_device(corners, "corners", fn))) return rc;
+  if ((rc = require_device(project, "project", fn))) return rc;
+  if ((rc = require_device(reg_scale, "reg_scale", fn))) return rc;
+  return 0;
+}
+
+int dfine_fdr_fwd(const void* corners, int c_dtype, const float* ref_init, const float* project,
+                  const float* reg_scale, float* dist, float* boxes, int64_t N, int reg_max,
+                  void* stream) {
+  const char* fn = "dfine_fdr_fwd";
+  int rc = fdr_common(fn, corners, c_dtype, project, reg_scale, N, reg_max);
+  if (rc || N == 0) return rc;
+  if (!dist && !boxes) {
+    set_error("%s: at least one of dist / boxes must be given", fn);
+    return DFINE_E_NULL;
+  }
+  if (boxes && (rc = require_device(ref_init, "ref_init", fn))) return rc;
+  if ((dist && !aligned16(dist)) || (boxes && (!aligned16(boxes) || !aligned16(ref_init)))) {
+    set_error("%s: dist / boxes / ref_init must be 16-byte aligned", fn);
+    return DFINE_E_ALIGN;
+  }
+  return cuda_rc(launch_fdr(false, corners, c_dtype == DFINE_BF16, ref_init, project, reg_scale,
+                            dist, boxes, nullptr, nullptr, nullptr, N, reg_max,
+                            (cudaStream_t)stream), fn);
+}
+
+int dfine_fdr_bwd(const void* corners, int c_dtype, const float* ref_init, const float* project,
+                  const float* reg_scale, const float* grad_boxes, const float* grad_dist,
+                  float* grad_corners, int64_t N, int reg_max, void* stream) {
+  const char* fn = "dfine_fdr_bwd";
+  int rc = fdr_common(fn, corners, c_dtype, project, reg_scale, N, reg_max);
+  if (rc || N == 0) return rc;
+  if ((rc = require_device(grad_corners, "grad_corners", fn))) return rc;
+  if (!grad_boxes && !grad_dist) {
+    set_error("%s: at least one of grad_boxes / grad_dist must be given", fn);
+    return DFINE_E_NULL;
+  }
+  if (grad_boxes && (rc = require_device(ref_init, "ref_init", fn))) return rc;
+  if ((grad_boxes && (!aligned16(grad_boxes) || !aligned16(ref_init))) ||
+      (grad_dist && !aligned16(grad_dist))) {
+    set_error("%s: grad_boxes / grad_dist / ref_init must be 16-byte aligned", fn);
+    return DFINE_E_ALIGN;
+  }
+  return cuda_rc(launch_fdr(true, corners, c_dtype == DFINE_BF16, ref_init, project, reg_scale,
+                            nullptr, nullptr, grad_boxes, grad_dist, grad_corners, N, reg_max,
+                            (cudaStream_t)stream), fn);
+}
+
+int dfine_mask_gemm_fwd(const void* coef, const void* proto, void* out, int B, int M, int K,
+                        int N, int out_dtype, int apply_sigmoid, void* stream) {
+  const char* fn = "dfine_mask_gemm_fwd";
+  int rc;
+  if (B <= 0 || M <= 0 || K <= 0 || N <= 0) {
+    set_error("%s: B, M, K, N must be positive (got %d, %d, %d, %d)", fn, B, M, K, N);
+    return DFINE_E_SHAPE;
+  }
+  if (K % 64 || K > 512 || N % 8) {
+    set_error("%s: K must be a multiple of 64 and <= 512, N a multiple of 8 (got K=%d, N=%d)",
+              fn, K, N);
+    return DFINE_E_UNSUPPORTED;
+  }
+  if (out_dtype != DFINE_F32 && out_dtype != DFINE_BF16) {
+    set_error("%s: out_dtype must be DFINE_F32 or DFINE_BF16", fn);
+    return DFINE_E_UNSUPPORTED;
+  }
+  if ((rc = require_device(coef, "coef", fn))) return rc;
+  if ((rc = require_device(proto, "proto", fn))) return rc;
+  if ((rc = require_device(out, "out", fn))) return rc;
+  if (!aligned16(coef) || !aligned16(proto) || !aligned16(out)) {
+    set_error("%s: coef / proto / out must be 16-byte aligned", fn);
+    return DFINE_E_ALIGN;
+  }
+  return cuda_rc(launch_mask_gemm(coef, proto, out, B, M, K, N, out_dtype, apply_sigmoid,
+                                  (cudaStream_t)stream), fn);
+}
+
+}  // extern "C"

@@ -1,0 +1,410 @@
+// K4: prototype x coefficient mask assembly on the 5th-gen tensor cores (sm_100a).
+//
+// Replaces torch.einsum("bqc,bchw->bqhw", mask_embed, mask_feat) of
+// DFINETransformer._mask_logits_from_h (reference src/d_fine/arch/dfine_decoder.py:937-940)
+// and the eval-mode sigmoid (dfine_decoder.py:1041):
+//     out[b, m, n] = act( sum_k coef[b, m, k] * proto[b, k, n] )
+// coef  bf16 [B, M, K]  K contiguous  -> UMMA operand A, K-major
+// proto bf16 [B, K, N]  N contiguous  -> UMMA operand B, MN-major (no transpose pass)
+//
+// Persistent, warp-specialised, one CTA per SM (192 threads):
+//   warp 0      TMA producer  : cp.async.bulk.tensor (3-D maps, batch outermost) into a
+//                               4-stage smem ring, 128B swizzle, mbarrier complete_tx
+//   warp 1      MMA issuer    : one elected lane issues tcgen05.mma.cta_group::1.kind::f16
+//                               (M=128, N=256, K=16) into one of two 256-column TMEM
+//                               accumulators; tcgen05.commit releases smem stages / signals
+//                               the epilogue.  Also owns tcgen05.alloc / dealloc.
+//   warps 2..5  epilogue      : tcgen05.ld (32 lanes x 32 columns) -> optional sigmoid ->
+//                               swizzled st.shared -> per-warp TMA store (coalesced, clipped
+//                               at the M / N edges by the tensor map).
+// The GEMM is HBM-write bound at D-FINE shapes: the double-buffered
+// accumulator lets the store of tile i overlap the MMAs of tile i+1.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace dfine {
+
+namespace mg {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_N = 256;
+constexpr int BLOCK_K = 64;            // one 128-byte swizzle row of bf16
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;          // 16 KiB
+constexpr int B_BOX_BYTES = BLOCK_K * 64 * 2;           // one [64 k][64 n] box: 8 KiB
+constexpr int B_BYTES = B_BOX_BYTES * (BLOCK_N / 64);   // 32 KiB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;          // 48 KiB
+constexpr int EPI_WARPS = 4;
+constexpr int EPI_BUF_BYTES = 32 * 128;                 // 32 rows x 128 B
+constexpr int EPI_BYTES = EPI_WARPS * 2 * EPI_BUF_BYTES;  // 32 KiB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int THREADS = 192;
+constexpr int TMEM_COLS = 512;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}"
+      ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t dst, uint32_t bar,
+                                            int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1,
+                                             int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+      ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+               ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte
+//   offset >> 4 | [46,48) version = 1 | [61,64) layout type (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, A K-major,
+// B MN-major, N = 256, M = 128.
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (1u << 16) |
+                            ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+
+template <bool kOutBf16>
+__global__ void __launch_bounds__(THREADS, 1)
+mask_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_o, int B, int M, int K, int N,
+                 int apply_sigmoid) {
+  extern __shared__ unsigned char smem_raw[];
+  // 1024-byte alignment: required by the 128B swizzle atoms of TMA and UMMA
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  unsigned char* smem_epi = smem + STAGES * STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + EPI_BYTES);
+  uint64_t* full_bar = bars;                    // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;          // [STAGES]
+  uint64_t* tmem_full = bars + 2 * STAGES;      // [2]
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2; // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+  const int n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
+  const int k_blocks = K / BLOCK_K;
+  const long long tiles = (long long)B * m_tiles * n_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(smem_u32(&full_bar[i]), 1);
+      mbar_init(smem_u32(&empty_bar[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&tmem_full[i]), 1);
+      mbar_init(smem_u32(&tmem_empty[i]), EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int mt = (int)(t % m_tiles);
+        const int nt = (int)((t / m_tiles) % n_tiles);
+        const int b = (int)(t / ((long long)m_tiles * n_tiles));
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_expect_tx(fb, STAGE_BYTES);
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+          tma_load_3d(&map_a, sa, fb, kb * BLOCK_K, mt * BLOCK_M, b);
+#pragma unroll
+          for (int j = 0; j < BLOCK_N / 64; ++j)
+            tma_load_3d(&map_b, sb + j * B_BOX_BYTES, fb, nt * BLOCK_N + j * 64, kb * BLOCK_K, b);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        mbar_wait(smem_u32(&tmem_empty[as]), aphase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // A: K-major SW128, 8-row groups 1024 B apart; +32 B per 16 k inside the row.
+            const uint64_t da = make_desc(sa + k * UMMA_K * 2, 16, 1024);
+            // B: MN-major SW128, 64-n blocks B_BOX_BYTES apart (LBO), 8-k groups 1024 B
+            // apart (SBO); +16 k rows = +2048 B.
+            const uint64_t db = make_desc(sb + k * UMMA_K * 128, B_BOX_BYTES, 1024);
+            umma_bf16(tmem_d, da, db, kIdesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&empty_bar[stage]));  // smem stage free once these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(smem_u32(&tmem_full[as]));  // accumulator complete
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int wq = warp & 3;  // TMEM lane quarter this warp may access
+    constexpr int COLS = kOutBf16 ? 64 : 32;   // columns per 128-byte smem row
+    unsigned char* my_buf = smem_epi + (warp - 2) * 2 * EPI_BUF_BYTES;
+    int as = 0;
+    uint32_t aphase = 0;
+    int buf = 0;
+    for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+      const int mt = (int)(t % m_tiles);
+      const int nt = (int)((t / m_tiles) % n_tiles);
+      const int b = (int)(t / ((long long)m_tiles * n_tiles));
+      const int row0 = mt * BLOCK_M + wq * 32;
+      mbar_wait(smem_u32(&tmem_full[as]), aphase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + as * BLOCK_N + ((uint32_t)(wq * 32) << 16);
+      for (int c0 = 0; c0 < BLOCK_N; c0 += COLS) {
+        const int col0 = nt * BLOCK_N + c0;
+        const bool store = row0 < M && col0 < N;
+        uint32_t packed[32];
+#pragma unroll
+        for (int half = 0; half < COLS / 32; ++half) {
+          uint32_t r[32];
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, "
+              "[%32];"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]),
+                "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
+                "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+                "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+                "=r"(r[30]), "=r"(r[31])
+              : "r"(taddr + c0 + half * 32));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (apply_sigmoid) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              r[i] = __float_as_uint(1.0f / (1.0f + __expf(-__uint_as_float(r[i]))));
+          }
+          if (kOutBf16) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const __nv_bfloat162 v =
+                  __floats2bfloat162_rn(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+              packed[half * 16 + i] = *reinterpret_cast<const uint32_t*>(&v);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) packed[i] = r[i];
+          }
+        }
+        if (store) {
+          // the buffer we are about to overwrite was handed to TMA two stores ago
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          __syncwarp();
+          unsigned char* dst = my_buf + buf * EPI_BUF_BYTES + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {  // 128B swizzle: 16-byte chunk j of row r -> j ^ (r & 7)
+            *reinterpret_cast<uint4*>(dst + ((j ^ (lane & 7)) << 4)) =
+                make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&map_o, smem_u32(my_buf + buf * EPI_BUF_BYTES), col0, row0, b);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          buf ^= 1;
+        }
+      }
+      // all TMEM reads of this accumulator are complete (wait::ld above): release it
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[as]));
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(TMEM_COLS));
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int encode_3d(EncodeTiledFn enc, CUtensorMap* map, CUtensorMapDataType dt, int esz,
+                     const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0,
+                     uint32_t b1, const char* what) {
+  const cuuint64_t dims[3] = {d0, d1, d2};
+  const cuuint64_t strides[2] = {d0 * esz, d0 * d1 * esz};
+  const cuuint32_t box[3] = {b0, b1, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = enc(map, dt, 3, const_cast<void*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("mask_gemm: cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
+    return DFINE_E_SHAPE;
+  }
+  return 0;
+}
+
+}  // namespace mg
+
+int launch_mask_gemm(const void* coef, const void* proto, void* out, int B, int M, int K, int N,
+                     int out_dtype, int apply_sigmoid, cudaStream_t s) {
+  using namespace mg;
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_error("mask_gemm: cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return DFINE_E_UNSUPPORTED;
+  }
+  alignas(64) CUtensorMap map_a, map_b, map_o;
+  int rc;
+  if ((rc = encode_3d(enc, &map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, coef, K, M, B, BLOCK_K,
+                      BLOCK_M, "coef")))
+    return rc;
+  if ((rc = encode_3d(enc, &map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, proto, N, K, B, 64,
+                      BLOCK_K, "proto")))
+    return rc;
+  const bool obf = out_dtype == DFINE_BF16;
+  if ((rc = encode_3d(enc, &map_o, obf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                       : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                      obf ? 2 : 4, out, N, M, B, obf ? 64 : 32, 32, "out")))
+    return rc;
+
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long tiles = (long long)B * ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BLOCK_N - 1) / BLOCK_N);
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  cudaError_t e;
+  if (obf) {
+    e = cudaFuncSetAttribute(mask_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    mask_gemm_kernel<true><<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, map_o, B, M, K, N,
+                                                             apply_sigmoid);
+  } else {
+    e = cudaFuncSetAttribute(mask_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    mask_gemm_kernel<false><<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, map_o, B, M, K, N,
+                                                              apply_sigmoid);
+  }
+  return (int)cudaGetLastError();
+}
+
+}  // namespace dfine

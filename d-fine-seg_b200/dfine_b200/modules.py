@@ -1,0 +1,181 @@
+"""Host-side mirror of the reference's module interface for the hot path.
+
+* MSDeformableAttention -- same constructor, parameters, buffers, state-dict keys and
+  forward signature as the reference module (src/d_fine/arch/dfine_decoder.py:49-178);
+  forward runs the two Linears (cuBLAS) and ONE fused CUDA kernel.
+* Integral -- same interface as dfine_decoder.py:274-295.
+* patch_model / unpatch_model -- swap the hot path inside an already built reference model
+  (checkpoints, training / inference scripts stay untouched).  The first-level hook is the
+  reference's own injection point, the instance attribute `ms_deformable_attn_core`
+  (dfine_decoder.py:90-92).
+"""
+from __future__ import annotations
+
+import functools
+import math
+import types
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+
+def _fused_forward(self, query: torch.Tensor, reference_points: torch.Tensor, value,
+                   value_spatial_shapes):
+    """MSDeformableAttention.forward (reference dfine_decoder.py:119-178).
+
+    query [bs, Lq, C]; reference_points [bs, Lq, 1, 4] (cx, cy, w, h) or [bs, Lq, n_levels, 2];
+    value: tuple of per-level views [bs, H, c, h_l*w_l] from TransformerDecoder.value_op;
+    value_spatial_shapes: [[h_l, w_l], ...].  Returns [bs, Lq, C].
+    """
+    bs, Lq = query.shape[:2]
+    P = sum(self.num_points_list)
+    last = reference_points.shape[-1]
+    if last == 4:
+        raw_off = self.sampling_offsets(query)
+        raw_logit = self.attention_weights(query)
+        return ops.msda_fused(value, value_spatial_shapes, raw_off, raw_logit, reference_points,
+                              self.num_points_scale, self.num_points_list, self.offset_scale)
+    if last == 2:
+        # legacy RT-DETR branch (dfine_decoder.py:149-155); not used by D-FINE.  Location
+        # arithmetic stays in torch, sampling runs in the plain-mode kernel.
+        so = self.sampling_offsets(query).reshape(bs, Lq, self.num_heads, P, 2)
+        aw = F.softmax(self.attention_weights(query).reshape(bs, Lq, self.num_heads, P), dim=-1)
+        norm = torch.tensor(value_spatial_shapes, device=query.device).flip([1])
+        norm = norm.reshape(1, 1, 1, self.num_levels, 1, 2)
+        loc = reference_points.reshape(bs, Lq, 1, self.num_levels, 1, 2) + so / norm
+        return ops.msda_core(value, value_spatial_shapes, loc, aw, self.num_points_list)
+    raise ValueError(
+        "Last dim of reference_points must be 2 or 4, but get {} instead.".format(last))
+
+
+class MSDeformableAttention(nn.Module):
+    """Multi-scale deformable attention with the reference's parameters and signature."""
+
+    def __init__(self, embed_dim=256, num_heads=8, num_levels=4, num_points=4, method="default",
+                 offset_scale=0.5):
+        super().__init__()
+        if method != "default":
+            raise NotImplementedError("only the bilinear ('default') sampling method is built")
+        self.embed_dim = embed_dim
+        self.num_heads = num_heads
+        self.num_levels = num_levels
+        self.offset_scale = offset_scale
+        if isinstance(num_points, (list, tuple)):
+            assert len(num_points) == num_levels, ""
+            self.num_points_list = list(num_points)
+        else:
+            self.num_points_list = [num_points] * num_levels
+        scale = [1.0 / n for n in self.num_points_list for _ in range(n)]
+        self.register_buffer("num_points_scale", torch.tensor(scale, dtype=torch.float32))
+        self.total_points = num_heads * sum(self.num_points_list)
+        self.method = method
+        self.head_dim = embed_dim // num_heads
+        assert self.head_dim * num_heads == embed_dim, "embed_dim must be divisible by num_heads"
+        self.sampling_offsets = nn.Linear(embed_dim, self.total_points * 2)
+        self.attention_weights = nn.Linear(embed_dim, self.total_points)
+        self.ms_deformable_attn_core = functools.partial(ops.msda_core, method=method)
+        self._reset_parameters()
+
+    def _reset_parameters(self):
+        # zero weights; offsets biased along num_heads directions, scaled by the point rank
+        # (same initial state as dfine_decoder.py:100-117)
+        nn.init.zeros_(self.sampling_offsets.weight)
+        ang = torch.arange(self.num_heads, dtype=torch.float32) * (2.0 * math.pi / self.num_heads)
+        dirs = torch.stack([ang.cos(), ang.sin()], dim=-1)
+        dirs = dirs / dirs.abs().max(dim=-1, keepdim=True).values
+        rank = torch.cat([torch.arange(1, n + 1) for n in self.num_points_list]).to(dirs.dtype)
+        bias = dirs[:, None, :] * rank[None, :, None]  # [H, P, 2]
+        with torch.no_grad():
+            self.sampling_offsets.bias.copy_(bias.reshape(-1))
+        nn.init.zeros_(self.attention_weights.weight)
+        nn.init.zeros_(self.attention_weights.bias)
+
+    forward = _fused_forward
+
+
+class Integral(nn.Module):
+    """sum Pr(n) W(n) over the reg_max+1 bins (reference dfine_decoder.py:274-295)."""
+
+    def __init__(self, reg_max=32):
+        super().__init__()
+        self.reg_max = reg_max
+
+    def forward(self, x, project):
+        return ops.fdr_integral(x, project.to(x.device), self.reg_max)
+
+
+def _integral_forward(self, x, project):
+    return ops.fdr_integral(x, project.to(x.device), self.reg_max)
+
+
+def _mask_logits_from_h(self, h, mask_feat):
+    """DFINETransformer._mask_logits_from_h (reference dfine_decoder.py:937-940)."""
+    mask_embed = self.mask_head(h)
+    use_tc = (mask_embed.is_cuda and mask_embed.shape[-1] % 64 == 0
+              and mask_embed.shape[-1] <= 512 and (mask_feat.shape[-1] * mask_feat.shape[-2]) % 8 == 0
+              and (torch.is_autocast_enabled() or mask_embed.dtype == torch.bfloat16))
+    if not use_tc:
+        # fp32 (non-AMP) contraction stays a plain library GEMM, exactly as in the reference
+        return torch.einsum("bqc,bchw->bqhw", mask_embed, mask_feat)
+    return ops.mask_logits(mask_embed, mask_feat)
+
+
+def _is_msda(m: nn.Module) -> bool:
+    return all(hasattr(m, a) for a in ("ms_deformable_attn_core", "sampling_offsets",
+                                       "attention_weights", "num_points_list", "num_points_scale"))
+
+
+_MISSING = "<dfine_b200:missing>"  # atomic under deepcopy
+
+
+def _swap(m: nn.Module, attr: str, new) -> None:
+    """Set an instance attribute, remembering what the instance held before (or that it
+    held nothing and the class attribute was in effect)."""
+    saved = m.__dict__.setdefault("_b200_saved", {})
+    if attr not in saved:
+        saved[attr] = m.__dict__.get(attr, _MISSING)
+    m.__dict__[attr] = new
+
+
+def patch_model(model: nn.Module, fused: bool = True, fdr: bool = True, mask: bool = True) -> dict:
+    """Route the decoder hot path of a built reference model through libdfine_b200.so.
+
+    fused=False only swaps `ms_deformable_attn_core` (the reference's own hook); fused=True
+    additionally replaces MSDeformableAttention.forward so that softmax + location
+    arithmetic run inside the kernel.  Parameters, buffers and state-dict keys are untouched.
+    Returns the number of patched modules per kind.
+    """
+    n = {"msda": 0, "integral": 0, "mask": 0}
+    for m in model.modules():
+        if _is_msda(m):
+            method = getattr(m, "method", "default")
+            if method != "default":
+                continue
+            _swap(m, "ms_deformable_attn_core", functools.partial(ops.msda_core, method=method))
+            if fused:
+                _swap(m, "forward", types.MethodType(_fused_forward, m))
+            n["msda"] += 1
+        elif fdr and type(m).__name__ == "Integral" and hasattr(m, "reg_max"):
+            _swap(m, "forward", types.MethodType(_integral_forward, m))
+            n["integral"] += 1
+        elif mask and hasattr(m, "_mask_logits_from_h") and hasattr(m, "mask_head"):
+            _swap(m, "_mask_logits_from_h", types.MethodType(_mask_logits_from_h, m))
+            n["mask"] += 1
+    return n
+
+
+def unpatch_model(model: nn.Module) -> None:
+    """Undo patch_model (needed before ONNX export: raw C-ABI calls are not traceable)."""
+    for m in model.modules():
+        saved = m.__dict__.pop("_b200_saved", None)
+        if not saved:
+            continue
+        for attr, old in saved.items():
+            if old is _MISSING:
+                m.__dict__.pop(attr, None)
+            else:
+                m.__dict__[attr] = old

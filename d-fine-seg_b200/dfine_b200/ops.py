@@ -1,0 +1,433 @@
+"""torch.autograd front ends of the C-ABI kernels (host plumbing only: shapes, dtypes,
+pointers, streams).  All compute happens in libdfine_b200.so; CPU tensors are rejected.
+"""
+from __future__ import annotations
+
+import functools
+from typing import List, Optional, Sequence, Tuple, Union
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, MSDA_FUSED_INPUTS, check
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+# Instrumentation used by bench.py: number of kernels launched through the C-ABI, and
+# optional CUDA-event brackets around each launch (on the launching stream).
+LAUNCHES = {"count": 0}
+_TIMERS = None  # None or dict: kernel name -> list of (start_event, end_event)
+
+
+def enable_kernel_timers(enable: bool = True) -> None:
+    global _TIMERS
+    _TIMERS = {} if enable else None
+
+
+def kernel_timers():
+    return _TIMERS
+
+
+class _timed:
+    """Counts the launch and, when timers are enabled, brackets it with CUDA events."""
+
+    def __init__(self, name: str, t: torch.Tensor, kernels: int = 1):
+        self.name, self.t, self.kernels = name, t, kernels
+
+    def __enter__(self):
+        LAUNCHES["count"] += self.kernels
+        if _TIMERS is not None:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record(torch.cuda.current_stream(self.t.device))
+        return self
+
+    def __exit__(self, *exc):
+        if _TIMERS is not None:
+            self.e.record(torch.cuda.current_stream(self.t.device))
+            _TIMERS.setdefault(self.name, []).append((self.s, self.e))
+        return False
+
+
+def _dt(t: torch.Tensor, what: str) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"{what}: dtype {t.dtype} not supported (float32 or bfloat16)") from None
+
+
+def _require_cuda(*tensors: torch.Tensor) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "dfine_b200 kernels run on CUDA tensors only (there is no CPU fallback); "
+                f"got a tensor on {t.device}")
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+class LevelSpec:
+    """Per-level tables in the form the C-ABI wants (host int32 arrays)."""
+
+    def __init__(self, spatial_shapes: Sequence[Sequence[int]], num_points: Sequence[int]):
+        shapes = [(int(h), int(w)) for h, w in spatial_shapes]
+        npts = [int(n) for n in num_points]
+        assert len(npts) == len(shapes), "len(num_points) must equal the number of levels"
+        self.shapes, self.npts = shapes, npts
+        self.n_lvl = len(shapes)
+        self.sizes = [h * w for h, w in shapes]
+        self.starts = [sum(self.sizes[:i]) for i in range(self.n_lvl)]
+        self.L = sum(self.sizes)
+        self.P = sum(npts)
+        self.hw_c = _lib.i32_array([v for hw in shapes for v in hw])
+        self.start_c = _lib.i32_array(self.starts)
+        self.npts_c = _lib.i32_array(npts)
+
+
+@functools.lru_cache(maxsize=64)
+def _level_spec(shapes: Tuple[Tuple[int, int], ...], npts: Tuple[int, ...]) -> LevelSpec:
+    return LevelSpec(shapes, npts)
+
+
+def level_spec(spatial_shapes, num_points) -> LevelSpec:
+    return _level_spec(tuple((int(h), int(w)) for h, w in spatial_shapes),
+                       tuple(int(n) for n in num_points))
+
+
+# --------------------------------------------------------------------------------------
+# value layout: recover `memory [B, L, H*c]` behind TransformerDecoder.value_op's views
+# --------------------------------------------------------------------------------------
+def memory_from_value(value: Union[torch.Tensor, Sequence[torch.Tensor]], spec: LevelSpec
+                      ) -> Tuple[torch.Tensor, int, int, bool]:
+    """Returns (memory [B, L, H*c], H, c, zero_copy).
+
+    `value` is either the `memory` tensor itself ([B, L, C] with `H` unknown is not
+    accepted here -- pass [B, L, H, c]) or the tuple of per-level views
+    [B, H, c, h_l*w_l] that TransformerDecoder.value_op builds
+    (reference dfine_decoder.py:416-426: reshape -> permute(0,2,3,1) -> split).  The views
+    alias one [B, L, H, c] buffer; when that pattern is recognised the kernel reads the
+    buffer in place and autograd is routed to the base tensor (one [B, L, C] gradient, no
+    cat / permute / reshape copies).  Anything else is packed with one copy.
+    """
+    if isinstance(value, torch.Tensor):
+        if value.dim() != 4:
+            raise ValueError("value tensor must be [B, L, H, c]")
+        B, L, H, c = value.shape
+        if L != spec.L:
+            raise ValueError(f"value length {L} != sum(h*w) = {spec.L}")
+        return value.reshape(B, L, H * c), H, c, True
+    views = list(value)
+    if len(views) != spec.n_lvl:
+        raise ValueError(f"expected {spec.n_lvl} value levels, got {len(views)}")
+    B, H, c, _ = views[0].shape
+    C = H * c
+    for v, n in zip(views, spec.sizes):
+        if tuple(v.shape) != (B, H, c, n):
+            raise ValueError(f"value level shape {tuple(v.shape)} != {(B, H, c, n)}")
+    base = views[0]._base
+    want_strides = (spec.L * C, c, 1, C)
+    ok = (base is not None and base.dim() == 3 and tuple(base.shape) == (B, spec.L, C)
+          and base.is_contiguous() and base.dtype == views[0].dtype
+          and base.requires_grad == views[0].requires_grad)
+    if ok:
+        esz = base.element_size()
+        for v, st in zip(views, spec.starts):
+            vb = v._base
+            if (vb is None or vb.data_ptr() != base.data_ptr() or vb.shape != base.shape
+                    or tuple(v.stride()) != want_strides
+                    or v.data_ptr() != base.data_ptr() + st * C * esz):
+                ok = False
+                break
+    if ok:
+        return base, H, c, True
+    # generic (slow) path: one packing copy, autograd flows through the views
+    mem = torch.cat([v.permute(0, 3, 1, 2) for v in views], dim=1)  # [B, L, H, c]
+    return mem.reshape(B, spec.L, C), H, c, False
+
+
+# --------------------------------------------------------------------------------------
+# K1 / K2
+# --------------------------------------------------------------------------------------
+def _mem_strides(memory: torch.Tensor) -> Tuple[int, int]:
+    if memory.stride(2) != 1:
+        raise ValueError("memory must have unit stride along the channel dimension")
+    return memory.stride(0), memory.stride(1)
+
+
+def msda_forward_raw(memory, spec: LevelSpec, H: int, samp, attn, ref, pts_scale,
+                     offset_scale: float, fused: bool, out_dtype: torch.dtype,
+                     want_idx: bool = False):
+    """Direct call of dfine_msda_fwd (no autograd).  Returns out [B, Lq, C] (, idx)."""
+    _require_cuda(memory, samp, attn, ref, pts_scale)
+    B, L, C = memory.shape
+    c = C // H
+    Lq = samp.shape[1]
+    sb, sl = _mem_strides(memory)
+    out = torch.empty((B, Lq, C), dtype=out_dtype, device=memory.device)
+    idx = (torch.empty((B, Lq, H, spec.P, 4), dtype=torch.int32, device=memory.device)
+           if want_idx else None)
+    with torch.cuda.device_of(memory), _timed("msda_fwd", memory):
+        rc = _lib.lib().dfine_msda_fwd(
+            memory.data_ptr(), sb, sl, spec.hw_c, spec.start_c, spec.npts_c, spec.n_lvl,
+            samp.data_ptr(), attn.data_ptr(), _ptr(ref), _ptr(pts_scale), float(offset_scale),
+            out.data_ptr(), _ptr(idx), B, Lq, H, c, _dt(memory, "value"), _dt(samp, "samp"),
+            _dt(out, "out"), MSDA_FUSED_INPUTS if fused else 0, _stream(memory))
+    check(rc, "dfine_msda_fwd")
+    return (out, idx) if want_idx else out
+
+
+def msda_backward_raw(memory, spec: LevelSpec, H: int, samp, attn, ref, pts_scale,
+                      offset_scale: float, fused: bool, grad_out):
+    """Direct call of dfine_msda_bwd.  Returns fp32 (grad_memory [B,L,C], grad_samp, grad_attn)."""
+    _require_cuda(memory, samp, attn, grad_out)
+    B, L, C = memory.shape
+    c = C // H
+    Lq = samp.shape[1]
+    sb, sl = _mem_strides(memory)
+    dev = memory.device
+    g_mem = torch.empty((B, spec.L, C), dtype=torch.float32, device=dev)
+    g_samp = torch.empty(samp.shape, dtype=torch.float32, device=dev)
+    g_attn = torch.empty(attn.shape, dtype=torch.float32, device=dev)
+    with torch.cuda.device_of(memory), _timed("msda_bwd", memory):
+        rc = _lib.lib().dfine_msda_bwd(
+            memory.data_ptr(), sb, sl, spec.hw_c, spec.start_c, spec.npts_c, spec.n_lvl,
+            samp.data_ptr(), attn.data_ptr(), _ptr(ref), _ptr(pts_scale), float(offset_scale),
+            grad_out.data_ptr(), g_mem.data_ptr(), g_samp.data_ptr(), g_attn.data_ptr(),
+            B, Lq, H, c, _dt(memory, "value"), _dt(samp, "samp"), _dt(grad_out, "grad_out"),
+            MSDA_FUSED_INPUTS if fused else 0, _stream(memory))
+    check(rc, "dfine_msda_bwd")
+    return g_mem, g_samp, g_attn
+
+
+def cast_f32_to_bf16(src: torch.Tensor) -> torch.Tensor:
+    dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    with torch.cuda.device_of(src), _timed("cast_bf16", src):
+        rc = _lib.lib().dfine_cast_f32_to_bf16(src.data_ptr(), dst.data_ptr(), src.numel(),
+                                               _stream(src))
+    check(rc, "dfine_cast_f32_to_bf16")
+    return dst
+
+
+class _MsdaFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, memory, samp, attn, ref, pts_scale, spec, H, offset_scale, fused, out_dtype):
+        samp = samp.contiguous()
+        attn = attn.contiguous()
+        out = msda_forward_raw(memory, spec, H, samp, attn, ref, pts_scale, offset_scale, fused,
+                               out_dtype)
+        ctx.save_for_backward(memory, samp, attn, ref, pts_scale)
+        ctx.spec, ctx.H, ctx.offset_scale, ctx.fused = spec, H, offset_scale, fused
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        memory, samp, attn, ref, pts_scale = ctx.saved_tensors
+        if grad_out.dtype not in _DT:
+            grad_out = grad_out.float()
+        g_mem, g_samp, g_attn = msda_backward_raw(memory, ctx.spec, ctx.H, samp, attn, ref,
+                                                  pts_scale, ctx.offset_scale, ctx.fused,
+                                                  grad_out.contiguous())
+        if memory.dtype == torch.bfloat16:
+            g_mem = cast_f32_to_bf16(g_mem)
+        if g_samp.dtype != samp.dtype:
+            g_samp = g_samp.to(samp.dtype)
+            g_attn = g_attn.to(attn.dtype)
+        return g_mem, g_samp, g_attn, None, None, None, None, None, None, None
+
+
+def msda_core(value, value_spatial_shapes, sampling_locations, attention_weights,
+              num_points_list, method: str = "default") -> torch.Tensor:
+    """Drop-in for deformable_attention_core_func_v2 (reference arch/utils.py:191-264).
+
+    value: tuple of [B, H, c, h_l*w_l] views (TransformerDecoder.value_op) or [B, L, H, c];
+    sampling_locations [B, Lq, H, P, 2]; attention_weights [B, Lq, H, P] -> [B, Lq, H*c].
+    """
+    if method != "default":
+        raise NotImplementedError(
+            "dfine_b200 implements the bilinear ('default') sampler only; "
+            "cross_attn_method='discrete' is not used by any shipped config")
+    spec = level_spec(value_spatial_shapes, num_points_list)
+    memory, H, c, _ = memory_from_value(value, spec)
+    _require_cuda(memory, sampling_locations, attention_weights)
+    out_dtype = torch.promote_types(memory.dtype, attention_weights.dtype)
+    if torch.is_autocast_enabled():
+        out_dtype = torch.float32  # grid_sampler is an autocast-to-fp32 op
+    loc = sampling_locations.float()
+    attn = attention_weights.float()
+    out = _MsdaFn.apply(memory, loc, attn, None, None, spec, H, 0.5, False, out_dtype)
+    return out
+
+
+def msda_fused(value, value_spatial_shapes, raw_offsets, raw_logits, ref_boxes, pts_scale,
+               num_points_list, offset_scale: float = 0.5) -> torch.Tensor:
+    """MSDeformableAttention.forward minus the two Linears (reference
+    dfine_decoder.py:144-176, reference_points last-dim 4): softmax over the P points,
+    sampling-location arithmetic, bilinear gather and weighted sum in one kernel.
+
+    raw_offsets [B, Lq, H*P*2] (or [B,Lq,H,P,2]); raw_logits [B, Lq, H*P];
+    ref_boxes [B, Lq, 1, 4] or [B, Lq, 4] (cx, cy, w, h); pts_scale [P] float32.
+    """
+    spec = level_spec(value_spatial_shapes, num_points_list)
+    memory, H, c, _ = memory_from_value(value, spec)
+    _require_cuda(memory, raw_offsets, raw_logits, ref_boxes, pts_scale)
+    B, Lq = raw_offsets.shape[:2]
+    if raw_offsets.dtype != raw_logits.dtype:
+        raw_logits = raw_logits.to(raw_offsets.dtype)
+    if raw_offsets.dtype not in _DT:
+        raw_offsets, raw_logits = raw_offsets.float(), raw_logits.float()
+    samp = raw_offsets.reshape(B, Lq, H, spec.P, 2)
+    attn = raw_logits.reshape(B, Lq, H, spec.P)
+    ref = ref_boxes.reshape(B, Lq, 4).float().contiguous()
+    out_dtype = torch.promote_types(memory.dtype, raw_offsets.dtype)
+    if torch.is_autocast_enabled():
+        out_dtype = torch.float32
+    return _MsdaFn.apply(memory, samp, attn, ref, pts_scale.float().contiguous(), spec, H,
+                         float(offset_scale), True, out_dtype)
+
+
+# --------------------------------------------------------------------------------------
+# K3
+# --------------------------------------------------------------------------------------
+def fdr_project(up: torch.Tensor, reg_scale: torch.Tensor, reg_max: int = 32) -> torch.Tensor:
+    """weighting_function (reference arch/utils.py:145-188) in one launch."""
+    _require_cuda(up, reg_scale)
+    up = up.detach().float().contiguous()
+    rs = reg_scale.detach().float().contiguous()
+    out = torch.empty(reg_max + 1, dtype=torch.float32, device=up.device)
+    with torch.cuda.device_of(up), _timed("fdr_project", up):
+        rc = _lib.lib().dfine_fdr_project(up.data_ptr(), rs.data_ptr(), out.data_ptr(), reg_max,
+                                          _stream(up))
+    check(rc, "dfine_fdr_project")
+    return out
+
+
+def _as_dev_scalar(v, like: torch.Tensor) -> torch.Tensor:
+    if isinstance(v, torch.Tensor):
+        return v.detach().to(device=like.device, dtype=torch.float32).reshape(-1)[:1].contiguous()
+    return torch.tensor([float(v)], dtype=torch.float32, device=like.device)
+
+
+class _FdrFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, corners, ref_init, project, reg_scale, reg_max, want_dist, want_boxes):
+        lead = corners.shape[:-1]
+        N = corners.numel() // (4 * (reg_max + 1))
+        dev = corners.device
+        dist = torch.empty((*lead, 4), dtype=torch.float32, device=dev) if want_dist else None
+        boxes = torch.empty((*lead, 4), dtype=torch.float32, device=dev) if want_boxes else None
+        with torch.cuda.device_of(corners), _timed("fdr_fwd", corners):
+            rc = _lib.lib().dfine_fdr_fwd(corners.data_ptr(), _dt(corners, "corners"),
+                                          _ptr(ref_init), project.data_ptr(), reg_scale.data_ptr(),
+                                          _ptr(dist), _ptr(boxes), N, reg_max, _stream(corners))
+        check(rc, "dfine_fdr_fwd")
+        ctx.save_for_backward(corners, ref_init, project, reg_scale)
+        ctx.reg_max = reg_max
+        return dist, boxes
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_dist, g_boxes):
+        corners, ref_init, project, reg_scale = ctx.saved_tensors
+        N = corners.numel() // (4 * (ctx.reg_max + 1))
+        gd = g_dist.float().contiguous() if g_dist is not None else None
+        gb = g_boxes.float().contiguous() if g_boxes is not None else None
+        gc = torch.empty(corners.shape, dtype=torch.float32, device=corners.device)
+        if gd is None and gb is None:
+            return gc.zero_().to(corners.dtype), None, None, None, None, None, None
+        with torch.cuda.device_of(corners), _timed("fdr_bwd", corners):
+            rc = _lib.lib().dfine_fdr_bwd(corners.data_ptr(), _dt(corners, "corners"),
+                                          _ptr(ref_init), project.data_ptr(), reg_scale.data_ptr(),
+                                          _ptr(gb), _ptr(gd), gc.data_ptr(), N, ctx.reg_max,
+                                          _stream(corners))
+        check(rc, "dfine_fdr_bwd")
+        return gc.to(corners.dtype), None, None, None, None, None, None
+
+
+def _fdr_prepare(corners, project, reg_scale, reg_max):
+    _require_cuda(corners, project)
+    if corners.dtype not in _DT:
+        corners = corners.float()
+    if corners.shape[-1] != 4 * (reg_max + 1):
+        raise ValueError(f"pred_corners last dim {corners.shape[-1]} != 4*(reg_max+1)")
+    return (corners.contiguous(), project.detach().float().contiguous(),
+            _as_dev_scalar(reg_scale, corners))
+
+
+def fdr_integral(corners: torch.Tensor, project: torch.Tensor, reg_max: int = 32) -> torch.Tensor:
+    """Drop-in for Integral.forward (reference dfine_decoder.py:291-295): [..., 4*(reg_max+1)]
+    -> [..., 4] distances, float32."""
+    corners, project, rs = _fdr_prepare(corners, project, 1.0, reg_max)
+    dist, _ = _FdrFn.apply(corners, None, project, rs, reg_max, True, False)
+    return dist
+
+
+def fdr_decode(corners: torch.Tensor, ref_init: torch.Tensor, project: torch.Tensor, reg_scale,
+               reg_max: int = 32, return_dist: bool = False):
+    """distance2bbox(ref_init, Integral(corners, project), reg_scale) in one kernel (reference
+    dfine_decoder.py:497-499, arch/utils.py:119-142): -> cxcywh boxes [..., 4] float32."""
+    corners, project, rs = _fdr_prepare(corners, project, reg_scale, reg_max)
+    _require_cuda(ref_init)
+    ref = ref_init.detach().float().contiguous()
+    dist, boxes = _FdrFn.apply(corners, ref, project, rs, reg_max, return_dist, True)
+    return (boxes, dist) if return_dist else boxes
+
+
+# --------------------------------------------------------------------------------------
+# K4
+# --------------------------------------------------------------------------------------
+def mask_gemm_raw(coef: torch.Tensor, proto: torch.Tensor, out_dtype: torch.dtype,
+                  apply_sigmoid: bool) -> torch.Tensor:
+    """coef bf16 [B, M, K] x proto bf16 [B, K, N] -> [B, M, N] on tcgen05 tensor cores."""
+    _require_cuda(coef, proto)
+    B, M, K = coef.shape
+    N = proto.shape[2]
+    out = torch.empty((B, M, N), dtype=out_dtype, device=coef.device)
+    with torch.cuda.device_of(coef), _timed("mask_gemm", coef):
+        rc = _lib.lib().dfine_mask_gemm_fwd(coef.data_ptr(), proto.data_ptr(), out.data_ptr(),
+                                            B, M, K, N, _dt(out, "out"), int(apply_sigmoid),
+                                            _stream(coef))
+    check(rc, "dfine_mask_gemm_fwd")
+    return out
+
+
+class _MaskFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, coef, proto, out_dtype, apply_sigmoid):
+        out = mask_gemm_raw(coef, proto, out_dtype, apply_sigmoid)
+        ctx.save_for_backward(coef, proto, out if apply_sigmoid else None)
+        ctx.apply_sigmoid = apply_sigmoid
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, go):
+        coef, proto, out = ctx.saved_tensors
+        if ctx.apply_sigmoid:
+            go = go * out * (1 - out)
+        go = go.to(torch.bfloat16)
+        # plain library GEMMs (cuBLAS) for the two gradient contractions
+        g_coef = torch.bmm(go, proto.transpose(1, 2))
+        g_proto = torch.bmm(coef.transpose(1, 2), go)
+        return g_coef, g_proto, None, None
+
+
+def mask_logits(coef: torch.Tensor, mask_feat: torch.Tensor, apply_sigmoid: bool = False,
+                out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """Drop-in for einsum("bqc,bchw->bqhw") (reference dfine_decoder.py:937-940).
+
+    Computes in bf16 with fp32 accumulation on the tensor cores, like the reference under
+    torch.autocast.  coef [B, Q, C], mask_feat [B, C, h, w] -> [B, Q, h, w].
+    """
+    B, Q, C = coef.shape
+    hh, ww = mask_feat.shape[-2:]
+    a = coef.to(torch.bfloat16).contiguous()
+    b = mask_feat.to(torch.bfloat16).reshape(B, C, hh * ww).contiguous()
+    out = _MaskFn.apply(a, b, out_dtype or torch.bfloat16, apply_sigmoid)
+    return out.reshape(B, Q, hh, ww)

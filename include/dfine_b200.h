@@ -29,6 +29,12 @@ extern "C" {
 
 #define DFINE_B200_VERSION 100 /* major*100 + minor */
 
+#if defined(__GNUC__)
+#define DFINE_API __attribute__((visibility("default")))
+#else
+#define DFINE_API
+#endif
+
 /* element types of value / grad_out / raw Linear outputs / GEMM operands */
 #define DFINE_F32 0
 #define DFINE_BF16 1
@@ -45,8 +51,8 @@ extern "C" {
 /* flags for dfine_msda_fwd / dfine_msda_bwd */
 #define DFINE_MSDA_FUSED_INPUTS 1 /* sampling inputs are raw Linear outputs + ref boxes */
 
-int dfine_version(void);
-const char* dfine_last_error(void);
+DFINE_API int dfine_version(void);
+DFINE_API const char* dfine_last_error(void);
 
 /* --------------------------------------------------------------------------
  * K1  multi-scale deformable attention, forward.
@@ -79,7 +85,7 @@ const char* dfine_last_error(void);
  *            y*w + x) of the nw, ne, sw, se corners, -1 where the corner is out of
  *            bounds (zero padding).  NULL to skip.
  * -------------------------------------------------------------------------- */
-int dfine_msda_fwd(const void* value, int64_t v_stride_b, int64_t v_stride_l,
+DFINE_API int dfine_msda_fwd(const void* value, int64_t v_stride_b, int64_t v_stride_l,
                    const int32_t* lvl_hw, const int32_t* lvl_start, const int32_t* lvl_npts,
                    int n_lvl, const void* samp, const void* attn, const float* ref_boxes,
                    const float* pts_scale, float offset_scale, void* out, int32_t* idx_debug,
@@ -103,7 +109,7 @@ int dfine_msda_fwd(const void* value, int64_t v_stride_b, int64_t v_stride_l,
  * No gradient is produced for ref_boxes: the reference detaches them
  * (dfine_decoder.py:465, :514).
  * -------------------------------------------------------------------------- */
-int dfine_msda_bwd(const void* value, int64_t v_stride_b, int64_t v_stride_l,
+DFINE_API int dfine_msda_bwd(const void* value, int64_t v_stride_b, int64_t v_stride_l,
                    const int32_t* lvl_hw, const int32_t* lvl_start, const int32_t* lvl_npts,
                    int n_lvl, const void* samp, const void* attn, const float* ref_boxes,
                    const float* pts_scale, float offset_scale, const void* grad_out,
@@ -112,7 +118,7 @@ int dfine_msda_bwd(const void* value, int64_t v_stride_b, int64_t v_stride_l,
                    void* stream);
 
 /* Packs fp32 grad_value [n] to bf16 (AMP: the gradient of a bf16 `memory`). */
-int dfine_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+DFINE_API int dfine_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 
 /* --------------------------------------------------------------------------
  * K3  FDR: weighting function, Integral and distance2bbox.
@@ -135,12 +141,12 @@ int dfine_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream)
  *   grad_boxes float32 [N,4] or NULL;  grad_dist float32 [N,4] or NULL (added)
  *   grad_corners float32 [N, 4*(reg_max+1)]
  * -------------------------------------------------------------------------- */
-int dfine_fdr_project(const float* up, const float* reg_scale, float* project, int reg_max,
+DFINE_API int dfine_fdr_project(const float* up, const float* reg_scale, float* project, int reg_max,
                       void* stream);
-int dfine_fdr_fwd(const void* corners, int c_dtype, const float* ref_init, const float* project,
+DFINE_API int dfine_fdr_fwd(const void* corners, int c_dtype, const float* ref_init, const float* project,
                   const float* reg_scale, float* dist, float* boxes, int64_t N, int reg_max,
                   void* stream);
-int dfine_fdr_bwd(const void* corners, int c_dtype, const float* ref_init, const float* project,
+DFINE_API int dfine_fdr_bwd(const void* corners, int c_dtype, const float* ref_init, const float* project,
                   const float* reg_scale, const float* grad_boxes, const float* grad_dist,
                   float* grad_corners, int64_t N, int reg_max, void* stream);
 
@@ -153,15 +159,12 @@ int dfine_fdr_bwd(const void* corners, int c_dtype, const float* ref_init, const
  * coef   bf16 [B, M, K]   mask_embed (row-major, K contiguous)
  * proto  bf16 [B, K, N]   mask_feat flattened over (h, w), N contiguous
  * out    out_dtype [B, M, N]
- * K must be a multiple of 64, N a multiple of 8; M is arbitrary.
- * `tensormaps` is caller-owned HOST scratch of DFINE_MASK_TMAP_BYTES bytes (the
- * library encodes its TMA descriptors there; they are passed to the kernel by
- * value, so the scratch may be reused as soon as the call returns).
+ * K must be a multiple of 64 (<= 512), N a multiple of 8; M is arbitrary.  All three
+ * base pointers must be 16-byte aligned.  TMA descriptors are encoded on the host inside
+ * the call and passed to the kernel by value.
  * -------------------------------------------------------------------------- */
-#define DFINE_MASK_TMAP_BYTES 512
-int dfine_mask_gemm_fwd(const void* coef, const void* proto, void* out, int B, int M, int K,
-                        int N, int out_dtype, int apply_sigmoid, void* tensormaps,
-                        void* stream);
+DFINE_API int dfine_mask_gemm_fwd(const void* coef, const void* proto, void* out, int B, int M, int K,
+                        int N, int out_dtype, int apply_sigmoid, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,352 @@
+"""GPU parity tests (run with `-m gpu` on a B200): the CUDA kernels, called through the
+C-ABI of libdfine_b200.so, against (a) the golden vectors produced by the unmodified
+reference, (b) the CPU oracle on seeded inputs, and (c) size-independent properties at the
+BASELINE.json sizes.  Tolerances are the ones north_star states: corner indices bit-exact,
+fp32 1e-5 relative, bf16 1e-2 relative (relative to the tensor's max magnitude).
+"""
+import numpy as np
+import pytest
+import torch
+
+from util import BF16_RTOL, FP32_RTOL, assert_close, bf16_bits_to_f32, golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+CORE_CASES = ["core_m_small", "core_n_small", "core_x444", "core_edge"]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "-m gpu tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def _t(a, dev, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    return t.to(dtype) if dtype is not None else t
+
+
+def _core_case(name, dev, vdtype):
+    import dfine_b200.ops as ops
+    g = golden(name)
+    H, c = int(g["H"]), int(g["c"])
+    mem = _t(bf16_bits_to_f32(g["memory_bf16"]), dev, vdtype)
+    go = _t(bf16_bits_to_f32(g["grad_out_bf16"]), dev)
+    spec = ops.level_spec(g["shapes"].tolist(), g["npts"].tolist())
+    return g, ops, spec, H, mem, _t(g["loc"], dev), _t(g["attn"], dev), go
+
+
+@pytest.mark.parametrize("vdtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("name", CORE_CASES)
+def test_core_forward_golden_and_indices(name, vdtype, dev):
+    from oracle import cpu_oracle as O
+    g, ops, spec, H, mem, loc, attn, _ = _core_case(name, dev, vdtype)
+    out, idx = ops.msda_forward_raw(mem, spec, H, loc, attn, None, None, 0.5, False,
+                                    torch.float32, want_idx=True)
+    # inputs are bf16-representable, accumulation is fp32 in both modes: same tolerance
+    assert_close(out.cpu().numpy(), g["out"], FP32_RTOL, "out")
+    B, L, C = mem.shape
+    _, o_idx, _ = O.msda_fwd(mem.float().cpu().numpy().reshape(B, L, H, C // H), g["shapes"],
+                             g["npts"], g["loc"], g["attn"], want_idx=True)
+    assert np.array_equal(idx.cpu().numpy(), o_idx), "corner indices / level offsets not bit-exact"
+
+
+@pytest.mark.parametrize("vdtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("name", CORE_CASES)
+def test_core_backward_golden(name, vdtype, dev):
+    g, ops, spec, H, mem, loc, attn, go = _core_case(name, dev, vdtype)
+    gm, gl, ga = ops.msda_backward_raw(mem, spec, H, loc, attn, None, None, 0.5, False, go)
+    assert_close(gm.cpu().numpy(), g["grad_memory"], FP32_RTOL, "grad_value")
+    assert_close(gl.cpu().numpy(), g["grad_loc"], FP32_RTOL, "grad_loc")
+    assert_close(ga.cpu().numpy(), g["grad_attn"], FP32_RTOL, "grad_attn")
+    # bf16 grad_out (pure-bf16 models)
+    gm2, gl2, ga2 = ops.msda_backward_raw(mem, spec, H, loc, attn, None, None, 0.5, False,
+                                          go.to(torch.bfloat16))
+    assert_close(gm2.cpu().numpy(), g["grad_memory"], FP32_RTOL, "grad_value (bf16 go)")
+    assert_close(ga2.cpu().numpy(), g["grad_attn"], FP32_RTOL, "grad_attn (bf16 go)")
+
+
+def test_core_autograd_through_value_views(dev):
+    """The drop-in core called exactly like the reference does: value = tuple of strided
+    views from value_op; gradients must reach `memory` through the zero-copy route."""
+    import dfine_b200
+    from oracle import torch_port as TP
+    g = golden("core_m_small")
+    H = int(g["H"])
+    mem = _t(bf16_bits_to_f32(g["memory_bf16"]), dev).requires_grad_(True)
+    loc = _t(g["loc"], dev).requires_grad_(True)
+    attn = _t(g["attn"], dev).requires_grad_(True)
+    shapes, npts = g["shapes"].tolist(), g["npts"].tolist()
+    value = TP.value_views(mem, H, shapes)
+    assert not value[0].is_contiguous()
+    out = dfine_b200.msda_core(value, shapes, loc, attn, npts)
+    assert out.shape == g["out"].shape and out.dtype == torch.float32
+    out.backward(_t(bf16_bits_to_f32(g["grad_out_bf16"]), dev))
+    assert_close(out.detach().cpu().numpy(), g["out"], FP32_RTOL, "out")
+    assert_close(mem.grad.cpu().numpy(), g["grad_memory"], FP32_RTOL, "grad_memory")
+    assert_close(loc.grad.cpu().numpy(), g["grad_loc"], FP32_RTOL, "grad_loc")
+    assert_close(attn.grad.cpu().numpy(), g["grad_attn"], FP32_RTOL, "grad_attn")
+    # packed (non zero-copy) route: values cloned level by level
+    mem2 = mem.detach().clone().requires_grad_(True)
+    value2 = tuple(v.clone() for v in TP.value_views(mem2, H, shapes))
+    out2 = dfine_b200.msda_core(value2, shapes, loc.detach(), attn.detach(), npts)
+    out2.backward(_t(bf16_bits_to_f32(g["grad_out_bf16"]), dev))
+    assert_close(mem2.grad.cpu().numpy(), g["grad_memory"], FP32_RTOL, "grad_memory (packed)")
+
+
+@pytest.mark.parametrize("name", ["module_m_small", "module_n_small"])
+def test_module_mirror_matches_reference(name, dev):
+    """dfine_b200.MSDeformableAttention loaded from the reference module's state dict."""
+    import dfine_b200
+    from oracle import torch_port as TP
+    g = golden(name)
+    H = int(g["H"])
+    shapes, npts = g["shapes"].tolist(), g["npts"].tolist()
+    mem = _t(bf16_bits_to_f32(g["memory_bf16"]), dev).requires_grad_(True)
+    C = mem.shape[-1]
+    m = dfine_b200.MSDeformableAttention(C, H, len(shapes), npts).to(dev)
+    assert sorted(m.state_dict().keys()) == [str(k) for k in g["state_dict_keys"]]
+    m.load_state_dict({"sampling_offsets.weight": _t(g["so_w"], dev),
+                       "sampling_offsets.bias": _t(g["so_b"], dev),
+                       "attention_weights.weight": _t(g["aw_w"], dev),
+                       "attention_weights.bias": _t(g["aw_b"], dev),
+                       "num_points_scale": _t(g["num_points_scale"], dev)})
+    q = _t(g["query"], dev).requires_grad_(True)
+    ref = _t(g["ref_points"], dev)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    out = m(q, ref, TP.value_views(mem, H, shapes), shapes)
+    out.backward(_t(bf16_bits_to_f32(g["grad_out_bf16"]), dev))
+    assert_close(out.detach().cpu().numpy(), g["out"], FP32_RTOL, "out")
+    assert_close(mem.grad.cpu().numpy(), g["grad_memory"], FP32_RTOL, "grad_memory")
+    # gradients that went through cuBLAS GEMMs: summation order differs, 5e-5
+    assert_close(q.grad.cpu().numpy(), g["grad_query"], 5e-5, "grad_query")
+    assert_close(m.sampling_offsets.weight.grad.cpu().numpy(), g["g_so_w"], 5e-5, "g_so_w")
+    assert_close(m.sampling_offsets.bias.grad.cpu().numpy(), g["g_so_b"], 5e-5, "g_so_b")
+    assert_close(m.attention_weights.weight.grad.cpu().numpy(), g["g_aw_w"], 5e-5, "g_aw_w")
+    assert_close(m.attention_weights.bias.grad.cpu().numpy(), g["g_aw_b"], 5e-5, "g_aw_b")
+    with pytest.raises(ValueError):
+        m(q, ref[..., :3], TP.value_views(mem, H, shapes), shapes)
+
+
+@pytest.mark.parametrize("name", ["module_m_small", "module_n_small"])
+def test_fused_kernel_from_raw_outputs(name, dev):
+    """Fused-input kernels fed with the reference's own raw Linear outputs (fp32), and with
+    bf16-rounded raw outputs + bf16 value (the AMP layout)."""
+    import dfine_b200.ops as ops
+    from oracle import cpu_oracle as O
+    g = golden(name)
+    H = int(g["H"])
+    shapes, npts = g["shapes"].tolist(), g["npts"].tolist()
+    spec = ops.level_spec(shapes, npts)
+    mem32 = bf16_bits_to_f32(g["memory_bf16"])
+    B, L, C = mem32.shape
+    go = bf16_bits_to_f32(g["grad_out_bf16"])
+    ref = _t(g["ref_points"].reshape(B, -1, 4), dev)
+    nps = _t(g["num_points_scale"], dev)
+    osc = float(g["offset_scale"])
+    # fp32
+    out = ops.msda_forward_raw(_t(mem32, dev), spec, H, _t(g["raw_off"], dev), _t(g["raw_logit"], dev),
+                               ref, nps, osc, True, torch.float32)
+    assert_close(out.cpu().numpy(), g["out"], FP32_RTOL, "fused out")
+    gm, gs, ga = ops.msda_backward_raw(_t(mem32, dev), spec, H, _t(g["raw_off"], dev),
+                                       _t(g["raw_logit"], dev), ref, nps, osc, True, _t(go, dev))
+    o_gv, o_goff, o_glog = O.msda_fused_bwd(mem32.reshape(B, L, H, C // H), shapes, npts, g["raw_off"],
+                                            g["raw_logit"], g["ref_points"], g["num_points_scale"], go, osc)
+    assert_close(gm.cpu().numpy(), g["grad_memory"], FP32_RTOL, "fused grad_memory")
+    assert_close(gs.cpu().numpy(), o_goff, FP32_RTOL, "fused grad raw offsets")
+    assert_close(ga.cpu().numpy(), o_glog, FP32_RTOL, "fused grad raw logits")
+    # AMP layout: bf16 value, bf16 raw Linear outputs; the oracle gets the same rounded inputs
+    off_bf = _t(g["raw_off"], dev, torch.bfloat16)
+    log_bf = _t(g["raw_logit"], dev, torch.bfloat16)
+    out_bf, idx = ops.msda_forward_raw(_t(mem32, dev, torch.bfloat16), spec, H, off_bf, log_bf, ref,
+                                       nps, osc, True, torch.float32, want_idx=True)
+    off_r, log_r = off_bf.float().cpu().numpy(), log_bf.float().cpu().numpy()
+    loc_r = O.msda_locations(off_r, g["ref_points"], g["num_points_scale"], osc)
+    o_out, o_idx, _ = O.msda_fwd(mem32.reshape(B, L, H, C // H), shapes, npts, loc_r,
+                                 O.softmax(log_r), want_idx=True)
+    assert np.array_equal(idx.cpu().numpy(), o_idx), "AMP-mode corner indices not bit-exact"
+    assert_close(out_bf.cpu().numpy(), o_out, FP32_RTOL, "AMP out vs oracle on rounded inputs")
+    assert_close(out_bf.cpu().numpy(), g["out"], BF16_RTOL, "AMP out vs fp32 reference")
+
+
+def test_aten_cuda_probe_indices(dev):
+    """Touched-pixel sets of aten::grid_sampler_2d ON THIS GPU vs the kernel's corner dump."""
+    import dfine_b200.ops as ops
+    g = golden("aten_corner_probe")
+    h, w = [int(v) for v in g["hw"]]
+    loc = _t(g["loc"], dev)
+    n = loc.shape[0]
+    inp = torch.ones(n, 1, h, w, device=dev, requires_grad=True)
+    out = torch.nn.functional.grid_sample(inp, (2 * loc - 1).reshape(n, 1, 1, 2), mode="bilinear",
+                                          padding_mode="zeros", align_corners=False)
+    out.sum().backward()
+    aten = inp.grad.reshape(n, h * w)
+    spec = ops.level_spec([[h, w]], [1])
+    value = torch.ones(1, h * w, 1 * 16, device=dev)  # H=1, c=16
+    attn = torch.ones(1, n, 1, 1, device=dev)
+    o, idx = ops.msda_forward_raw(value, spec, 1, loc.reshape(1, n, 1, 1, 2).contiguous(), attn,
+                                  None, None, 0.5, False, torch.float32, want_idx=True)
+    idx = idx.reshape(n, 4).cpu().numpy()
+    touched = np.zeros((n, h * w), bool)
+    for j in range(4):
+        ok = idx[:, j] >= 0
+        touched[np.nonzero(ok)[0], idx[ok, j]] = True
+    aten_nz = aten.cpu().numpy() != 0
+    # every pixel ATen touched with non-zero weight must be one of our corners; our extra
+    # corners may only be zero-weight ones (invisible to the probe)
+    assert not (aten_nz & ~touched).any(), "ATen touched a pixel outside our corner set"
+    assert np.array_equal(aten_nz, g["grad_input"] != 0), "ATen CUDA and ATen CPU disagree"
+    assert_close(o[0, :, 0].cpu().numpy(), g["out"], FP32_RTOL, "probe out")
+
+
+def test_fdr_golden(dev):
+    import dfine_b200
+    g = golden("fdr")
+    for tag in ("m", "x", "odd"):
+        up, rs = [float(v) for v in g[f"up_rs_{tag}"]]
+        proj = dfine_b200.fdr_project(torch.tensor([up], device=dev), torch.tensor([rs], device=dev), 32)
+        assert_close(proj.cpu().numpy(), g[f"project_{tag}"], FP32_RTOL, f"project {tag}")
+    corners = _t(g["corners"], dev).requires_grad_(True)
+    ref = _t(g["ref_init"], dev)
+    project = _t(g["project"], dev)
+    rs = torch.tensor([float(g["reg_scale"])], device=dev)
+    dist = dfine_b200.fdr_integral(corners, project, 32)
+    assert_close(dist.detach().cpu().numpy(), g["dist"], FP32_RTOL, "integral")
+    boxes, dist2 = dfine_b200.fdr_decode(corners, ref, project, rs, 32, return_dist=True)
+    assert_close(boxes.detach().cpu().numpy(), g["boxes"], FP32_RTOL, "boxes")
+    (boxes * _t(g["grad_boxes"], dev)).sum().backward()
+    assert_close(corners.grad.cpu().numpy(), g["grad_corners_from_boxes"], FP32_RTOL, "gc boxes")
+    corners.grad = None
+    boxes, dist2 = dfine_b200.fdr_decode(corners, ref, project, rs, 32, return_dist=True)
+    ((boxes * _t(g["grad_boxes"], dev)).sum() + (dist2 * _t(g["grad_dist"], dev)).sum()).backward()
+    assert_close(corners.grad.cpu().numpy(), g["grad_corners_from_both"], FP32_RTOL, "gc both")
+    # bf16 logits (AMP): same inputs are bf16-representable
+    b16 = dfine_b200.fdr_decode(corners.detach().to(torch.bfloat16), ref, project, rs, 32)
+    assert_close(b16.cpu().numpy(), g["boxes"], FP32_RTOL, "boxes from bf16 logits")
+
+
+def test_msda_vs_oracle_full_resolution(dev):
+    """640x640 level shapes (80/40/20), B=2, Lq=300, seeded inputs, against the CPU oracle."""
+    import dfine_b200.ops as ops
+    from oracle import cpu_oracle as O
+    rng = np.random.default_rng(3)
+    B, Lq, H, c = 2, 300, 8, 32
+    shapes, npts = [[80, 80], [40, 40], [20, 20]], [3, 6, 3]
+    spec = ops.level_spec(shapes, npts)
+    mem = torch.from_numpy(rng.standard_normal((B, spec.L, H * c), dtype=np.float32)).to(torch.bfloat16)
+    raw_off = torch.from_numpy(rng.standard_normal((B, Lq, H, 12, 2), dtype=np.float32) * 2).to(torch.bfloat16)
+    raw_log = torch.from_numpy(rng.standard_normal((B, Lq, H, 12), dtype=np.float32)).to(torch.bfloat16)
+    ref = np.concatenate([rng.uniform(-0.05, 1.05, (B, Lq, 2)), rng.uniform(0.02, 0.9, (B, Lq, 2))], -1).astype(np.float32)
+    nps = np.asarray([1 / 3] * 3 + [1 / 6] * 6 + [1 / 3] * 3, np.float32)
+    go = rng.standard_normal((B, Lq, H * c), dtype=np.float32)
+    args = (spec, H, raw_off.to(dev), raw_log.to(dev), _t(ref, dev), _t(nps, dev), 0.5, True)
+    out, idx = ops.msda_forward_raw(mem.to(dev), *args, torch.float32, want_idx=True)
+    gm, gs, ga = ops.msda_backward_raw(mem.to(dev), *args, _t(go, dev))
+    m32 = mem.float().numpy().reshape(B, spec.L, H, c)
+    loc = O.msda_locations(raw_off.float().numpy(), ref, nps, 0.5)
+    attn = O.softmax(raw_log.float().numpy())
+    o_out, o_idx, _ = O.msda_fwd(m32, shapes, npts, loc, attn, want_idx=True)
+    o_gv, o_gs, o_ga = O.msda_fused_bwd(m32, shapes, npts, raw_off.float().numpy(), raw_log.float().numpy(),
+                                        ref, nps, go, 0.5)
+    assert np.array_equal(idx.cpu().numpy(), o_idx)
+    assert (o_idx < 0).mean() > 0.01, "test should exercise out-of-bounds corners"
+    assert_close(out.cpu().numpy(), o_out, FP32_RTOL, "out")
+    assert_close(gm.cpu().numpy().reshape(o_gv.shape), o_gv, FP32_RTOL, "grad_value")
+    assert_close(gs.cpu().numpy(), o_gs, FP32_RTOL, "grad_offsets")
+    assert_close(ga.cpu().numpy(), o_ga, FP32_RTOL, "grad_logits")
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(name="config3 m train", B=32, Lq=500, shapes=[[80, 80], [40, 40], [20, 20]], npts=[3, 6, 3]),
+    dict(name="config5 x 1024", B=8, Lq=500, shapes=[[128, 128], [64, 64], [32, 32]], npts=[4, 4, 4]),
+])
+def test_full_size_properties(cfg, dev):
+    """BASELINE.json sizes, bf16 value: (1) against eager PyTorch (F.grid_sample restatement)
+    on the same GPU, (2) the adjoint identity <out(V), G> == <V, grad_value(G)> which holds
+    for any size because the op is linear in V, (3) attention weights sum to one => sampling
+    a constant map returns the constant wherever all corners are in bounds."""
+    import dfine_b200.ops as ops
+    from oracle import torch_port as TP
+    torch.manual_seed(0)
+    B, Lq, H, c = cfg["B"], cfg["Lq"], 8, 32
+    shapes, npts = cfg["shapes"], cfg["npts"]
+    spec = ops.level_spec(shapes, npts)
+    P = spec.P
+    mem = torch.randn(B, spec.L, H * c, device=dev).to(torch.bfloat16)
+    ref = torch.cat([torch.rand(B, Lq, 2, device=dev) * 0.9 + 0.05,
+                     torch.rand(B, Lq, 2, device=dev) * 0.4 + 0.02], -1)
+    raw_off = (torch.randn(B, Lq, H, P, 2, device=dev)).to(torch.bfloat16)
+    raw_log = torch.randn(B, Lq, H, P, device=dev).to(torch.bfloat16)
+    nps = torch.tensor([1.0 / n for n in npts for _ in range(n)], device=dev)
+    G = torch.randn(B, Lq, H * c, device=dev)
+    out = ops.msda_forward_raw(mem, spec, H, raw_off, raw_log, ref, nps, 0.5, True, torch.float32)
+    gm, gs, ga = ops.msda_backward_raw(mem, spec, H, raw_off, raw_log, ref, nps, 0.5, True, G)
+    # (1) eager reference on the GPU (fp32 math on the same bf16-rounded inputs)
+    m32 = mem.float().requires_grad_(True)
+    ro, rl = raw_off.float().requires_grad_(True), raw_log.float().requires_grad_(True)
+    want = TP.msda_from_raw(ro, rl, ref.unsqueeze(2), TP.value_views(m32, H, shapes), shapes, nps, npts)
+    want.backward(G)
+    assert rel_err(out.cpu().numpy(), want.detach().cpu().numpy()) <= FP32_RTOL
+    assert rel_err(gm.cpu().numpy(), m32.grad.cpu().numpy()) <= FP32_RTOL
+    assert rel_err(gs.cpu().numpy(), ro.grad.cpu().numpy()) <= 2e-5
+    assert rel_err(ga.cpu().numpy(), rl.grad.cpu().numpy()) <= 2e-5
+    # (2) adjoint identity in float64
+    lhs = (out.double() * G.double()).sum().item()
+    rhs = (mem.double() * gm.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-6 * max(abs(lhs), abs(rhs), 1.0), (lhs, rhs)
+    # (3) constant map
+    ones = torch.ones_like(mem)
+    o1, idx = ops.msda_forward_raw(ones, spec, H, raw_off, raw_log, ref, nps, 0.5, True,
+                                   torch.float32, want_idx=True)
+    inb = (idx >= 0).all(-1).all(-1)  # [B, Lq, H]: every corner of every point in bounds
+    assert inb.float().mean() > 0.3
+    got = o1.reshape(B, Lq, H, c)[inb]
+    assert (got - 1.0).abs().max().item() <= 1e-5
+
+
+def test_mask_gemm(dev):
+    """tcgen05 GEMM vs golden (reference einsum on bf16-representable inputs) and vs
+    torch.bmm at the config-4 shape; bf16 products are exact in fp32, so only the
+    accumulation order differs."""
+    import dfine_b200
+    import dfine_b200.ops as ops
+    g = golden("mask")
+    coef, proto = _t(g["coef"], dev), _t(g["proto"], dev)
+    out = dfine_b200.mask_logits(coef, proto, out_dtype=torch.float32)
+    assert_close(out.cpu().numpy(), g["logits"], 2e-5, "mask logits (fp32 out)")
+    out_b = dfine_b200.mask_logits(coef, proto)
+    assert out_b.dtype == torch.bfloat16
+    assert_close(out_b.float().cpu().numpy(), g["logits"], BF16_RTOL, "mask logits (bf16 out)")
+    prob = dfine_b200.mask_logits(coef, proto, apply_sigmoid=True, out_dtype=torch.float32)
+    assert_close(prob.cpu().numpy(), g["probs"], 2e-5, "mask probs")
+    torch.manual_seed(1)
+    for (B, M, K, N) in [(2, 500, 256, 160 * 160), (1, 300, 256, 160 * 160), (3, 200, 128, 1000), (1, 77, 64, 264)]:
+        a = torch.randn(B, M, K, device=dev).to(torch.bfloat16)
+        b = torch.randn(B, K, N, device=dev).to(torch.bfloat16)
+        got = ops.mask_gemm_raw(a, b, torch.float32, False)
+        want = torch.bmm(a.float(), b.float())
+        assert rel_err(got.cpu().numpy(), want.cpu().numpy()) <= 2e-5, (B, M, K, N)
+        gotb = ops.mask_gemm_raw(a, b, torch.bfloat16, False)
+        assert rel_err(gotb.float().cpu().numpy(), want.cpu().numpy()) <= BF16_RTOL, (B, M, K, N)
+    # autograd (gradients are plain cuBLAS GEMMs)
+    a = torch.randn(2, 50, 64, device=dev, requires_grad=True)
+    b = torch.randn(2, 64, 8, 16, device=dev, requires_grad=True)
+    dfine_b200.mask_logits(a, b, out_dtype=torch.float32).sum().backward()
+    assert a.grad.shape == a.shape and b.grad.shape == b.shape
+
+
+def test_error_behaviour(dev):
+    import dfine_b200
+    import dfine_b200.ops as ops
+    spec = ops.level_spec([[4, 4]], [2])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        dfine_b200.msda_core(torch.zeros(1, 16, 2, 16), [[4, 4]], torch.zeros(1, 1, 2, 2, 2),
+                             torch.zeros(1, 1, 2, 2), [2])
+    with pytest.raises(dfine_b200.DfineB200Error, match="head_dim"):
+        ops.msda_forward_raw(torch.zeros(1, 16, 2 * 24, device=dev), spec, 2,
+                             torch.zeros(1, 1, 2, 2, 2, device=dev), torch.zeros(1, 1, 2, 2, device=dev),
+                             None, None, 0.5, False, torch.float32)
+    with pytest.raises(NotImplementedError):
+        dfine_b200.msda_core(torch.zeros(1, 16, 2, 16, device=dev), [[4, 4]],
+                             torch.zeros(1, 1, 2, 2, 2, device=dev), torch.zeros(1, 1, 2, 2, device=dev),
+                             [2], method="discrete")

@@ -1,0 +1,161 @@
+"""CPU-side tests: the C-ABI symbol table, argument validation (no compute calls), the
+zero-copy recovery of `memory` behind value_op's views, model patching, and the
+world_size-2 (gloo) logic of bench.py."""
+import ctypes
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFERENCE = "/root/reference"
+
+
+def test_cabi_exports_every_declared_symbol():
+    import dfine_b200
+    from dfine_b200 import build
+    build.build()
+    header = open(os.path.join(ROOT, "include", "dfine_b200.h")).read()
+    declared = re.findall(r"^DFINE_API\s+[\w\s\*]+?\b(dfine_\w+)\s*\(", header, flags=re.M)
+    assert len(declared) >= 9
+    lib = ctypes.CDLL(dfine_b200.library_path())
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/dfine_b200.h but not exported"
+    assert sorted(declared) == dfine_b200._lib.exported_symbols()
+    assert dfine_b200._lib.lib().dfine_version() == 100
+
+
+def test_argument_validation_without_gpu():
+    """Bad arguments are rejected before any CUDA call: negative return + message."""
+    from dfine_b200 import _lib
+    lib = _lib.lib()
+    hw, st, npts = _lib.i32_array([4, 4]), _lib.i32_array([0]), _lib.i32_array([2])
+    rc = lib.dfine_msda_fwd(None, 0, 0, hw, st, npts, 1, None, None, None, None, 0.5, None, None,
+                            0, 1, 1, 32, 0, 0, 0, 0, None)
+    assert rc == -2 and b"positive" in lib.dfine_last_error()
+    rc = lib.dfine_msda_fwd(None, 0, 0, hw, st, npts, 9, None, None, None, None, 0.5, None, None,
+                            1, 1, 1, 32, 0, 0, 0, 0, None)
+    assert rc == -3 and b"n_lvl" in lib.dfine_last_error()
+    rc = lib.dfine_msda_fwd(None, 0, 0, hw, st, _lib.i32_array([40]), 1, None, None, None, None, 0.5,
+                            None, None, 1, 1, 1, 32, 0, 0, 0, 0, None)
+    assert rc == -3 and b"sampling points" in lib.dfine_last_error()
+    rc = lib.dfine_msda_fwd(None, 0, 0, hw, st, npts, 1, None, None, None, None, 0.5, None, None,
+                            1, 1, 1, 32, 0, 0, 0, 0, None)
+    assert rc == -1 and b"NULL" in lib.dfine_last_error()
+    assert lib.dfine_mask_gemm_fwd(None, None, None, 1, 8, 100, 64, 1, 0, None) == -3
+    assert lib.dfine_fdr_project(None, None, None, 31, None) == -2
+    with pytest.raises(_lib.DfineB200Error):
+        _lib.check(rc, "probe")
+
+
+def test_cpu_tensors_are_rejected():
+    import dfine_b200
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        dfine_b200.fdr_integral(torch.zeros(3, 132), torch.zeros(33))
+    m = dfine_b200.MSDeformableAttention(64, 4, 2, [2, 2])
+    with pytest.raises(ValueError, match="Last dim of reference_points"):
+        m(torch.zeros(1, 3, 64), torch.zeros(1, 3, 1, 3), torch.zeros(1, 20, 4, 16), [[4, 4], [2, 2]])
+    with pytest.raises(AssertionError):
+        dfine_b200.MSDeformableAttention(64, 4, 3, [2, 2])
+
+
+def test_memory_recovered_zero_copy_from_value_views():
+    from dfine_b200 import ops
+    B, H, c = 2, 4, 16
+    shapes, npts = [[3, 5], [2, 2]], [2, 1]
+    spec = ops.level_spec(shapes, npts)
+    assert (spec.L, spec.P, spec.starts) == (19, 3, [0, 15])
+    mem = torch.randn(B, spec.L, H * c, requires_grad=True)
+    views = mem.reshape(B, spec.L, H, c).permute(0, 2, 3, 1).split(spec.sizes, dim=-1)
+    base, h2, c2, zero_copy = ops.memory_from_value(views, spec)
+    assert zero_copy and base is mem and (h2, c2) == (H, c)
+    # anything else is packed into the same layout
+    clones = tuple(v.clone() for v in views)
+    packed, _, _, zero_copy = ops.memory_from_value(clones, spec)
+    assert not zero_copy and torch.equal(packed, mem.detach())
+    sliced = torch.randn(B, spec.L + 3, H * c)[:, :spec.L]
+    v2 = sliced.reshape(B, spec.L, H, c).permute(0, 2, 3, 1).split(spec.sizes, dim=-1)
+    packed, _, _, zero_copy = ops.memory_from_value(v2, spec)
+    assert not zero_copy and torch.equal(packed, sliced)
+    with pytest.raises(ValueError):
+        ops.memory_from_value(views[:1], spec)
+
+
+def test_module_mirror_has_reference_parameters():
+    import dfine_b200
+    m = dfine_b200.MSDeformableAttention(256, 8, 3, [3, 6, 3])
+    sd = m.state_dict()
+    assert sorted(sd) == ["attention_weights.bias", "attention_weights.weight", "num_points_scale",
+                          "sampling_offsets.bias", "sampling_offsets.weight"]
+    assert sd["sampling_offsets.weight"].shape == (8 * 12 * 2, 256)
+    assert sd["attention_weights.weight"].shape == (8 * 12, 256)
+    assert torch.allclose(sd["num_points_scale"], torch.tensor([1 / 3] * 3 + [1 / 6] * 6 + [1 / 3] * 3))
+    assert float(sd["sampling_offsets.weight"].abs().max()) == 0.0
+    if os.path.isdir(REFERENCE):
+        sys.path.insert(0, REFERENCE)
+        from src.d_fine.arch.dfine_decoder import MSDeformableAttention as Ref
+        torch.manual_seed(0)
+        r = Ref(256, 8, 3, [3, 6, 3])
+        for k, v in r.state_dict().items():
+            assert torch.allclose(sd[k], v, atol=1e-6), k
+        m.load_state_dict(r.state_dict(), strict=True)
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference tree not present")
+def test_patch_model_keeps_reference_checkpoint_format():
+    import dfine_b200
+    sys.path.insert(0, REFERENCE)
+    from src.d_fine.dfine import build_model
+    torch.manual_seed(0)
+    model = build_model("n", 80, True, "cpu", img_size=[640, 640])
+    keys = list(model.state_dict().keys())
+    n = dfine_b200.patch_model(model)
+    assert n["msda"] == 3 and n["integral"] == 1 and n["mask"] == 1
+    assert list(model.state_dict().keys()) == keys
+    assert "decoder.decoder.layers.0.cross_attn.num_points_scale" in keys
+    layer = model.decoder.decoder.layers[0].cross_attn
+    assert layer.ms_deformable_attn_core.func is dfine_b200.ops.msda_core
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model.eval()(torch.rand(1, 3, 640, 640))  # the patched path refuses CPU tensors
+    dfine_b200.unpatch_model(model)
+    with torch.no_grad():
+        out = model.eval()(torch.rand(1, 3, 640, 640))  # reference path restored
+    assert out["pred_boxes"].shape == (1, 300, 4)
+    import copy
+    dfine_b200.patch_model(model)
+    copy.deepcopy(model)  # EMA deep-copies the model (reference src/dl/train.py:56)
+
+
+def _gloo_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    import bench
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ms = bench.max_over_ranks(10.0 * (rank + 1), torch.device("cpu"), True)
+    wl = dict(bench.WORKLOADS[bench.DEFAULT_WORKLOAD], B=1, Lq=3, layers=1, shapes=[[2, 2]], npts=[1])
+    inp = bench.make_inputs(wl, 1, bench.rank_seed(rank), "cpu")
+    q.put((rank, ms, float(inp["memory"].sum()), bench.job_throughput(32, world, 4, ms)))
+    dist.destroy_process_group()
+
+
+def test_bench_multi_rank_logic_gloo():
+    """world_size 2 over gloo: ranks draw different shards, the step time is the max over
+    ranks and the reported throughput is the whole-job aggregate."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in procs)
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    (r0, ms0, sum0, thr0), (r1, ms1, sum1, thr1) = res
+    assert ms0 == ms1 == 20.0
+    assert sum0 != sum1
+    assert thr0 == thr1 == 32 * 2 * 4 / 0.020
