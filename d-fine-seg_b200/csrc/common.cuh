@@ -65,25 +65,40 @@ __device__ __forceinline__ float load_scalar(const void* p, size_t i, int is_bf1
                  : reinterpret_cast<const float*>(p)[i];
 }
 
-// 16-byte read-only vector load of VPL elements, widened to float.
+// 16-byte read-only vector load of VPL elements; widened to float only when consumed so
+// that loads in flight stay packed in registers.
 template <typename VT> struct Vec16;
 template <> struct Vec16<float> {
   static constexpr int kElems = 4;
-  __device__ static __forceinline__ void load(const float* p, float (&v)[4]) {
-    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+  using Raw = float4;
+  __device__ static __forceinline__ Raw load_raw(const float* p) {
+    return __ldg(reinterpret_cast<const float4*>(p));
+  }
+  __device__ static __forceinline__ Raw zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ static __forceinline__ void unpack(const Raw& t, float (&v)[4]) {
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  __device__ static __forceinline__ void load(const float* p, float (&v)[4]) {
+    unpack(load_raw(p), v);
   }
 };
 template <> struct Vec16<__nv_bfloat16> {
   static constexpr int kElems = 8;
-  __device__ static __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
-    const uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+  using Raw = uint4;
+  __device__ static __forceinline__ Raw load_raw(const __nv_bfloat16* p) {
+    return __ldg(reinterpret_cast<const uint4*>(p));
+  }
+  __device__ static __forceinline__ Raw zero() { return make_uint4(0u, 0u, 0u, 0u); }
+  __device__ static __forceinline__ void unpack(const Raw& t, float (&v)[8]) {
     const uint32_t u[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {  // bf16 -> f32 is a 16-bit shift
       v[2 * i] = __uint_as_float(u[i] << 16);
       v[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
     }
+  }
+  __device__ static __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+    unpack(load_raw(p), v);
   }
 };
 

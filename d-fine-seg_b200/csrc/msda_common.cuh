@@ -1,0 +1,98 @@
+// Phase 1 shared by K1 (msda_fwd.cu) and K2 (msda_bwd.cu): per sampling point, the fused
+// input arithmetic (softmax over the points of a head + sampling location from the raw
+// Linear output, reference dfine_decoder.py:144-166) and the bit-exact bilinear geometry.
+//
+// A warp handles IPW "items" (one item = one (query, head) pair of image blockIdx.y); the
+// LPI = 32/IPW lanes of an item each own one sampling point (P <= LPI).
+#pragma once
+#include "common.cuh"
+
+namespace dfine {
+
+struct PointCtx {
+  float a;            // attention weight of this lane's point (after softmax in fused mode)
+  float ps;           // fused: num_points_scale of the point
+  float4 ref;         // fused: reference box (cx, cy, w, h)
+  int lw, lh, lstart; // level of the point
+  Geometry g;
+  bool active;        // lane owns a real point of a real item
+};
+
+template <int LPI>
+__device__ __forceinline__ float group_max(float v) {
+#pragma unroll
+  for (int o = LPI / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+template <int LPI>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPI / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// item : flattened (q * H + h) index of this lane's item (warp-uniform per LPI group)
+// pl   : point index of this lane inside its item
+template <int LPI>
+__device__ __forceinline__ PointCtx point_phase(const MsdaParams& p, int b, int item, int pl,
+                                                bool item_valid) {
+  PointCtx c;
+  const int P = p.P;
+  c.active = item_valid && pl < P;
+  const int lvl = (pl >= p.lvl_pend[0]) + (pl >= p.lvl_pend[1]) + (pl >= p.lvl_pend[2]);
+  c.lw = lvl == 0 ? p.lvl_w[0] : lvl == 1 ? p.lvl_w[1] : lvl == 2 ? p.lvl_w[2] : p.lvl_w[3];
+  c.lh = lvl == 0 ? p.lvl_h[0] : lvl == 1 ? p.lvl_h[1] : lvl == 2 ? p.lvl_h[2] : p.lvl_h[3];
+  c.lstart = lvl == 0 ? p.lvl_start[0]
+                      : lvl == 1 ? p.lvl_start[1] : lvl == 2 ? p.lvl_start[2] : p.lvl_start[3];
+  // sample index inside [B, Lq, H, P]
+  const size_t s = ((size_t)b * p.Lq * p.H + item) * P + pl;
+  float lx = 0.f, ly = 0.f;
+  c.a = 0.f;
+  c.ps = 0.f;
+  c.ref = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.fused) {
+    float logit = -INFINITY;
+    if (c.active) {
+      float rx, ry;
+      if (p.samp_bf16) {
+        const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(p.samp) + s);
+        rx = __uint_as_float(u << 16);
+        ry = __uint_as_float(u & 0xffff0000u);
+        logit = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.attn)[s]);
+      } else {
+        const float2 t = __ldg(reinterpret_cast<const float2*>(p.samp) + s);
+        rx = t.x;
+        ry = t.y;
+        logit = __ldg(reinterpret_cast<const float*>(p.attn) + s);
+      }
+      const int q = item / p.H;
+      c.ref = __ldg(reinterpret_cast<const float4*>(p.ref) + (size_t)b * p.Lq + q);
+      c.ps = __ldg(p.pts_scale + pl);
+      // ((raw * num_points_scale) * ref_wh) * offset_scale, then ref_xy + offset
+      // (dfine_decoder.py:159-166), evaluated left to right without contraction.
+      lx = __fadd_rn(c.ref.x, __fmul_rn(__fmul_rn(__fmul_rn(rx, c.ps), c.ref.z), p.offset_scale));
+      ly = __fadd_rn(c.ref.y, __fmul_rn(__fmul_rn(__fmul_rn(ry, c.ps), c.ref.w), p.offset_scale));
+    }
+    // F.softmax(..., dim=-1) over the P points of this head (dfine_decoder.py:147)
+    const float m = group_max<LPI>(logit);
+    const float e = c.active ? expf(logit - m) : 0.f;
+    const float sum = group_sum<LPI>(e);
+    c.a = e / sum;
+  } else if (c.active) {
+    const float2 l2 = __ldg(reinterpret_cast<const float2*>(p.samp) + s);
+    lx = l2.x;
+    ly = l2.y;
+    c.a = __ldg(reinterpret_cast<const float*>(p.attn) + s);
+  }
+  c.g = sample_geometry(lx, ly, c.lh, c.lw);
+  return c;
+}
+
+// flattened pixel index of corner j (0 nw, 1 ne, 2 sw, 3 se) or -1 when out of bounds
+__device__ __forceinline__ int corner_pixel(const PointCtx& c, int j) {
+  const int x = c.g.x0 + (j & 1), y = c.g.y0 + (j >> 1);
+  const bool in = c.g.inrange && x >= 0 && x < c.lw && y >= 0 && y < c.lh;
+  return in ? c.lstart + y * c.lw + x : -1;
+}
+
+}  // namespace dfine

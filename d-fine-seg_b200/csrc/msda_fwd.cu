@@ -16,7 +16,7 @@
 //
 // value is read in place from `memory [B, L, H*c]` (no NCHW repack, no per-level copies,
 // no [B*H, c, Lq, P] intermediate as in the reference path).
-#include "common.cuh"
+#include "msda_common.cuh"
 
 namespace dfine {
 
@@ -55,144 +55,122 @@ struct SlotReduce {
   }
 };
 
-template <typename VT, int LPC>
+template <typename VT, int LPC, int IPW>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 msda_fwd_kernel(const MsdaParams p) {
   constexpr int VPL = Vec16<VT>::kElems;   // channels per lane
   constexpr int CPR = 32 / LPC;            // corners per warp-wide load
+  constexpr int LPI = 32 / IPW;            // lanes (= max points) per item in phase 1
   constexpr int U = 6;                     // loads in flight per lane
 
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // per warp: IPW x (4*LPI) corner records {element offset | 0xffffffff, weight*attn}
+  __shared__ __align__(16) uint2 s_rec[kWarpsPerCta][128];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int P = p.P;
-  const int ncorner = 4 * P;
-  int* s_off = reinterpret_cast<int*>(smem_raw) + warp * 2 * 4 * kMaxPoints;
-  float* s_cw = reinterpret_cast<float*>(s_off + 4 * kMaxPoints);
-
-  const long long wid = (long long)blockIdx.x * kWarpsPerCta + warp;
-  const long long total = (long long)p.B * p.Lq * p.H;
-  if (wid >= total) return;
-  const int h = (int)(wid % p.H);
-  const long long bq = wid / p.H;
-  const int b = (int)(bq / p.Lq);
+  const int b = blockIdx.y;
+  const int n_items = p.Lq * p.H;
+  const int item0 = (blockIdx.x * kWarpsPerCta + warp) * IPW;
+  if (item0 >= n_items) return;
+  const int ncorner = 4 * p.P;
 
   // ---- phase 1: per-point geometry -------------------------------------------------
   {
-    const size_t s = (size_t)wid * P + lane;
-    float lx = 0.f, ly = 0.f, a = 0.f;
-    int lvl = 0;
-    if (lane < P) {
-      while (lane >= p.lvl_pend[lvl]) ++lvl;
-    }
-    if (p.fused) {
-      float logit = -INFINITY;
-      if (lane < P) {
-        const float rx = load_scalar(p.samp, 2 * s, p.samp_bf16);
-        const float ry = load_scalar(p.samp, 2 * s + 1, p.samp_bf16);
-        logit = load_scalar(p.attn, s, p.samp_bf16);
-        const float4 r = __ldg(reinterpret_cast<const float4*>(p.ref) + bq);
-        const float ps = __ldg(p.pts_scale + lane);
-        // ((raw * num_points_scale) * ref_wh) * offset_scale, then ref_xy + offset
-        // (dfine_decoder.py:159-166), evaluated left to right without contraction.
-        lx = __fadd_rn(r.x, __fmul_rn(__fmul_rn(__fmul_rn(rx, ps), r.z), p.offset_scale));
-        ly = __fadd_rn(r.y, __fmul_rn(__fmul_rn(__fmul_rn(ry, ps), r.w), p.offset_scale));
-      }
-      // F.softmax(..., dim=-1) over the P points of this head (dfine_decoder.py:147)
-      const float m = warp_max(logit);
-      const float e = lane < P ? expf(logit - m) : 0.f;
-      const float sum = warp_sum(e);
-      a = e / sum;
-    } else if (lane < P) {
-      const float2 l2 = __ldg(reinterpret_cast<const float2*>(p.samp) + s);
-      lx = l2.x;
-      ly = l2.y;
-      a = __ldg(reinterpret_cast<const float*>(p.attn) + s);
-    }
-    if (lane < P) {
-      const int lh = p.lvl_h[lvl], lw = p.lvl_w[lvl];
-      const Geometry g = sample_geometry(lx, ly, lh, lw);
-      const float wt[4] = {g.fs * g.fe, g.fs * g.fw, g.fn * g.fe, g.fn * g.fw};
+    const int slot_i = lane / LPI, pl = lane % LPI;
+    const int item = item0 + slot_i;
+    const PointCtx c = point_phase<LPI>(p, b, item, pl, item < n_items);
+    if (c.active) {
+      const float wt[4] = {c.g.fs * c.g.fe, c.g.fs * c.g.fw, c.g.fn * c.g.fe, c.g.fn * c.g.fw};
       int pix[4];
+      uint32_t rec[8];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int x = g.x0 + (j & 1), y = g.y0 + (j >> 1);
-        const bool in = g.inrange && x >= 0 && x < lw && y >= 0 && y < lh;
-        pix[j] = in ? p.lvl_start[lvl] + y * lw + x : -1;
-        s_off[4 * lane + j] = pix[j];
-        s_cw[4 * lane + j] = wt[j] * a;
+        pix[j] = corner_pixel(c, j);
+        rec[2 * j] = pix[j] >= 0 ? (uint32_t)pix[j] * (uint32_t)p.stride_l : 0xffffffffu;
+        rec[2 * j + 1] = __float_as_uint(wt[j] * c.a);
       }
+      uint4* dst = reinterpret_cast<uint4*>(&s_rec[warp][slot_i * 4 * LPI + 4 * pl]);
+      dst[0] = make_uint4(rec[0], rec[1], rec[2], rec[3]);
+      dst[1] = make_uint4(rec[4], rec[5], rec[6], rec[7]);
       if (p.idx_debug) {
+        const size_t s = ((size_t)b * n_items + item) * p.P + pl;
         reinterpret_cast<int4*>(p.idx_debug)[s] = make_int4(pix[0], pix[1], pix[2], pix[3]);
       }
     }
   }
   __syncwarp();
 
-  // ---- phase 2: gather --------------------------------------------------------------
+  // ---- phase 2 + 3: gather, reduce over corner slots, store ---------------------------
   const int slot = lane / LPC;
   const int sub = lane % LPC;
-  const VT* vbase = reinterpret_cast<const VT*>(p.value) + (size_t)b * p.stride_b +
-                    (size_t)h * p.c + sub * VPL;
-  float acc[VPL];
+  const VT* vimg = reinterpret_cast<const VT*>(p.value) + (size_t)b * p.stride_b + sub * VPL;
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) acc[i] = 0.f;
-
-  for (int k0 = 0; k0 < ncorner; k0 += U * CPR) {
-    float v[U][VPL];
-    float cw[U];
+  for (int it = 0; it < IPW; ++it) {
+    const int item = item0 + it;
+    if (item >= n_items) break;
+    const int h = item % p.H;
+    const VT* vbase = vimg + h * p.c;
+    const uint2* rec = &s_rec[warp][it * 4 * LPI];
+    float acc[VPL];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int k = k0 + u * CPR + slot;
-      int pix = -1;
-      cw[u] = 0.f;
-      if (k < ncorner) {
-        pix = s_off[k];
-        cw[u] = s_cw[k];
+    for (int i = 0; i < VPL; ++i) acc[i] = 0.f;
+    for (int k0 = 0; k0 < ncorner; k0 += U * CPR) {
+      typename Vec16<VT>::Raw raw[U];
+      float cw[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int k = k0 + u * CPR + slot;
+        uint2 r = make_uint2(0xffffffffu, 0u);
+        if (k < ncorner) r = rec[k];
+        cw[u] = __uint_as_float(r.y);
+        raw[u] = Vec16<VT>::zero();  // masked gather of 0 (zeros padding)
+        if (r.x != 0xffffffffu) raw[u] = Vec16<VT>::load_raw(vbase + r.x);
       }
-      if (pix >= 0) {
-        Vec16<VT>::load(vbase + (size_t)pix * p.stride_l, v[u]);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float v[VPL];
+        Vec16<VT>::unpack(raw[u], v);
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) acc[i] = fmaf(v[i], cw[u], acc[i]);
+      }
+    }
+    int base;
+    bool writer;
+    SlotReduce<LPC, VPL>::run(acc, lane, base, writer);
+    constexpr int n = SlotReduce<LPC, VPL>::kOut;
+    if (writer) {
+      const size_t o = ((size_t)b * n_items + item) * p.c + sub * VPL + base;
+      if (p.out_bf16) {
+        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + o;
+#pragma unroll
+        for (int i = 0; i < n; ++i) out[i] = __float2bfloat16_rn(acc[i]);
       } else {
+        float* out = reinterpret_cast<float*>(p.out) + o;
 #pragma unroll
-        for (int i = 0; i < VPL; ++i) v[u][i] = 0.f;  // masked gather of 0 (zeros padding)
+        for (int i = 0; i < n; ++i) out[i] = acc[i];
       }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-#pragma unroll
-      for (int i = 0; i < VPL; ++i) acc[i] = fmaf(v[u][i], cw[u], acc[i]);
-    }
-  }
-
-  // ---- phase 3: reduce over corner slots and store ------------------------------------
-  int base;
-  bool writer;
-  SlotReduce<LPC, VPL>::run(acc, lane, base, writer);
-  constexpr int n = SlotReduce<LPC, VPL>::kOut;
-  if (writer) {
-    const size_t o = (size_t)bq * p.H * p.c + (size_t)h * p.c + sub * VPL + base;
-    if (p.out_bf16) {
-      __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + o;
-#pragma unroll
-      for (int i = 0; i < n; ++i) out[i] = __float2bfloat16_rn(acc[i]);
-    } else {
-      float* out = reinterpret_cast<float*>(p.out) + o;
-#pragma unroll
-      for (int i = 0; i < n; ++i) out[i] = acc[i];
     }
   }
 }
 
 template <typename VT, int LPC>
 static int launch_fwd_t(const MsdaParams& p, cudaStream_t s) {
-  const long long warps = (long long)p.B * p.Lq * p.H;
-  const long long ctas = (warps + kWarpsPerCta - 1) / kWarpsPerCta;
-  if (ctas > 0x7fffffffLL) {
-    set_error("msda_fwd: grid too large (%lld CTAs)", ctas);
+  if ((long long)p.L * p.stride_l >= 0x7fffffffLL) {
+    set_error("msda_fwd: one image of value spans %lld elements; 32-bit offsets need < 2^31",
+              (long long)p.L * p.stride_l);
     return DFINE_E_SHAPE;
   }
-  const size_t smem = (size_t)kWarpsPerCta * 2 * 4 * kMaxPoints * sizeof(int);
-  msda_fwd_kernel<VT, LPC><<<(unsigned)ctas, kWarpsPerCta * 32, smem, s>>>(p);
+  const int ipw = p.P <= 16 ? 2 : 1;
+  const long long per_cta = (long long)kWarpsPerCta * ipw;
+  const long long ctas = ((long long)p.Lq * p.H + per_cta - 1) / per_cta;
+  if (ctas > 0x7fffffffLL || p.B > 65535) {
+    set_error("msda_fwd: grid too large (%lld x %d CTAs)", ctas, p.B);
+    return DFINE_E_SHAPE;
+  }
+  const dim3 grid((unsigned)ctas, (unsigned)p.B);
+  if (ipw == 2)
+    msda_fwd_kernel<VT, LPC, 2><<<grid, kWarpsPerCta * 32, 0, s>>>(p);
+  else
+    msda_fwd_kernel<VT, LPC, 1><<<grid, kWarpsPerCta * 32, 0, s>>>(p);
   return (int)cudaGetLastError();
 }
 
