@@ -142,6 +142,14 @@ static int fill_msda(MsdaParams& p, const char* fn, const void* value, int64_t s
   p.offset_scale = offset_scale;
   p.B = B; p.Lq = Lq; p.H = H; p.c = c; p.n_lvl = n_lvl; p.P = P; p.L = (int)L;
   p.samp_bf16 = samp_dtype == DFINE_BF16;
+  p.h_shift = -1;
+  for (int sft = 0; sft < 16; ++sft)
+    if ((1 << sft) == H) p.h_shift = sft;
+  if ((long long)B * Lq * H * P >= 0x3fffffffLL) {
+    set_error("%s: B*Lq*H*P = %lld sampling points exceed the 2^30 the kernels index", fn,
+              (long long)B * Lq * H * P);
+    return DFINE_E_SHAPE;
+  }
   return 0;
 }
 
@@ -199,9 +207,9 @@ int dfine_msda_bwd(const void* value, int64_t v_stride_b, int64_t v_stride_l,
                    const int32_t* lvl_hw, const int32_t* lvl_start, const int32_t* lvl_npts,
                    int n_lvl, const void* samp, const void* attn, const float* ref_boxes,
                    const float* pts_scale, float offset_scale, const void* grad_out,
-                   float* grad_value, float* grad_samp, float* grad_attn, int B, int Lq, int H,
+                   void* grad_value, float* grad_samp, float* grad_attn, int B, int Lq, int H,
                    int c, int value_dtype, int samp_dtype, int go_dtype, int flags,
-                   void* stream) {
+                   void* workspace, int64_t workspace_bytes, void* stream) {
   MsdaParams p;
   int rc = fill_msda(p, "dfine_msda_bwd", value, v_stride_b, v_stride_l, lvl_hw, lvl_start,
                      lvl_npts, n_lvl, samp, attn, ref_boxes, pts_scale, offset_scale, B, Lq, H, c,
@@ -222,14 +230,47 @@ int dfine_msda_bwd(const void* value, int64_t v_stride_b, int64_t v_stride_l,
   }
   p.grad_out = grad_out;
   p.go_bf16 = go_dtype == DFINE_BF16;
-  p.grad_value = grad_value;
+  p.grad_value = reinterpret_cast<float*>(grad_value);
   p.grad_samp = grad_samp;
   p.grad_attn = grad_attn;
   cudaStream_t s = (cudaStream_t)stream;
+  const int gv_bf16 = (flags & DFINE_MSDA_GRAD_VALUE_BF16) ? 1 : 0;
+  const size_t ws_need = msda_bwd_workspace_bytes(B, Lq, H, p.P);
+  if (!(flags & DFINE_MSDA_FORCE_ATOMIC) && workspace && (size_t)workspace_bytes >= ws_need) {
+    // preferred: the dots kernel leaves per-sample records in the workspace, then grad_value
+    // is produced by in-CTA counting sort + gather (no float atomics, no memset)
+    if ((rc = require_device(workspace, "workspace", "dfine_msda_bwd"))) return rc;
+    if (!aligned16(workspace)) {
+      set_error("dfine_msda_bwd: workspace must be 16-byte aligned");
+      return DFINE_E_ALIGN;
+    }
+    p.rec = reinterpret_cast<uint4*>(workspace);
+    // shape check first: nothing is launched if the gather path cannot take this shape
+    rc = launch_msda_bwd_value(p, nullptr, gv_bf16, s);
+    if (rc == 0) {
+      if ((rc = launch_msda_bwd(p, value_dtype, /*scatter=*/false, s)))
+        return cuda_rc(rc, "dfine_msda_bwd");
+      return cuda_rc(launch_msda_bwd_value(p, grad_value, gv_bf16, s), "dfine_msda_bwd(value)");
+    }
+    if (rc != DFINE_E_UNSUPPORTED) return cuda_rc(rc, "dfine_msda_bwd(value)");
+    p.rec = nullptr;
+  }
+  if (gv_bf16) {
+    set_error("dfine_msda_bwd: a bf16 grad_value needs the gather path (workspace of "
+              "dfine_msda_bwd_workspace_bytes() bytes, a shape whose pixel CSR fits shared "
+              "memory, no DFINE_MSDA_FORCE_ATOMIC); pass a float32 buffer and cast instead");
+    return DFINE_E_UNSUPPORTED;
+  }
+  // fallback: fp32 vector reductions into a zero-filled buffer
   const size_t bytes = (size_t)B * p.L * H * c * sizeof(float);
   cudaError_t e = cudaMemsetAsync(grad_value, 0, bytes, s);
   if (e != cudaSuccess) return cuda_rc((int)e, "dfine_msda_bwd(memset)");
-  return cuda_rc(launch_msda_bwd(p, value_dtype, s), "dfine_msda_bwd");
+  return cuda_rc(launch_msda_bwd(p, value_dtype, /*scatter=*/true, s), "dfine_msda_bwd");
+}
+
+int64_t dfine_msda_bwd_workspace_bytes(int B, int Lq, int H, int P) {
+  if (B <= 0 || Lq <= 0 || H <= 0 || P <= 0) return 0;
+  return (int64_t)msda_bwd_workspace_bytes(B, Lq, H, P);
 }
 
 int dfine_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {

@@ -27,9 +27,11 @@ struct MsdaParams {
   float* grad_value;     // bwd: [B,L,H,c] fp32 contiguous
   float* grad_samp;      // bwd: [B,Lq,H,P,2]
   float* grad_attn;      // bwd: [B,Lq,H,P]
+  uint4* rec;            // bwd: optional [B,H,P,Lq] sample records for the gather path
   int B, Lq, H, c, n_lvl, P, L;
   int lvl_h[kMaxLevels], lvl_w[kMaxLevels], lvl_start[kMaxLevels], lvl_pend[kMaxLevels];
   int samp_bf16, out_bf16, go_bf16, fused;
+  int h_shift;           // log2(H) when H is a power of two, else -1
 };
 
 // One bilinear sample: integer corner origin + the four fractional factors.
@@ -117,6 +119,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 void set_error(const char* fmt, ...);
 
 int launch_msda_fwd(const MsdaParams& p, int value_dtype, cudaStream_t s);
-int launch_msda_bwd(const MsdaParams& p, int value_dtype, cudaStream_t s);
+int launch_msda_bwd(const MsdaParams& p, int value_dtype, bool scatter, cudaStream_t s);
+int launch_msda_bwd_value(const MsdaParams& p, void* grad_value, int gv_bf16, cudaStream_t s);
+size_t msda_bwd_workspace_bytes(int B, int Lq, int H, int P);
 
 }  // namespace dfine

@@ -1,23 +1,25 @@
-// K2: multi-scale deformable attention backward (sm_100a).
+// K2: multi-scale deformable attention backward, sample-centric part (sm_100a).
 //
 // Replaces what autograd runs for the reference path src/d_fine/arch/utils.py:215-262
-// (sum / mul / cat backward, aten::grid_sampler_2d_backward per level, the reshape-copy
-// backward) and, in fused-input mode, softmax backward and the location arithmetic backward
-// of src/d_fine/arch/dfine_decoder.py:144-166.
+// (sum / mul / cat backward, the grad_grid half of aten::grid_sampler_2d_backward) and, in
+// fused-input mode, softmax backward and the location arithmetic backward of
+// src/d_fine/arch/dfine_decoder.py:144-166.  grad_value is produced by msda_bwd_value.cu
+// from the per-sample records this kernel leaves in the workspace; only the fallback
+// (kScatter) scatters it from here with fp32 vector reductions.
 //
 // One warp handles IPW = 2 items (item = (query, head) of image blockIdx.y).
 //   phase 1  half a warp per item, one lane per sampling point: fused input arithmetic and
-//            bit-exact geometry (msda_common.cuh); per-corner records {pixel, w, dw/dix,
-//            dw/diy} and the point's attention weight go to a per-warp smem table.
+//            bit-exact geometry (msda_common.cuh); per point {fw, fn, attn} and per corner
+//            the global address of its head slice go to per-warp smem tables.
 //   phase 2  lane = (slot, sub): `sub` selects 16 bytes of the head slice (LPC lanes per
 //            corner), `slot` selects a sampling point; the lower half of the slots serves
-//            item 0, the upper half item 1, so a lane's grad_out slice and image/head base
-//            never change.  The four corners of a point are visited in four consecutive
-//            rounds by the SAME lanes, so the point's partial sums stay in registers:
-//              grad_value : (w*attn) * grad_out  -> red.global.add.v4.f32 (fp32 [B,L,H,c])
-//              grad_attn  : sum_corner w  * <V_corner, grad_out>
-//              grad_ix/iy : sum_corner dw * <V_corner, grad_out>
-//            and only one LPC-lane reduce-scatter per point (3 shuffles) is needed.
+//            item 0, the upper half item 1, so a lane's grad_out slice never changes.  The
+//            four corners of a point are loaded together by the SAME lanes, so the point's
+//            sums stay in registers:
+//              d_j       = <V_corner_j, grad_out>          (this lane's channels)
+//              grad_attn = sum_j w_j d_j
+//              grad_ix   = fs (d1 - d0) + fn (d3 - d2),  grad_iy = fe (d2 - d0) + fw (d3 - d1)
+//            followed by ONE reduce-scatter over the LPC lanes of the point (3 shuffles).
 //   phase 3  one lane per point again: scale by attn and (W, H); fused mode applies softmax
 //            backward (reduction over the points of the head) and the offset chain rule.
 #include "msda_common.cuh"
@@ -47,8 +49,8 @@ __device__ __forceinline__ void load_go(const void* go, size_t i, int is_bf16, f
   }
 }
 
-template <typename VT, int LPC>
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+template <typename VT, int LPC, bool kScatter, int kP>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 3)
 msda_bwd_kernel(const MsdaParams p) {
   constexpr int VPL = Vec16<VT>::kElems;
   constexpr int IPW = 2;
@@ -57,11 +59,10 @@ msda_bwd_kernel(const MsdaParams p) {
   constexpr int SPI = SLOTS / IPW;       // slots per item
   static_assert(SPI >= 1, "head slice too wide for two items per warp");
 
-  // per warp and item: 4*LPI corner records {pixel, w, dw/dix, dw/diy}, LPI attn weights,
-  // 3*LPI per-point results
-  __shared__ __align__(16) uint4 s_rec[kWarpsPerCta][IPW][4 * LPI];
-  __shared__ float s_attn[kWarpsPerCta][IPW][LPI];
-  __shared__ float s_res[kWarpsPerCta][IPW][3][LPI];
+  __shared__ __align__(16) uint2 s_adr[kWarpsPerCta][IPW][4 * LPI];   // corner addresses
+  __shared__ __align__(16) float4 s_pt[kWarpsPerCta][IPW][LPI];       // {fw, fn, attn, -}
+  __shared__ float s_res[kWarpsPerCta][IPW][3][LPI];                  // per-point sums
+  __shared__ int s_pix[kScatter ? kWarpsPerCta : 1][IPW][kScatter ? 4 * LPI : 1];
 
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -69,23 +70,29 @@ msda_bwd_kernel(const MsdaParams p) {
   const int n_items = p.Lq * p.H;
   const int item0 = (blockIdx.x * kWarpsPerCta + warp) * IPW;
   if (item0 >= n_items) return;
-  const int P = p.P;
+  const int P = kP ? kP : p.P;
+  const char* img = reinterpret_cast<const char*>(reinterpret_cast<const VT*>(p.value) +
+                                                  (size_t)b * p.stride_b);
 
   // ---- phase 1 ------------------------------------------------------------------------------
   const int slot_i = lane / LPI, pl = lane % LPI;
-  const PointCtx c = point_phase<LPI>(p, b, item0 + slot_i, pl, item0 + slot_i < n_items);
+  const PointCtx c = point_phase<LPI>(p, P, b, item0 + slot_i, pl, item0 + slot_i < n_items);
   if (c.active) {
-    const float wt[4] = {c.g.fs * c.g.fe, c.g.fs * c.g.fw, c.g.fn * c.g.fe, c.g.fn * c.g.fw};
-    // d sampled / d ix = -v_nw*s + v_ne*s - v_sw*n + v_se*n ;  d / d iy likewise
-    const float sx[4] = {-c.g.fs, c.g.fs, -c.g.fn, c.g.fn};
-    const float sy[4] = {-c.g.fe, -c.g.fw, c.g.fe, c.g.fw};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      s_rec[warp][slot_i][4 * pl + j] =
-          make_uint4((uint32_t)corner_pixel(c, j), __float_as_uint(wt[j]), __float_as_uint(sx[j]),
-                     __float_as_uint(sy[j]));
+      const int pix = corner_pixel_local(c, j);
+      const uint64_t a = corner_address<VT>(p, img, c.h, pix, c.lstart);
+      s_adr[warp][slot_i][4 * pl + j] = make_uint2((uint32_t)a, (uint32_t)(a >> 32));
+      if (kScatter) s_pix[warp][slot_i][4 * pl + j] = pix >= 0 ? pix + c.lstart : -1;
     }
-    s_attn[warp][slot_i][pl] = c.a;
+    s_pt[warp][slot_i][pl] = make_float4(c.g.fw, c.g.fn, c.a, 0.f);
+    if (p.rec) {
+      // compact record for msda_bwd_value.cu: {x0 | y0 << 16, fw, fn, attn}, laid out
+      // [b][h][point][query] so that one (b, h, level) is a contiguous run
+      const uint32_t xy = ((uint32_t)c.g.x0 & 0xffffu) | ((uint32_t)c.g.y0 << 16);
+      p.rec[(((size_t)b * p.H + c.h) * P + pl) * p.Lq + c.q] =
+          make_uint4(xy, __float_as_uint(c.g.fw), __float_as_uint(c.g.fn), __float_as_uint(c.a));
+    }
   }
   __syncwarp();
 
@@ -97,52 +104,58 @@ msda_bwd_kernel(const MsdaParams p) {
     const int ps = slot % SPI;             // point slot inside the item
     const int item = item0 + it;
     const bool item_ok = item < n_items;
-    const int h = item_ok ? item % p.H : 0;
-    const int chan = h * p.c + sub * VPL;
-    const VT* vbase = reinterpret_cast<const VT*>(p.value) + (size_t)b * p.stride_b + chan;
-    float* gvbase = p.grad_value + (size_t)b * p.L * p.H * p.c + chan;
-    const uint32_t gv_stride = (uint32_t)(p.H * p.c);
+    const uint32_t sub_bytes = (uint32_t)sub * 16u;
     float go[VPL];
 #pragma unroll
     for (int i = 0; i < VPL; ++i) go[i] = 0.f;
     if (item_ok) load_go<VPL>(p.grad_out, ((size_t)b * n_items + item) * p.c + sub * VPL, p.go_bf16, go);
+    const int h = p.h_shift >= 0 ? (item & (p.H - 1)) : item % p.H;
 
+#pragma unroll 1
     for (int pt0 = 0; pt0 < P; pt0 += SPI) {
       const int pt = pt0 + ps;
       const bool live = item_ok && pt < P;
-      uint4 rec[4];
+      const int ptc = live ? pt : 0;
       typename Vec16<VT>::Raw raw[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        rec[j] = make_uint4(0xffffffffu, 0u, 0u, 0u);
-        if (live) rec[j] = s_rec[warp][it][4 * pt + j];
-        raw[j] = Vec16<VT>::zero();  // masked gather of 0 (zeros padding)
-        if (rec[j].x != 0xffffffffu)
-          raw[j] = Vec16<VT>::load_raw(vbase + (size_t)rec[j].x * (uint32_t)p.stride_l);
+        const uint2 ad = s_adr[warp][it][4 * ptc + j];
+        const char* a = reinterpret_cast<const char*>(((uint64_t)ad.y << 32) | ad.x);
+        if (!live) a = reinterpret_cast<const char*>(g_zero_row);
+        raw[j] = Vec16<VT>::load_raw(reinterpret_cast<const VT*>(a + sub_bytes));
       }
-      const float a = live ? s_attn[warp][it][pt] : 0.f;
-      float t[4] = {0.f, 0.f, 0.f, 0.f};
+      const float4 pr = s_pt[warp][it][ptc];
+      const float fw = pr.x, fn = pr.y, fe = 1.0f - fw, fs = 1.0f - fn;
+      float d[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float v[VPL];
         Vec16<VT>::unpack(raw[j], v);
-        const float wt = __uint_as_float(rec[j].y);
-        if (rec[j].x != 0xffffffffu) {
-          const float cw = wt * a;
-          float* dst = gvbase + (size_t)rec[j].x * gv_stride;
+        d[j] = 0.f;  // <V_corner, grad_out> over this lane's channels
 #pragma unroll
-          for (int i = 0; i < VPL; i += 4) {
-            atomicAdd(reinterpret_cast<float4*>(dst + i),
-                      make_float4(cw * go[i], cw * go[i + 1], cw * go[i + 2], cw * go[i + 3]));
+        for (int i = 0; i < VPL; ++i) d[j] = fmaf(v[i], go[i], d[j]);
+      }
+      if (kScatter && live) {
+        const float wt[4] = {fs * fe, fs * fw, fn * fe, fn * fw};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int pix = s_pix[warp][it][4 * pt + j];
+          if (pix >= 0) {
+            const float cw = wt[j] * pr.z;
+            float* dst = p.grad_value + ((size_t)b * p.L + pix) * (size_t)(p.H * p.c) + h * p.c + sub * VPL;
+#pragma unroll
+            for (int i = 0; i < VPL; i += 4)
+              atomicAdd(reinterpret_cast<float4*>(dst + i),
+                        make_float4(cw * go[i], cw * go[i + 1], cw * go[i + 2], cw * go[i + 3]));
           }
         }
-        float d = 0.f;  // <V_corner, grad_out> over this lane's channels
-#pragma unroll
-        for (int i = 0; i < VPL; ++i) d = fmaf(v[i], go[i], d);
-        t[0] = fmaf(wt, d, t[0]);
-        t[1] = fmaf(__uint_as_float(rec[j].z), d, t[1]);
-        t[2] = fmaf(__uint_as_float(rec[j].w), d, t[2]);
       }
+      float t[4];
+      t[0] = (fs * fe) * d[0] + (fs * fw) * d[1] + (fn * fe) * d[2] + (fn * fw) * d[3];
+      t[1] = fs * (d[1] - d[0]) + fn * (d[3] - d[2]);
+      t[2] = fe * (d[2] - d[0]) + fw * (d[3] - d[1]);
+      t[3] = 0.f;
+      if (!live) t[0] = t[1] = t[2] = 0.f;
       // reduce the three sums over the LPC lanes of the point (reduce-scatter, then butterfly)
       int which = 0;
       if constexpr (LPC >= 2) {
@@ -190,7 +203,7 @@ msda_bwd_kernel(const MsdaParams p) {
       gx = c.a * s_res[warp][slot_i][1][pl] * (float)c.lw;
       gy = c.a * s_res[warp][slot_i][2][pl] * (float)c.lh;
     }
-    const size_t s = ((size_t)b * n_items + item0 + slot_i) * P + pl;
+    const int s = (b * n_items + item0 + slot_i) * P + pl;
     if (p.fused) {
       // softmax backward over the points of the head: g_logit = a * (S - sum_j a_j S_j)
       const float dot = group_sum<LPI>(c.active ? c.a * S : 0.f);
@@ -207,8 +220,8 @@ msda_bwd_kernel(const MsdaParams p) {
 }
 
 template <typename VT, int LPC>
-static int launch_bwd_t(const MsdaParams& p, cudaStream_t s) {
-  if ((long long)p.L * p.stride_l >= 0x7fffffffLL || (long long)p.L * p.H * p.c >= 0x7fffffffLL) {
+static int launch_bwd_t(const MsdaParams& p, bool scatter, cudaStream_t s) {
+  if ((long long)p.L * p.stride_l + (long long)p.H * p.c >= 0xffffffffLL) {
     set_error("msda_bwd: one image of value spans too many elements for 32-bit offsets");
     return DFINE_E_SHAPE;
   }
@@ -222,19 +235,27 @@ static int launch_bwd_t(const MsdaParams& p, cudaStream_t s) {
     set_error("msda_bwd: grid too large (%lld x %d CTAs)", ctas, p.B);
     return DFINE_E_SHAPE;
   }
-  msda_bwd_kernel<VT, LPC><<<dim3((unsigned)ctas, (unsigned)p.B), kWarpsPerCta * 32, 0, s>>>(p);
+  const dim3 grid((unsigned)ctas, (unsigned)p.B);
+  constexpr int T = kWarpsPerCta * 32;
+  if (scatter) {
+    msda_bwd_kernel<VT, LPC, true, 0><<<grid, T, 0, s>>>(p);
+  } else if (p.P == 12) {
+    msda_bwd_kernel<VT, LPC, false, 12><<<grid, T, 0, s>>>(p);
+  } else {
+    msda_bwd_kernel<VT, LPC, false, 0><<<grid, T, 0, s>>>(p);
+  }
   return (int)cudaGetLastError();
 }
 
-int launch_msda_bwd(const MsdaParams& p, int value_dtype, cudaStream_t s) {
+int launch_msda_bwd(const MsdaParams& p, int value_dtype, bool scatter, cudaStream_t s) {
   if (value_dtype == DFINE_BF16) {
-    if (p.c == 16) return launch_bwd_t<__nv_bfloat16, 2>(p, s);
-    if (p.c == 32) return launch_bwd_t<__nv_bfloat16, 4>(p, s);
-    if (p.c == 64) return launch_bwd_t<__nv_bfloat16, 8>(p, s);
+    if (p.c == 16) return launch_bwd_t<__nv_bfloat16, 2>(p, scatter, s);
+    if (p.c == 32) return launch_bwd_t<__nv_bfloat16, 4>(p, scatter, s);
+    if (p.c == 64) return launch_bwd_t<__nv_bfloat16, 8>(p, scatter, s);
   } else {
-    if (p.c == 16) return launch_bwd_t<float, 4>(p, s);
-    if (p.c == 32) return launch_bwd_t<float, 8>(p, s);
-    if (p.c == 64) return launch_bwd_t<float, 16>(p, s);
+    if (p.c == 16) return launch_bwd_t<float, 4>(p, scatter, s);
+    if (p.c == 32) return launch_bwd_t<float, 8>(p, scatter, s);
+    if (p.c == 64) return launch_bwd_t<float, 16>(p, scatter, s);
   }
   set_error("msda_bwd: head_dim %d not built; supported: 16, 32, 64", p.c);
   return DFINE_E_UNSUPPORTED;

@@ -1,0 +1,291 @@
+// K2b: grad_value of multi-scale deformable attention WITHOUT floating-point atomics (sm_100a).
+//
+// aten::grid_sampler_2d_backward scatters with global atomicAdd (the reference path,
+// src/d_fine/arch/utils.py:229 under autograd).  Here every (image b, head h, level chunk)
+// is owned by one CTA that turns the scatter into a gather:
+//   S1  threads read the 16-byte sample records {x0, y0, fw, fn, attn} that the K2 dots
+//       kernel (msda_bwd.cu, same bit-exact geometry as K1) left in the workspace, and COUNT
+//       in-bounds corners per pixel with native shared-memory integer atomics;
+//   S2  block-wide exclusive scan -> CSR row offsets per pixel;
+//   S3  second pass over the records FILLS the CSR with {query, pixel, weight*attn};
+//   S4  the CSR is consumed as flat streams by "workers" of c/4 lanes (4 channels per lane,
+//       e.g. 8 lanes x float4 = one 128-byte row of grad_out[b, q, h, :]); a warp therefore
+//       advances 32/(c/4) entries per instruction.  Workers own contiguous pixel ranges
+//       balanced by entry count (binary search in the offsets); U entries are in flight per
+//       worker regardless of pixel boundaries; when the pixel id changes the finished row is
+//       stored.  Pixels without entries are stored as zeros.
+// grad_value is written exactly once, coalesced, directly in its final dtype (fp32, or bf16
+// under AMP): no zero-fill pass, no float atomics, no cast pass.  The summation order inside
+// a pixel follows the integer-atomic fill order (like the reference's atomics, results are
+// reproducible up to fp32 rounding only).
+#include "msda_common.cuh"
+
+namespace dfine {
+
+constexpr int kBvThreads = 512;
+constexpr int kBvMaxChunks = 32;
+constexpr int kBvMaxChunkPx = 4096;  // chunk-local pixel ids use 13 bits
+
+struct BvChunks {
+  int n;
+  int lvl[kBvMaxChunks];
+  int px0[kBvMaxChunks];  // level-local pixel range [px0, px1)
+  int px1[kBvMaxChunks];
+};
+
+struct BvEntry {  // 8 bytes
+  uint32_t qp;    // query index << 13 | chunk-local pixel
+  float cw;       // bilinear weight * attention weight
+};
+
+// exclusive scan of s_cnt[0..n) into s_off[0..n], s_off[n] = total.  All threads call.
+__device__ __forceinline__ void block_exclusive_scan(const int* s_cnt, int* s_off, int n,
+                                                     int* s_warp /*[32]*/) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int per = (n + nthr - 1) / nthr;
+  const int beg = min(tid * per, n), end = min(beg + per, n);
+  int sum = 0;
+  for (int i = beg; i < end; ++i) sum += s_cnt[i];
+  const int lane = tid & 31, warp = tid >> 5;
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = lane < (nthr >> 5) ? s_warp[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += t;
+    }
+    s_warp[lane] = w;  // inclusive over warps
+  }
+  __syncthreads();
+  int run = incl - sum + (warp > 0 ? s_warp[warp - 1] : 0);
+  for (int i = beg; i < end; ++i) {
+    const int cnt = s_cnt[i];
+    s_off[i] = run;
+    run += cnt;
+  }
+  if (tid == nthr - 1) s_off[n] = s_warp[(nthr >> 5) - 1];
+  __syncthreads();
+}
+
+// One sample record -> its in-chunk corners.  kFill=false counts, kFill=true writes entries.
+template <bool kFill>
+__device__ __forceinline__ void bv_visit(const uint4 r, int q, int lw, int lh, int px0, int px1,
+                                         int* s_cur, BvEntry* s_ent) {
+  const int x0 = (int)(short)(r.x & 0xffffu), y0 = (int)(short)(r.x >> 16);
+  if (x0 < -1 || y0 < -1 || x0 >= lw || y0 >= lh) return;  // every corner out of bounds
+  const float fw = __uint_as_float(r.y), fn = __uint_as_float(r.z), a = __uint_as_float(r.w);
+  const float fe = __fsub_rn(1.0f, fw), fs = __fsub_rn(1.0f, fn);
+  const float wt[4] = {fs * fe, fs * fw, fn * fe, fn * fw};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int x = x0 + (j & 1), y = y0 + (j >> 1);
+    if (x < 0 || x >= lw || y < 0 || y >= lh) continue;
+    const int px = y * lw + x;
+    if (px < px0 || px >= px1) continue;
+    const int slot = atomicAdd(&s_cur[px - px0], 1);
+    if (kFill) {
+      BvEntry e;
+      e.qp = ((uint32_t)q << 13) | (uint32_t)(px - px0);
+      e.cw = wt[j] * a;
+      s_ent[slot] = e;
+    }
+  }
+}
+
+template <typename GT> struct GoRow;  // 4 consecutive channels of grad_out
+template <> struct GoRow<float> {
+  using Raw = float4;
+  __device__ static __forceinline__ Raw load(const float* p) {
+    return __ldg(reinterpret_cast<const float4*>(p));
+  }
+  __device__ static __forceinline__ float4 widen(const Raw& r) { return r; }
+};
+template <> struct GoRow<__nv_bfloat16> {
+  using Raw = uint2;
+  __device__ static __forceinline__ Raw load(const __nv_bfloat16* p) {
+    return __ldg(reinterpret_cast<const uint2*>(p));
+  }
+  __device__ static __forceinline__ float4 widen(const Raw& r) {
+    return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u),
+                       __uint_as_float(r.y << 16), __uint_as_float(r.y & 0xffff0000u));
+  }
+};
+
+template <int kC, typename GT>
+__global__ void __launch_bounds__(kBvThreads, 1)
+msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ grad_value,
+                      int gv_bf16, int max_px) {
+  constexpr int LPR = kC / 4;          // lanes per row (4 channels each)
+  constexpr int WPW = 32 / LPR;        // workers per warp
+  constexpr int NWORK = (kBvThreads / 32) * WPW;
+  constexpr int U = 4;                 // entries in flight per worker
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int* s_off = reinterpret_cast<int*>(smem_raw);   // [max_px + 1]
+  int* s_cur = s_off + (max_px + 1);               // [max_px]
+  int* s_warp = s_cur + max_px;                    // [32]
+  BvEntry* s_ent = reinterpret_cast<BvEntry*>(s_warp + 32 + 1);  // (2*max_px + 34) ints: 8B aligned
+
+  const int lvl = ch.lvl[blockIdx.x], px0 = ch.px0[blockIdx.x], px1 = ch.px1[blockIdx.x];
+  const int npx = px1 - px0;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int p0 = lvl == 0 ? 0 : p.lvl_pend[lvl - 1];
+  const int np = p.lvl_pend[lvl] - p0;
+  const int lw = p.lvl_w[lvl], lh = p.lvl_h[lvl];
+  const int tid = threadIdx.x;
+  const int nsamp = np * p.Lq;
+  const uint4* recs = p.rec + (((size_t)b * p.H + h) * p.P + p0) * p.Lq;
+
+  for (int i = tid; i < npx; i += kBvThreads) s_cur[i] = 0;
+  __syncthreads();
+  // S1: count corners per pixel
+  for (int t = tid; t < nsamp; t += kBvThreads)
+    bv_visit<false>(__ldg(recs + t), t % p.Lq, lw, lh, px0, px1, s_cur, s_ent);
+  __syncthreads();
+  // S2: CSR offsets
+  block_exclusive_scan(s_cur, s_off, npx, s_warp);
+  for (int i = tid; i < npx; i += kBvThreads) s_cur[i] = s_off[i];
+  __syncthreads();
+  // S3: fill
+  for (int t = tid; t < nsamp; t += kBvThreads)
+    bv_visit<true>(__ldg(recs + t), t % p.Lq, lw, lh, px0, px1, s_cur, s_ent);
+  __syncthreads();
+
+  // S4: gather
+  const int lane = tid & 31;
+  const int worker = (tid >> 5) * WPW + lane / LPR;
+  const int sub = lane % LPR;
+  const int total = s_off[npx];
+  auto first_px_at = [&](int target) {  // smallest pixel i with s_off[i] >= target
+    int lo = 0, hi = npx;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (s_off[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+  };
+  const int pa = worker == 0 ? 0 : first_px_at((int)((long long)total * worker / NWORK));
+  const int pb = worker == NWORK - 1 ? npx : first_px_at((int)((long long)total * (worker + 1) / NWORK));
+  const uint32_t row_stride = (uint32_t)(p.H * kC);
+  const GT* gob = reinterpret_cast<const GT*>(p.grad_out) + (size_t)b * p.Lq * row_stride +
+                  (size_t)h * kC + 4 * sub;
+  const size_t gv0 = ((size_t)b * p.L + p.lvl_start[lvl] + px0) * row_stride + (size_t)h * kC + 4 * sub;
+
+  auto store_row = [&](int px, const float4& v) {
+    const size_t o = gv0 + (size_t)px * row_stride;
+    if (gv_bf16) {
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(grad_value) + o) = pk;
+    } else {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(grad_value) + o) = v;
+    }
+  };
+
+  if (pa < pb) {
+    const int e1 = s_off[pb];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cur = -1;
+    for (int e = s_off[pa]; e < e1; e += U) {
+      BvEntry ent[U];
+      typename GoRow<GT>::Raw raw[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int ee = min(e + u, e1 - 1);  // clamp: the tail re-reads the last entry, unused
+        ent[u] = s_ent[ee];
+        raw[u] = GoRow<GT>::load(gob + (size_t)(ent[u].qp >> 13) * row_stride);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (e + u < e1) {
+          const int px = (int)(ent[u].qp & 0x1fffu);
+          if (px != cur) {
+            if (cur >= 0) store_row(cur, acc);
+            acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            cur = px;
+          }
+          const float4 g = GoRow<GT>::widen(raw[u]);
+          acc.x = fmaf(ent[u].cw, g.x, acc.x);
+          acc.y = fmaf(ent[u].cw, g.y, acc.y);
+          acc.z = fmaf(ent[u].cw, g.z, acc.z);
+          acc.w = fmaf(ent[u].cw, g.w, acc.w);
+        }
+      }
+    }
+    if (cur >= 0) store_row(cur, acc);
+  }
+  // pixels that no sample touched: explicit zeros (this replaces the memset pass)
+  for (int px = worker; px < npx; px += NWORK)
+    if (s_off[px + 1] == s_off[px]) store_row(px, make_float4(0.f, 0.f, 0.f, 0.f));
+}
+
+size_t msda_bwd_workspace_bytes(int B, int Lq, int H, int P) {
+  return (size_t)B * H * P * Lq * sizeof(uint4);
+}
+
+// Returns 0 on launch, DFINE_E_UNSUPPORTED when the shape does not fit this kernel (the
+// caller then uses the atomic path), >0 on a CUDA error.  grad_value == nullptr only checks
+// the shape (nothing is launched).
+int launch_msda_bwd_value(const MsdaParams& p, void* grad_value, int gv_bf16, cudaStream_t s) {
+  if (p.Lq >= (1 << 19) || p.B > 65535 || p.H > 65535 || !p.rec) return DFINE_E_UNSUPPORTED;
+  BvChunks ch;
+  ch.n = 0;
+  int max_px = 0, cap = 0;
+  for (int l = 0; l < p.n_lvl; ++l) {
+    const int npx = p.lvl_h[l] * p.lvl_w[l];
+    if (p.lvl_h[l] > 32767 || p.lvl_w[l] > 32767) return DFINE_E_UNSUPPORTED;
+    const int np = p.lvl_pend[l] - (l ? p.lvl_pend[l - 1] : 0);
+    const int nchunk = (npx + kBvMaxChunkPx - 1) / kBvMaxChunkPx;
+    const int per = (npx + nchunk - 1) / nchunk;
+    for (int k = 0; k < nchunk; ++k) {
+      if (ch.n >= kBvMaxChunks) return DFINE_E_UNSUPPORTED;
+      ch.lvl[ch.n] = l;
+      ch.px0[ch.n] = k * per;
+      ch.px1[ch.n] = (k + 1) * per < npx ? (k + 1) * per : npx;
+      if (ch.px1[ch.n] - ch.px0[ch.n] > max_px) max_px = ch.px1[ch.n] - ch.px0[ch.n];
+      ++ch.n;
+    }
+    // worst case: every corner of every sample of the level lands in one chunk
+    const long long c = 4LL * np * p.Lq;
+    if (c > cap) cap = (int)(c > 0x3fffffff ? 0x3fffffff : c);
+  }
+  const size_t smem = (size_t)(2 * max_px + 34) * sizeof(int) + (size_t)cap * sizeof(BvEntry) + 16;
+  if (smem > 200 * 1024) return DFINE_E_UNSUPPORTED;
+  if (p.c != 16 && p.c != 32 && p.c != 64) return DFINE_E_UNSUPPORTED;
+  if (!grad_value) return 0;
+  const dim3 grid((unsigned)ch.n, (unsigned)p.H, (unsigned)p.B);
+  cudaError_t e = cudaSuccess;
+#define DFINE_BV_LAUNCH(C, GT)                                                                   \
+  do {                                                                                           \
+    e = cudaFuncSetAttribute(msda_bwd_value_kernel<C, GT>,                                       \
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
+    if (e == cudaSuccess)                                                                        \
+      msda_bwd_value_kernel<C, GT><<<grid, kBvThreads, smem, s>>>(p, ch, grad_value, gv_bf16,    \
+                                                                  max_px);                       \
+  } while (0)
+  if (p.go_bf16) {
+    if (p.c == 16) DFINE_BV_LAUNCH(16, __nv_bfloat16);
+    else if (p.c == 32) DFINE_BV_LAUNCH(32, __nv_bfloat16);
+    else if (p.c == 64) DFINE_BV_LAUNCH(64, __nv_bfloat16);
+    else return DFINE_E_UNSUPPORTED;
+  } else {
+    if (p.c == 16) DFINE_BV_LAUNCH(16, float);
+    else if (p.c == 32) DFINE_BV_LAUNCH(32, float);
+    else if (p.c == 64) DFINE_BV_LAUNCH(64, float);
+    else return DFINE_E_UNSUPPORTED;
+  }
+#undef DFINE_BV_LAUNCH
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaGetLastError();
+}
+
+}  // namespace dfine

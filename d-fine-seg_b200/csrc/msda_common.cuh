@@ -9,11 +9,16 @@
 
 namespace dfine {
 
+// Out-of-bounds corners are gathered from this row of zeros: exactly the "masked gather of
+// 0" of grid_sample's zeros padding, without a predicate or select in the gather loop.
+static __device__ __align__(256) unsigned char g_zero_row[256];
+
 struct PointCtx {
   float a;            // attention weight of this lane's point (after softmax in fused mode)
   float ps;           // fused: num_points_scale of the point
   float4 ref;         // fused: reference box (cx, cy, w, h)
   int lw, lh, lstart; // level of the point
+  int q, h;           // query / head of the lane's item
   Geometry g;
   bool active;        // lane owns a real point of a real item
 };
@@ -31,21 +36,30 @@ __device__ __forceinline__ float group_sum(float v) {
   return v;
 }
 
-// item : flattened (q * H + h) index of this lane's item (warp-uniform per LPI group)
-// pl   : point index of this lane inside its item
+__device__ __forceinline__ int sel3(int lvl, int v0, int v1, int v2, int v3) {
+  return lvl == 0 ? v0 : (lvl == 1 ? v1 : (lvl == 2 ? v2 : v3));
+}
+
+// item : flattened (q * H + h) index of this lane's item (uniform per LPI group)
+// pl   : point index of this lane inside its item;  P: points per head
 template <int LPI>
-__device__ __forceinline__ PointCtx point_phase(const MsdaParams& p, int b, int item, int pl,
+__device__ __forceinline__ PointCtx point_phase(const MsdaParams& p, int P, int b, int item, int pl,
                                                 bool item_valid) {
   PointCtx c;
-  const int P = p.P;
   c.active = item_valid && pl < P;
   const int lvl = (pl >= p.lvl_pend[0]) + (pl >= p.lvl_pend[1]) + (pl >= p.lvl_pend[2]);
-  c.lw = lvl == 0 ? p.lvl_w[0] : lvl == 1 ? p.lvl_w[1] : lvl == 2 ? p.lvl_w[2] : p.lvl_w[3];
-  c.lh = lvl == 0 ? p.lvl_h[0] : lvl == 1 ? p.lvl_h[1] : lvl == 2 ? p.lvl_h[2] : p.lvl_h[3];
-  c.lstart = lvl == 0 ? p.lvl_start[0]
-                      : lvl == 1 ? p.lvl_start[1] : lvl == 2 ? p.lvl_start[2] : p.lvl_start[3];
-  // sample index inside [B, Lq, H, P]
-  const size_t s = ((size_t)b * p.Lq * p.H + item) * P + pl;
+  c.lw = sel3(lvl, p.lvl_w[0], p.lvl_w[1], p.lvl_w[2], p.lvl_w[3]);
+  c.lh = sel3(lvl, p.lvl_h[0], p.lvl_h[1], p.lvl_h[2], p.lvl_h[3]);
+  c.lstart = sel3(lvl, p.lvl_start[0], p.lvl_start[1], p.lvl_start[2], p.lvl_start[3]);
+  if (p.h_shift >= 0) {  // H is a power of two in every D-FINE config (8)
+    c.q = item >> p.h_shift;
+    c.h = item & (p.H - 1);
+  } else {
+    c.q = item / p.H;
+    c.h = item - c.q * p.H;
+  }
+  // sample index inside [B, Lq, H, P] (the launcher guarantees it fits 31 bits)
+  const int s = (b * p.Lq * p.H + item) * P + pl;
   float lx = 0.f, ly = 0.f;
   c.a = 0.f;
   c.ps = 0.f;
@@ -58,15 +72,14 @@ __device__ __forceinline__ PointCtx point_phase(const MsdaParams& p, int b, int 
         const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(p.samp) + s);
         rx = __uint_as_float(u << 16);
         ry = __uint_as_float(u & 0xffff0000u);
-        logit = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.attn)[s]);
+        logit = __uint_as_float((uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p.attn) + s) << 16);
       } else {
         const float2 t = __ldg(reinterpret_cast<const float2*>(p.samp) + s);
         rx = t.x;
         ry = t.y;
         logit = __ldg(reinterpret_cast<const float*>(p.attn) + s);
       }
-      const int q = item / p.H;
-      c.ref = __ldg(reinterpret_cast<const float4*>(p.ref) + (size_t)b * p.Lq + q);
+      c.ref = __ldg(reinterpret_cast<const float4*>(p.ref) + b * p.Lq + c.q);
       c.ps = __ldg(p.pts_scale + pl);
       // ((raw * num_points_scale) * ref_wh) * offset_scale, then ref_xy + offset
       // (dfine_decoder.py:159-166), evaluated left to right without contraction.
@@ -77,7 +90,7 @@ __device__ __forceinline__ PointCtx point_phase(const MsdaParams& p, int b, int 
     const float m = group_max<LPI>(logit);
     const float e = c.active ? expf(logit - m) : 0.f;
     const float sum = group_sum<LPI>(e);
-    c.a = e / sum;
+    c.a = __fdividef(e, sum);
   } else if (c.active) {
     const float2 l2 = __ldg(reinterpret_cast<const float2*>(p.samp) + s);
     lx = l2.x;
@@ -88,11 +101,21 @@ __device__ __forceinline__ PointCtx point_phase(const MsdaParams& p, int b, int 
   return c;
 }
 
-// flattened pixel index of corner j (0 nw, 1 ne, 2 sw, 3 se) or -1 when out of bounds
-__device__ __forceinline__ int corner_pixel(const PointCtx& c, int j) {
+// level-local pixel index y*w+x of corner j (0 nw, 1 ne, 2 sw, 3 se), -1 when out of bounds
+__device__ __forceinline__ int corner_pixel_local(const PointCtx& c, int j) {
   const int x = c.g.x0 + (j & 1), y = c.g.y0 + (j >> 1);
   const bool in = c.g.inrange && x >= 0 && x < c.lw && y >= 0 && y < c.lh;
-  return in ? c.lstart + y * c.lw + x : -1;
+  return in ? y * c.lw + x : -1;
+}
+
+// Global address of the head slice of corner `pix` (flattened pixel incl. level start) of
+// the lane's item, or the zero row when the corner is out of bounds.
+template <typename VT>
+__device__ __forceinline__ uint64_t corner_address(const MsdaParams& p, const char* img, int h,
+                                                   int pix_local, int lstart) {
+  const uint32_t off = (uint32_t)(pix_local + lstart) * (uint32_t)p.stride_l + (uint32_t)(h * p.c);
+  const char* a = img + (size_t)off * sizeof(VT);
+  return reinterpret_cast<uint64_t>(pix_local >= 0 ? a : reinterpret_cast<const char*>(g_zero_row));
 }
 
 }  // namespace dfine

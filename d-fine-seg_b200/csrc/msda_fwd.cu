@@ -4,13 +4,16 @@
 // and, in fused-input mode, the softmax + sampling-location arithmetic of
 // MSDeformableAttention.forward (reference src/d_fine/arch/dfine_decoder.py:144-166).
 //
-// Work decomposition: one warp per (image b, query q, head h).
-//   phase 1  lane p < P owns sampling point p: (fused: location arithmetic + softmax over
-//            the P lanes with warp shuffles) -> bit-exact bilinear geometry -> the four
-//            (element offset, weight*attention) corner records go to a per-warp smem table.
-//   phase 2  the 4P corners are gathered LPC lanes per corner, 16 bytes per lane, i.e. one
-//            warp-wide load instruction fetches 32/LPC whole head-slices (c channels each)
-//            fully coalesced per corner.  All loads of a batch are issued before the FMAs.
+// Work decomposition: one warp per IPW = 2 items (item = (query q, head h) of image
+// blockIdx.y).
+//   phase 1  half a warp per item, one lane per sampling point: (fused: location arithmetic
+//            + softmax over the points with warp shuffles) -> bit-exact bilinear geometry ->
+//            four 16-byte corner records {global address of the corner's head slice,
+//            weight*attention} in a per-warp smem table.  Out-of-bounds corners point at a
+//            row of zeros (zeros padding) so the gather needs no predicate.
+//   phase 2  per item, the 4P corners are gathered LPC lanes per corner, 16 bytes per lane:
+//            one warp-wide load instruction fetches 32/LPC whole head slices, coalesced per
+//            corner.  All U loads of a batch are issued before the first FMA.
 //   phase 3  reduce-scatter across the corner slots with warp shuffles; every lane ends up
 //            with distinct channels and the warp stores its c outputs as one segment.
 //
@@ -55,44 +58,49 @@ struct SlotReduce {
   }
 };
 
-template <typename VT, int LPC, int IPW>
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+// kP: points per head known at compile time (12 in every D-FINE config), 0 = runtime.
+// IPW: items per warp (2 when P <= 16).
+// (the explicit min-blocks hint makes ptxas hoist all U gather loads ahead of their consumers)
+template <typename VT, int LPC, int IPW, int kP>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 4)
 msda_fwd_kernel(const MsdaParams p) {
   constexpr int VPL = Vec16<VT>::kElems;   // channels per lane
   constexpr int CPR = 32 / LPC;            // corners per warp-wide load
   constexpr int LPI = 32 / IPW;            // lanes (= max points) per item in phase 1
   constexpr int U = 6;                     // loads in flight per lane
 
-  // per warp: IPW x (4*LPI) corner records {element offset | 0xffffffff, weight*attn}
-  __shared__ __align__(16) uint2 s_rec[kWarpsPerCta][128];
+  // per warp: IPW x (4*LPI) corner records {address lo, address hi, weight*attn, -}
+  __shared__ __align__(16) uint4 s_rec[kWarpsPerCta][128];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
   const int n_items = p.Lq * p.H;
   const int item0 = (blockIdx.x * kWarpsPerCta + warp) * IPW;
   if (item0 >= n_items) return;
-  const int ncorner = 4 * p.P;
+  const int P = kP ? kP : p.P;
+  const int ncorner = 4 * P;
+  const char* img = reinterpret_cast<const char*>(reinterpret_cast<const VT*>(p.value) +
+                                                  (size_t)b * p.stride_b);
 
   // ---- phase 1: per-point geometry -------------------------------------------------
   {
     const int slot_i = lane / LPI, pl = lane % LPI;
     const int item = item0 + slot_i;
-    const PointCtx c = point_phase<LPI>(p, b, item, pl, item < n_items);
+    const PointCtx c = point_phase<LPI>(p, P, b, item, pl, item < n_items);
     if (c.active) {
       const float wt[4] = {c.g.fs * c.g.fe, c.g.fs * c.g.fw, c.g.fn * c.g.fe, c.g.fn * c.g.fw};
       int pix[4];
-      uint32_t rec[8];
+      uint4* dst = &s_rec[warp][slot_i * 4 * LPI + 4 * pl];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        pix[j] = corner_pixel(c, j);
-        rec[2 * j] = pix[j] >= 0 ? (uint32_t)pix[j] * (uint32_t)p.stride_l : 0xffffffffu;
-        rec[2 * j + 1] = __float_as_uint(wt[j] * c.a);
+        pix[j] = corner_pixel_local(c, j);
+        const uint64_t a = corner_address<VT>(p, img, c.h, pix[j], c.lstart);
+        dst[j] = make_uint4((uint32_t)a, (uint32_t)(a >> 32), __float_as_uint(wt[j] * c.a), 0u);
       }
-      uint4* dst = reinterpret_cast<uint4*>(&s_rec[warp][slot_i * 4 * LPI + 4 * pl]);
-      dst[0] = make_uint4(rec[0], rec[1], rec[2], rec[3]);
-      dst[1] = make_uint4(rec[4], rec[5], rec[6], rec[7]);
       if (p.idx_debug) {
-        const size_t s = ((size_t)b * n_items + item) * p.P + pl;
+        const size_t s = ((size_t)b * n_items + item) * P + pl;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pix[j] = pix[j] >= 0 ? pix[j] + c.lstart : -1;
         reinterpret_cast<int4*>(p.idx_debug)[s] = make_int4(pix[0], pix[1], pix[2], pix[3]);
       }
     }
@@ -101,29 +109,30 @@ msda_fwd_kernel(const MsdaParams p) {
 
   // ---- phase 2 + 3: gather, reduce over corner slots, store ---------------------------
   const int slot = lane / LPC;
-  const int sub = lane % LPC;
-  const VT* vimg = reinterpret_cast<const VT*>(p.value) + (size_t)b * p.stride_b + sub * VPL;
+  const uint32_t sub_bytes = (uint32_t)(lane % LPC) * 16u;
 #pragma unroll
   for (int it = 0; it < IPW; ++it) {
     const int item = item0 + it;
     if (item >= n_items) break;
-    const int h = item % p.H;
-    const VT* vbase = vimg + h * p.c;
-    const uint2* rec = &s_rec[warp][it * 4 * LPI];
+    const uint4* rec = &s_rec[warp][it * 4 * LPI];
     float acc[VPL];
 #pragma unroll
     for (int i = 0; i < VPL; ++i) acc[i] = 0.f;
+#pragma unroll 1
     for (int k0 = 0; k0 < ncorner; k0 += U * CPR) {
       typename Vec16<VT>::Raw raw[U];
       float cw[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int k = k0 + u * CPR + slot;
-        uint2 r = make_uint2(0xffffffffu, 0u);
-        if (k < ncorner) r = rec[k];
-        cw[u] = __uint_as_float(r.y);
-        raw[u] = Vec16<VT>::zero();  // masked gather of 0 (zeros padding)
-        if (r.x != 0xffffffffu) raw[u] = Vec16<VT>::load_raw(vbase + r.x);
+        int k = k0 + u * CPR + slot;
+        const bool live = k < ncorner;   // folds away when kP divides evenly
+        k = live ? k : 0;
+        const uint4 r = rec[k];
+        cw[u] = live ? __uint_as_float(r.z) : 0.f;
+        const char* a = reinterpret_cast<const char*>(((uint64_t)r.y << 32) | r.x);
+        if (!live) a = reinterpret_cast<const char*>(g_zero_row);  // idle slot of a ragged tail
+        a += sub_bytes;
+        raw[u] = Vec16<VT>::load_raw(reinterpret_cast<const VT*>(a));
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -138,7 +147,7 @@ msda_fwd_kernel(const MsdaParams p) {
     SlotReduce<LPC, VPL>::run(acc, lane, base, writer);
     constexpr int n = SlotReduce<LPC, VPL>::kOut;
     if (writer) {
-      const size_t o = ((size_t)b * n_items + item) * p.c + sub * VPL + base;
+      const size_t o = ((size_t)b * n_items + item) * p.c + (lane % LPC) * VPL + base;
       if (p.out_bf16) {
         __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out) + o;
 #pragma unroll
@@ -154,8 +163,8 @@ msda_fwd_kernel(const MsdaParams p) {
 
 template <typename VT, int LPC>
 static int launch_fwd_t(const MsdaParams& p, cudaStream_t s) {
-  if ((long long)p.L * p.stride_l >= 0x7fffffffLL) {
-    set_error("msda_fwd: one image of value spans %lld elements; 32-bit offsets need < 2^31",
+  if ((long long)p.L * p.stride_l + (long long)p.H * p.c >= 0xffffffffLL) {
+    set_error("msda_fwd: one image of value spans %lld elements; offsets need < 2^32",
               (long long)p.L * p.stride_l);
     return DFINE_E_SHAPE;
   }
@@ -167,10 +176,12 @@ static int launch_fwd_t(const MsdaParams& p, cudaStream_t s) {
     return DFINE_E_SHAPE;
   }
   const dim3 grid((unsigned)ctas, (unsigned)p.B);
-  if (ipw == 2)
-    msda_fwd_kernel<VT, LPC, 2><<<grid, kWarpsPerCta * 32, 0, s>>>(p);
+  if (p.P == 12)
+    msda_fwd_kernel<VT, LPC, 2, 12><<<grid, kWarpsPerCta * 32, 0, s>>>(p);
+  else if (ipw == 2)
+    msda_fwd_kernel<VT, LPC, 2, 0><<<grid, kWarpsPerCta * 32, 0, s>>>(p);
   else
-    msda_fwd_kernel<VT, LPC, 1><<<grid, kWarpsPerCta * 32, 0, s>>>(p);
+    msda_fwd_kernel<VT, LPC, 1, 0><<<grid, kWarpsPerCta * 32, 0, s>>>(p);
   return (int)cudaGetLastError();
 }
 

@@ -183,25 +183,46 @@ def msda_forward_raw(memory, spec: LevelSpec, H: int, samp, attn, ref, pts_scale
 
 
 def msda_backward_raw(memory, spec: LevelSpec, H: int, samp, attn, ref, pts_scale,
-                      offset_scale: float, fused: bool, grad_out):
-    """Direct call of dfine_msda_bwd.  Returns fp32 (grad_memory [B,L,C], grad_samp, grad_attn)."""
+                      offset_scale: float, fused: bool, grad_out,
+                      gv_dtype: torch.dtype = torch.float32, force_atomic: bool = False):
+    """Direct call of dfine_msda_bwd.  Returns (grad_memory [B,L,C] in `gv_dtype`, fp32
+    grad_samp, fp32 grad_attn).  The library normally produces grad_memory with its
+    atomic-free gather path directly in `gv_dtype`; shapes it cannot take (or
+    force_atomic=True) use fp32 vector reductions, followed by a cast if bf16 was asked."""
     _require_cuda(memory, samp, attn, grad_out)
     B, L, C = memory.shape
     c = C // H
     Lq = samp.shape[1]
     sb, sl = _mem_strides(memory)
     dev = memory.device
-    g_mem = torch.empty((B, spec.L, C), dtype=torch.float32, device=dev)
     g_samp = torch.empty(samp.shape, dtype=torch.float32, device=dev)
     g_attn = torch.empty(attn.shape, dtype=torch.float32, device=dev)
-    with torch.cuda.device_of(memory), _timed("msda_bwd", memory):
-        rc = _lib.lib().dfine_msda_bwd(
-            memory.data_ptr(), sb, sl, spec.hw_c, spec.start_c, spec.npts_c, spec.n_lvl,
-            samp.data_ptr(), attn.data_ptr(), _ptr(ref), _ptr(pts_scale), float(offset_scale),
-            grad_out.data_ptr(), g_mem.data_ptr(), g_samp.data_ptr(), g_attn.data_ptr(),
-            B, Lq, H, c, _dt(memory, "value"), _dt(samp, "samp"), _dt(grad_out, "grad_out"),
-            MSDA_FUSED_INPUTS if fused else 0, _stream(memory))
-    check(rc, "dfine_msda_bwd")
+    base_flags = MSDA_FUSED_INPUTS if fused else 0
+    ws, ws_bytes = None, 0
+    if not force_atomic:
+        ws_bytes = _lib.lib().dfine_msda_bwd_workspace_bytes(B, Lq, H, spec.P)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+
+    def call(buf, flags):
+        with torch.cuda.device_of(memory), _timed("msda_bwd", memory, 2):
+            return _lib.lib().dfine_msda_bwd(
+                memory.data_ptr(), sb, sl, spec.hw_c, spec.start_c, spec.npts_c, spec.n_lvl,
+                samp.data_ptr(), attn.data_ptr(), _ptr(ref), _ptr(pts_scale), float(offset_scale),
+                grad_out.data_ptr(), buf.data_ptr(), g_samp.data_ptr(), g_attn.data_ptr(),
+                B, Lq, H, c, _dt(memory, "value"), _dt(samp, "samp"), _dt(grad_out, "grad_out"),
+                flags, _ptr(ws), ws_bytes, _stream(memory))
+
+    if gv_dtype == torch.bfloat16 and not force_atomic:
+        g_mem = torch.empty((B, spec.L, C), dtype=torch.bfloat16, device=dev)
+        rc = call(g_mem, base_flags | _lib.MSDA_GRAD_VALUE_BF16)
+        if rc == 0:
+            return g_mem, g_samp, g_attn
+        if rc != _lib.E_UNSUPPORTED:
+            check(rc, "dfine_msda_bwd")
+    g_mem = torch.empty((B, spec.L, C), dtype=torch.float32, device=dev)
+    check(call(g_mem, base_flags | (_lib.MSDA_FORCE_ATOMIC if force_atomic else 0)), "dfine_msda_bwd")
+    if gv_dtype == torch.bfloat16:
+        g_mem = cast_f32_to_bf16(g_mem)
     return g_mem, g_samp, g_attn
 
 
@@ -233,9 +254,7 @@ class _MsdaFn(torch.autograd.Function):
             grad_out = grad_out.float()
         g_mem, g_samp, g_attn = msda_backward_raw(memory, ctx.spec, ctx.H, samp, attn, ref,
                                                   pts_scale, ctx.offset_scale, ctx.fused,
-                                                  grad_out.contiguous())
-        if memory.dtype == torch.bfloat16:
-            g_mem = cast_f32_to_bf16(g_mem)
+                                                  grad_out.contiguous(), gv_dtype=memory.dtype)
         if g_samp.dtype != samp.dtype:
             g_samp = g_samp.to(samp.dtype)
             g_attn = g_attn.to(attn.dtype)

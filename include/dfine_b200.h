@@ -49,7 +49,9 @@ extern "C" {
 #define DFINE_MAX_POINTS 32 /* sum(num_points_list) per head */
 
 /* flags for dfine_msda_fwd / dfine_msda_bwd */
-#define DFINE_MSDA_FUSED_INPUTS 1 /* sampling inputs are raw Linear outputs + ref boxes */
+#define DFINE_MSDA_FUSED_INPUTS 1    /* sampling inputs are raw Linear outputs + ref boxes */
+#define DFINE_MSDA_GRAD_VALUE_BF16 2 /* bwd: grad_value is a bf16 buffer (AMP) */
+#define DFINE_MSDA_FORCE_ATOMIC 4    /* bwd: force the fp32 vector-reduction fallback */
 
 DFINE_API int dfine_version(void);
 DFINE_API const char* dfine_last_error(void);
@@ -100,8 +102,13 @@ DFINE_API int dfine_msda_fwd(const void* value, int64_t v_stride_b, int64_t v_st
  * arithmetic backward of dfine_decoder.py:144-166.
  *
  * grad_out    go_dtype [B, Lq, H*c] contiguous
- * grad_value  float32  [B, L, H, c] contiguous (L = sum h_l*w_l).  The library
- *             zero-fills it on `stream` before accumulating.
+ * grad_value  float32 (or bf16 with DFINE_MSDA_GRAD_VALUE_BF16) [B, L, H, c] contiguous
+ *             (L = sum h_l*w_l); every element is written (no pre-zeroing needed).  With a
+ *             workspace the library builds a per-(image, head, level) pixel CSR in shared
+ *             memory and gathers, so no float atomics are used; without one, or for shapes
+ *             whose CSR does not fit shared memory, it falls back to fp32 vector reductions
+ *             (float32 buffer only; a bf16 request then returns DFINE_E_UNSUPPORTED).
+ * workspace   caller-owned device scratch of dfine_msda_bwd_workspace_bytes() bytes, or NULL
  * grad_samp   float32  [B, Lq, H, P, 2]  d/d sampling_locations (plain) or
  *             d/d raw offsets (fused)
  * grad_attn   float32  [B, Lq, H, P]     d/d attention weights (plain) or
@@ -113,9 +120,14 @@ DFINE_API int dfine_msda_bwd(const void* value, int64_t v_stride_b, int64_t v_st
                    const int32_t* lvl_hw, const int32_t* lvl_start, const int32_t* lvl_npts,
                    int n_lvl, const void* samp, const void* attn, const float* ref_boxes,
                    const float* pts_scale, float offset_scale, const void* grad_out,
-                   float* grad_value, float* grad_samp, float* grad_attn, int B, int Lq, int H,
+                   void* grad_value, float* grad_samp, float* grad_attn, int B, int Lq, int H,
                    int c, int value_dtype, int samp_dtype, int go_dtype, int flags,
-                   void* stream);
+                   void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Device scratch (bytes) the atomic-free grad_value path of dfine_msda_bwd needs: one
+ * 16-byte record per sampling point.  Passing workspace == NULL (or too small) selects the
+ * fp32 vector-reduction fallback. */
+DFINE_API int64_t dfine_msda_bwd_workspace_bytes(int B, int Lq, int H, int P);
 
 /* Packs fp32 grad_value [n] to bf16 (AMP: the gradient of a bf16 `memory`). */
 DFINE_API int dfine_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
