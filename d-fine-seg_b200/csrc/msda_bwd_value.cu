@@ -22,7 +22,7 @@
 
 namespace dfine {
 
-constexpr int kBvThreads = 512;
+constexpr int kBvThreads = 1024;
 constexpr int kBvMaxChunks = 32;
 constexpr int kBvMaxChunkPx = 4096;  // chunk-local pixel ids use 13 bits
 
@@ -103,14 +103,18 @@ __device__ __forceinline__ void bv_visit(const uint4 r, int q, int lw, int lh, i
 template <typename GT> struct GoRow;  // 4 consecutive channels of grad_out
 template <> struct GoRow<float> {
   using Raw = float4;
+  template <bool kSmem>
   __device__ static __forceinline__ Raw load(const float* p) {
+    if (kSmem) return *reinterpret_cast<const float4*>(p);
     return __ldg(reinterpret_cast<const float4*>(p));
   }
   __device__ static __forceinline__ float4 widen(const Raw& r) { return r; }
 };
 template <> struct GoRow<__nv_bfloat16> {
   using Raw = uint2;
+  template <bool kSmem>
   __device__ static __forceinline__ Raw load(const __nv_bfloat16* p) {
+    if (kSmem) return *reinterpret_cast<const uint2*>(p);
     return __ldg(reinterpret_cast<const uint2*>(p));
   }
   __device__ static __forceinline__ float4 widen(const Raw& r) {
@@ -119,10 +123,12 @@ template <> struct GoRow<__nv_bfloat16> {
   }
 };
 
-template <int kC, typename GT>
+// kStage: the grad_out slice of this (image, head) -- Lq rows of c channels -- is staged in
+// shared memory with cp.async while the CSR is being built, so that S4 gathers from smem.
+template <int kC, typename GT, bool kStage>
 __global__ void __launch_bounds__(kBvThreads, 1)
 msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ grad_value,
-                      int gv_bf16, int max_px) {
+                      int gv_bf16, int max_px, int cap) {
   constexpr int LPR = kC / 4;          // lanes per row (4 channels each)
   constexpr int WPW = 32 / LPR;        // workers per warp
   constexpr int NWORK = (kBvThreads / 32) * WPW;
@@ -132,6 +138,9 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
   int* s_cur = s_off + (max_px + 1);               // [max_px]
   int* s_warp = s_cur + max_px;                    // [32]
   BvEntry* s_ent = reinterpret_cast<BvEntry*>(s_warp + 32 + 1);  // (2*max_px + 34) ints: 8B aligned
+  // staged grad_out rows follow the entries, 16-byte aligned
+  unsigned char* s_go = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(s_ent + cap) + 15) & ~static_cast<uintptr_t>(15));
 
   const int lvl = ch.lvl[blockIdx.x], px0 = ch.px0[blockIdx.x], px1 = ch.px1[blockIdx.x];
   const int npx = px1 - px0;
@@ -143,6 +152,21 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
   const int nsamp = np * p.Lq;
   const uint4* recs = p.rec + (((size_t)b * p.H + h) * p.P + p0) * p.Lq;
 
+  constexpr int kRowBytes = kC * (int)sizeof(GT);
+  if (kStage) {
+    // cp.async: 16 bytes per thread, rows of kRowBytes (global row stride H*c elements)
+    constexpr int CPRW = kRowBytes / 16;  // chunks per row
+    const char* src = reinterpret_cast<const char*>(
+        reinterpret_cast<const GT*>(p.grad_out) + (size_t)b * p.Lq * p.H * kC + (size_t)h * kC);
+    const size_t src_row = (size_t)p.H * kC * sizeof(GT);
+    for (int i = tid; i < p.Lq * CPRW; i += kBvThreads) {
+      const int q = i / CPRW, k = i % CPRW;
+      const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(s_go + q * kRowBytes + k * 16));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + q * src_row + k * 16)
+                   : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   for (int i = tid; i < npx; i += kBvThreads) s_cur[i] = 0;
   __syncthreads();
   // S1: count corners per pixel
@@ -156,6 +180,7 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
   // S3: fill
   for (int t = tid; t < nsamp; t += kBvThreads)
     bv_visit<true>(__ldg(recs + t), t % p.Lq, lw, lh, px0, px1, s_cur, s_ent);
+  if (kStage) asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
   // S4: gather
@@ -173,59 +198,68 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
   };
   const int pa = worker == 0 ? 0 : first_px_at((int)((long long)total * worker / NWORK));
   const int pb = worker == NWORK - 1 ? npx : first_px_at((int)((long long)total * (worker + 1) / NWORK));
-  const uint32_t row_stride = (uint32_t)(p.H * kC);
-  const GT* gob = reinterpret_cast<const GT*>(p.grad_out) + (size_t)b * p.Lq * row_stride +
-                  (size_t)h * kC + 4 * sub;
-  const size_t gv0 = ((size_t)b * p.L + p.lvl_start[lvl] + px0) * row_stride + (size_t)h * kC + 4 * sub;
+  // byte strides of one query row of grad_out / one pixel row of grad_value
+  const uint32_t go_row = kStage ? (uint32_t)kRowBytes : (uint32_t)(p.H * kC) * (uint32_t)sizeof(GT);
+  const uint32_t gv_row = (uint32_t)(p.H * kC) * (gv_bf16 ? 2u : 4u);
+  const char* gob = kStage ? reinterpret_cast<const char*>(s_go) + 4 * sub * sizeof(GT)
+                           : reinterpret_cast<const char*>(reinterpret_cast<const GT*>(p.grad_out) +
+                                                           (size_t)b * p.Lq * p.H * kC +
+                                                           (size_t)h * kC + 4 * sub);
+  char* gvb = reinterpret_cast<char*>(grad_value) +
+              (((size_t)b * p.L + p.lvl_start[lvl] + px0) * p.H * kC + (size_t)h * kC + 4 * sub) *
+                  (gv_bf16 ? 2 : 4);
 
-  auto store_row = [&](int px, const float4& v) {
-    const size_t o = gv0 + (size_t)px * row_stride;
+  auto store_row = [&](int px, const float4& v, bool pred) {
+    char* o = gvb + (uint32_t)px * gv_row;
     if (gv_bf16) {
       const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
       uint2 pk;
       pk.x = *reinterpret_cast<const uint32_t*>(&lo);
       pk.y = *reinterpret_cast<const uint32_t*>(&hi);
-      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(grad_value) + o) = pk;
+      if (pred) *reinterpret_cast<uint2*>(o) = pk;
     } else {
-      *reinterpret_cast<float4*>(reinterpret_cast<float*>(grad_value) + o) = v;
+      if (pred) *reinterpret_cast<float4*>(o) = v;
     }
+  };
+  // one CSR entry: flush the finished row when the pixel changes (predicated, no branch)
+  auto consume = [&](const BvEntry& en, const float4& g, float4& acc, int& cur) {
+    const int px = (int)(en.qp & 0x1fffu);
+    const bool fresh = px != cur;
+    store_row(cur, acc, fresh && cur >= 0);
+    acc.x = fmaf(en.cw, g.x, fresh ? 0.f : acc.x);
+    acc.y = fmaf(en.cw, g.y, fresh ? 0.f : acc.y);
+    acc.z = fmaf(en.cw, g.z, fresh ? 0.f : acc.z);
+    acc.w = fmaf(en.cw, g.w, fresh ? 0.f : acc.w);
+    cur = px;
   };
 
   if (pa < pb) {
     const int e1 = s_off[pb];
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int cur = -1;
-    for (int e = s_off[pa]; e < e1; e += U) {
+    int e = s_off[pa];
+    for (; e + U <= e1; e += U) {
       BvEntry ent[U];
       typename GoRow<GT>::Raw raw[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int ee = min(e + u, e1 - 1);  // clamp: the tail re-reads the last entry, unused
-        ent[u] = s_ent[ee];
-        raw[u] = GoRow<GT>::load(gob + (size_t)(ent[u].qp >> 13) * row_stride);
+        ent[u] = s_ent[e + u];
+        raw[u] = GoRow<GT>::template load<kStage>(reinterpret_cast<const GT*>(gob + (ent[u].qp >> 13) * go_row));
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (e + u < e1) {
-          const int px = (int)(ent[u].qp & 0x1fffu);
-          if (px != cur) {
-            if (cur >= 0) store_row(cur, acc);
-            acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            cur = px;
-          }
-          const float4 g = GoRow<GT>::widen(raw[u]);
-          acc.x = fmaf(ent[u].cw, g.x, acc.x);
-          acc.y = fmaf(ent[u].cw, g.y, acc.y);
-          acc.z = fmaf(ent[u].cw, g.z, acc.z);
-          acc.w = fmaf(ent[u].cw, g.w, acc.w);
-        }
-      }
+      for (int u = 0; u < U; ++u) consume(ent[u], GoRow<GT>::widen(raw[u]), acc, cur);
     }
-    if (cur >= 0) store_row(cur, acc);
+    for (; e < e1; ++e) {
+      const BvEntry en = s_ent[e];
+      const typename GoRow<GT>::Raw raw =
+          GoRow<GT>::template load<kStage>(reinterpret_cast<const GT*>(gob + (en.qp >> 13) * go_row));
+      consume(en, GoRow<GT>::widen(raw), acc, cur);
+    }
+    store_row(cur, acc, cur >= 0);
   }
   // pixels that no sample touched: explicit zeros (this replaces the memset pass)
   for (int px = worker; px < npx; px += NWORK)
-    if (s_off[px + 1] == s_off[px]) store_row(px, make_float4(0.f, 0.f, 0.f, 0.f));
+    store_row(px, make_float4(0.f, 0.f, 0.f, 0.f), s_off[px + 1] == s_off[px]);
 }
 
 size_t msda_bwd_workspace_bytes(int B, int Lq, int H, int P) {
@@ -258,32 +292,39 @@ int launch_msda_bwd_value(const MsdaParams& p, void* grad_value, int gv_bf16, cu
     const long long c = 4LL * np * p.Lq;
     if (c > cap) cap = (int)(c > 0x3fffffff ? 0x3fffffff : c);
   }
-  const size_t smem = (size_t)(2 * max_px + 34) * sizeof(int) + (size_t)cap * sizeof(BvEntry) + 16;
-  if (smem > 200 * 1024) return DFINE_E_UNSUPPORTED;
+  const size_t base_smem = (size_t)(2 * max_px + 34) * sizeof(int) + (size_t)cap * sizeof(BvEntry) + 32;
+  const size_t go_smem = (size_t)p.Lq * p.c * (p.go_bf16 ? 2 : 4);
+  constexpr size_t kSmemLimit = 227 * 1024;
+  if (base_smem > kSmemLimit) return DFINE_E_UNSUPPORTED;
+  const bool stage = base_smem + go_smem <= kSmemLimit;
+  const size_t smem = base_smem + (stage ? go_smem : 0);
   if (p.c != 16 && p.c != 32 && p.c != 64) return DFINE_E_UNSUPPORTED;
   if (!grad_value) return 0;
   const dim3 grid((unsigned)ch.n, (unsigned)p.H, (unsigned)p.B);
   cudaError_t e = cudaSuccess;
-#define DFINE_BV_LAUNCH(C, GT)                                                                   \
+#define DFINE_BV_LAUNCH2(C, GT, ST)                                                              \
   do {                                                                                           \
-    e = cudaFuncSetAttribute(msda_bwd_value_kernel<C, GT>,                                       \
+    e = cudaFuncSetAttribute(msda_bwd_value_kernel<C, GT, ST>,                                   \
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
     if (e == cudaSuccess)                                                                        \
-      msda_bwd_value_kernel<C, GT><<<grid, kBvThreads, smem, s>>>(p, ch, grad_value, gv_bf16,    \
-                                                                  max_px);                       \
+      msda_bwd_value_kernel<C, GT, ST><<<grid, kBvThreads, smem, s>>>(p, ch, grad_value,         \
+                                                                      gv_bf16, max_px, cap);     \
+  } while (0)
+#define DFINE_BV_LAUNCH(C, GT)                                                                   \
+  do {                                                                                           \
+    if (stage) DFINE_BV_LAUNCH2(C, GT, true); else DFINE_BV_LAUNCH2(C, GT, false);               \
   } while (0)
   if (p.go_bf16) {
     if (p.c == 16) DFINE_BV_LAUNCH(16, __nv_bfloat16);
     else if (p.c == 32) DFINE_BV_LAUNCH(32, __nv_bfloat16);
-    else if (p.c == 64) DFINE_BV_LAUNCH(64, __nv_bfloat16);
-    else return DFINE_E_UNSUPPORTED;
+    else DFINE_BV_LAUNCH(64, __nv_bfloat16);
   } else {
     if (p.c == 16) DFINE_BV_LAUNCH(16, float);
     else if (p.c == 32) DFINE_BV_LAUNCH(32, float);
-    else if (p.c == 64) DFINE_BV_LAUNCH(64, float);
-    else return DFINE_E_UNSUPPORTED;
+    else DFINE_BV_LAUNCH(64, float);
   }
 #undef DFINE_BV_LAUNCH
+#undef DFINE_BV_LAUNCH2
   if (e != cudaSuccess) return (int)e;
   return (int)cudaGetLastError();
 }
