@@ -302,10 +302,16 @@ int launch_msda_bwd_value(const MsdaParams& p, void* grad_value, int gv_bf16, cu
   if (!grad_value) return 0;
   const dim3 grid((unsigned)ch.n, (unsigned)p.H, (unsigned)p.B);
   cudaError_t e = cudaSuccess;
+  // the opt-in shared-memory ceiling is raised once per instantiation (not per launch, so that
+  // nothing but the launch itself happens under CUDA-graph capture)
 #define DFINE_BV_LAUNCH2(C, GT, ST)                                                              \
   do {                                                                                           \
-    e = cudaFuncSetAttribute(msda_bwd_value_kernel<C, GT, ST>,                                   \
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
+    static bool configured = false;                                                              \
+    if (!configured) {                                                                           \
+      e = cudaFuncSetAttribute(msda_bwd_value_kernel<C, GT, ST>,                                 \
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit);    \
+      configured = e == cudaSuccess;                                                             \
+    }                                                                                            \
     if (e == cudaSuccess)                                                                        \
       msda_bwd_value_kernel<C, GT, ST><<<grid, kBvThreads, smem, s>>>(p, ch, grad_value,         \
                                                                       gv_bf16, max_px, cap);     \
