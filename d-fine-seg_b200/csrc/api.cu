@@ -55,7 +55,7 @@ static int fill_msda(MsdaParams& p, const char* fn, const void* value, int64_t s
                      const int32_t* lvl_hw, const int32_t* lvl_start, const int32_t* lvl_npts,
                      int n_lvl, const void* samp, const void* attn, const float* ref,
                      const float* pts_scale, float offset_scale, int B, int Lq, int H, int c,
-                     int value_dtype, int samp_dtype, int flags) {
+                     int value_dtype, int samp_dtype, int flags, int64_t samp_rs, int64_t attn_rs) {
   memset(&p, 0, sizeof p);
   if (!lvl_hw || !lvl_start || !lvl_npts) {
     set_error("%s: level tables must be host pointers, got NULL", fn);
@@ -128,10 +128,20 @@ static int fill_msda(MsdaParams& p, const char* fn, const void* value, int64_t s
               (long long)sl, H * c);
     return DFINE_E_SHAPE;
   }
-  if (!aligned16(samp) || !aligned16(attn)) {
-    set_error("%s: samp / attn must be 16-byte aligned", fn);
+  if ((reinterpret_cast<uintptr_t>(samp) & 7u) || (reinterpret_cast<uintptr_t>(attn) & 3u)) {
+    set_error("%s: samp must be 8-byte and attn 4-byte aligned", fn);
     return DFINE_E_ALIGN;
   }
+  if (samp_rs == 0) samp_rs = 2LL * H * P;
+  if (attn_rs == 0) attn_rs = (int64_t)H * P;
+  if (samp_rs < 2LL * H * P || attn_rs < (int64_t)H * P || (samp_rs & 1) ||
+      (long long)B * Lq * samp_rs >= 0x7fffffffLL || (long long)B * Lq * attn_rs >= 0x7fffffffLL) {
+    set_error("%s: row strides (%lld, %lld) must be >= (2HP, HP), samp's even, and B*Lq*stride < 2^31",
+              fn, (long long)samp_rs, (long long)attn_rs);
+    return DFINE_E_SHAPE;
+  }
+  p.samp_rs = (int)samp_rs;
+  p.attn_rs = (int)attn_rs;
   p.value = value;
   p.stride_b = sb;
   p.stride_l = sl;
@@ -182,11 +192,11 @@ int dfine_msda_fwd(const void* value, int64_t v_stride_b, int64_t v_stride_l,
                    int n_lvl, const void* samp, const void* attn, const float* ref_boxes,
                    const float* pts_scale, float offset_scale, void* out, int32_t* idx_debug,
                    int B, int Lq, int H, int c, int value_dtype, int samp_dtype, int out_dtype,
-                   int flags, void* stream) {
+                   int flags, int64_t samp_row_stride, int64_t attn_row_stride, void* stream) {
   MsdaParams p;
   int rc = fill_msda(p, "dfine_msda_fwd", value, v_stride_b, v_stride_l, lvl_hw, lvl_start,
                      lvl_npts, n_lvl, samp, attn, ref_boxes, pts_scale, offset_scale, B, Lq, H, c,
-                     value_dtype, samp_dtype, flags);
+                     value_dtype, samp_dtype, flags, samp_row_stride, attn_row_stride);
   if (rc) return rc;
   if ((rc = require_device(out, "out", "dfine_msda_fwd"))) return rc;
   if (out_dtype != DFINE_F32 && out_dtype != DFINE_BF16) {
@@ -207,13 +217,15 @@ int dfine_msda_bwd(const void* value, int64_t v_stride_b, int64_t v_stride_l,
                    const int32_t* lvl_hw, const int32_t* lvl_start, const int32_t* lvl_npts,
                    int n_lvl, const void* samp, const void* attn, const float* ref_boxes,
                    const float* pts_scale, float offset_scale, const void* grad_out,
-                   void* grad_value, float* grad_samp, float* grad_attn, int B, int Lq, int H,
+                   void* grad_value, void* grad_samp, void* grad_attn, int B, int Lq, int H,
                    int c, int value_dtype, int samp_dtype, int go_dtype, int flags,
-                   void* workspace, int64_t workspace_bytes, void* stream) {
+                   int64_t samp_row_stride, int64_t attn_row_stride, int64_t gsamp_row_stride,
+                   int64_t gattn_row_stride, void* workspace, int64_t workspace_bytes,
+                   void* stream) {
   MsdaParams p;
   int rc = fill_msda(p, "dfine_msda_bwd", value, v_stride_b, v_stride_l, lvl_hw, lvl_start,
                      lvl_npts, n_lvl, samp, attn, ref_boxes, pts_scale, offset_scale, B, Lq, H, c,
-                     value_dtype, samp_dtype, flags);
+                     value_dtype, samp_dtype, flags, samp_row_stride, attn_row_stride);
   if (rc) return rc;
   if ((rc = require_device(grad_out, "grad_out", "dfine_msda_bwd"))) return rc;
   if ((rc = require_device(grad_value, "grad_value", "dfine_msda_bwd"))) return rc;
@@ -223,16 +235,29 @@ int dfine_msda_bwd(const void* value, int64_t v_stride_b, int64_t v_stride_l,
     set_error("dfine_msda_bwd: go_dtype must be DFINE_F32 or DFINE_BF16");
     return DFINE_E_UNSUPPORTED;
   }
-  if (!aligned16(grad_out) || !aligned16(grad_value) || !aligned16(grad_samp) ||
-      !aligned16(grad_attn)) {
-    set_error("dfine_msda_bwd: gradient buffers must be 16-byte aligned");
+  if (!aligned16(grad_out) || !aligned16(grad_value) ||
+      (reinterpret_cast<uintptr_t>(grad_samp) & 7u) || (reinterpret_cast<uintptr_t>(grad_attn) & 3u)) {
+    set_error("dfine_msda_bwd: grad_out / grad_value must be 16-byte, grad_samp 8-byte, grad_attn "
+              "4-byte aligned");
     return DFINE_E_ALIGN;
   }
+  if (gsamp_row_stride == 0) gsamp_row_stride = 2LL * H * p.P;
+  if (gattn_row_stride == 0) gattn_row_stride = (int64_t)H * p.P;
+  if (gsamp_row_stride < 2LL * H * p.P || gattn_row_stride < (int64_t)H * p.P || (gsamp_row_stride & 1) ||
+      (long long)B * Lq * gsamp_row_stride >= 0x7fffffffLL ||
+      (long long)B * Lq * gattn_row_stride >= 0x7fffffffLL) {
+    set_error("dfine_msda_bwd: gradient row strides (%lld, %lld) invalid",
+              (long long)gsamp_row_stride, (long long)gattn_row_stride);
+    return DFINE_E_SHAPE;
+  }
+  p.gsamp_rs = (int)gsamp_row_stride;
+  p.gattn_rs = (int)gattn_row_stride;
+  p.gs_bf16 = (flags & DFINE_MSDA_GRAD_SAMP_BF16) ? 1 : 0;
   p.grad_out = grad_out;
   p.go_bf16 = go_dtype == DFINE_BF16;
   p.grad_value = reinterpret_cast<float*>(grad_value);
-  p.grad_samp = grad_samp;
-  p.grad_attn = grad_attn;
+  p.grad_samp = reinterpret_cast<float*>(grad_samp);
+  p.grad_attn = reinterpret_cast<float*>(grad_attn);
   cudaStream_t s = (cudaStream_t)stream;
   const int gv_bf16 = (flags & DFINE_MSDA_GRAD_VALUE_BF16) ? 1 : 0;
   const size_t ws_need = msda_bwd_workspace_bytes(B, Lq, H, p.P);

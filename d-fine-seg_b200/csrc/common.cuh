@@ -32,6 +32,9 @@ struct MsdaParams {
   int lvl_h[kMaxLevels], lvl_w[kMaxLevels], lvl_start[kMaxLevels], lvl_pend[kMaxLevels];
   int samp_bf16, out_bf16, go_bf16, fused;
   int h_shift;           // log2(H) when H is a power of two, else -1
+  int samp_rs, attn_rs;  // row strides (elements) of samp / attn per (b, q); contiguous: 2HP / HP
+  int gsamp_rs, gattn_rs;  // same for grad_samp / grad_attn
+  int gs_bf16;           // bwd: grad_samp / grad_attn are bf16
 };
 
 // One bilinear sample: integer corner origin + the four fractional factors.

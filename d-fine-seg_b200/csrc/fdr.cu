@@ -7,8 +7,9 @@
 //                       + box_xyxy_to_cxcywh               arch/utils.py:70-73
 //   fdr_bwd_kernel      their autograd graph w.r.t. pred_corners
 //
-// One warp per box: the 4 x (reg_max+1) logits are read once, coalesced; softmax and the dot
-// with W(n) are warp-shuffle reductions; lane 0 decodes the box.  HBM-bound, tiny.
+// One warp per box, 8 lanes per edge: the 4 x (reg_max+1) logits are read once; softmax and
+// the dot with W(n) are quarter-warp shuffle reductions, the four edges run concurrently;
+// lane 0 decodes the box.  HBM/latency-bound, tiny.
 #include "common.cuh"
 
 namespace dfine {
@@ -32,7 +33,9 @@ __global__ void fdr_project_kernel(const float* __restrict__ up, const float* __
   project[k] = v;
 }
 
-template <int kMaxBinsPerLane, bool kBackward>
+// One warp per box; the four edges are processed CONCURRENTLY, 8 lanes per edge (bins
+// lane8 + 8*t), so every reduction is a 3-step shuffle inside a quarter warp.
+template <int kBinsPerLane, bool kBackward>
 __global__ void __launch_bounds__(256)
 fdr_kernel(const void* __restrict__ corners, int c_bf16, const float* __restrict__ ref_init,
            const float* __restrict__ project, const float* __restrict__ reg_scale,
@@ -42,79 +45,71 @@ fdr_kernel(const void* __restrict__ corners, int c_bf16, const float* __restrict
   const int lane = threadIdx.x & 31;
   const long long i = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= N) return;
+  const int e = lane >> 3, l8 = lane & 7;  // edge, lane inside the edge group
   const float rs = fabsf(__ldg(reg_scale));
+  const size_t row = ((size_t)i * 4 + e) * nb;
 
-  float w[kMaxBinsPerLane];
+  float x[kBinsPerLane], w[kBinsPerLane];
+  float m = -INFINITY;
 #pragma unroll
-  for (int t = 0; t < kMaxBinsPerLane; ++t) {
-    const int k = lane + 32 * t;
+  for (int t = 0; t < kBinsPerLane; ++t) {
+    const int k = l8 + 8 * t;
     w[t] = k < nb ? __ldg(project + k) : 0.f;
+    x[t] = k < nb ? load_scalar(corners, row + k, c_bf16) : -INFINITY;
+    m = fmaxf(m, x[t]);
   }
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float sum = 0.f;
+#pragma unroll
+  for (int t = 0; t < kBinsPerLane; ++t) {
+    x[t] = (l8 + 8 * t) < nb ? expf(x[t] - m) : 0.f;
+    sum += x[t];
+  }
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  float d = 0.f;
+#pragma unroll
+  for (int t = 0; t < kBinsPerLane; ++t) {
+    x[t] = x[t] / sum;  // Pr(n)
+    d = fmaf(x[t], w[t], d);
+  }
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);  // sum Pr(n) W(n)
 
-  float gd[4] = {0.f, 0.f, 0.f, 0.f};
   if (kBackward) {
+    float gd = 0.f;
     if (grad_boxes) {
       const float4 pt = __ldg(reinterpret_cast<const float4*>(ref_init) + i);
       const float4 gb = __ldg(reinterpret_cast<const float4*>(grad_boxes) + i);
-      const float sx = pt.z / rs, sy = pt.w / rs;
       // cx = (x1+x2)/2, w = x2-x1 with x1 = px-(..+d0)*sx, x2 = px+(..+d2)*sx
-      gd[0] = -(gb.x * 0.5f - gb.z) * sx;
-      gd[1] = -(gb.y * 0.5f - gb.w) * sy;
-      gd[2] = (gb.x * 0.5f + gb.z) * sx;
-      gd[3] = (gb.y * 0.5f + gb.w) * sy;
+      const float sx = pt.z / rs, sy = pt.w / rs;
+      gd = e == 0 ? -(gb.x * 0.5f - gb.z) * sx
+         : e == 1 ? -(gb.y * 0.5f - gb.w) * sy
+         : e == 2 ? (gb.x * 0.5f + gb.z) * sx : (gb.y * 0.5f + gb.w) * sy;
     }
-    if (grad_dist) {
-      const float4 g4 = __ldg(reinterpret_cast<const float4*>(grad_dist) + i);
-      gd[0] += g4.x; gd[1] += g4.y; gd[2] += g4.z; gd[3] += g4.w;
+    if (grad_dist) gd += __ldg(grad_dist + i * 4 + e);
+    // d dist / d logit_k = Pr_k * (W_k - dist)
+#pragma unroll
+    for (int t = 0; t < kBinsPerLane; ++t) {
+      const int k = l8 + 8 * t;
+      if (k < nb) grad_corners[row + k] = gd * x[t] * (w[t] - d);
     }
-  }
-
-  float d[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const size_t row = ((size_t)i * 4 + e) * nb;
-    float x[kMaxBinsPerLane];
-    float m = -INFINITY;
-#pragma unroll
-    for (int t = 0; t < kMaxBinsPerLane; ++t) {
-      const int k = lane + 32 * t;
-      x[t] = k < nb ? load_scalar(corners, row + k, c_bf16) : -INFINITY;
-      m = fmaxf(m, x[t]);
-    }
-    m = warp_max(m);
-    float sum = 0.f, dot = 0.f;
-#pragma unroll
-    for (int t = 0; t < kMaxBinsPerLane; ++t) {
-      x[t] = (lane + 32 * t) < nb ? expf(x[t] - m) : 0.f;
-      sum += x[t];
-    }
-    sum = warp_sum(sum);
-#pragma unroll
-    for (int t = 0; t < kMaxBinsPerLane; ++t) {
-      x[t] = x[t] / sum;  // Pr(n)
-      dot = fmaf(x[t], w[t], dot);
-    }
-    d[e] = warp_sum(dot);  // sum Pr(n) W(n)
-    if (kBackward) {
-      // d dist / d logit_k = Pr_k * (W_k - dist)
-#pragma unroll
-      for (int t = 0; t < kMaxBinsPerLane; ++t) {
-        const int k = lane + 32 * t;
-        if (k < nb) grad_corners[row + k] = gd[e] * x[t] * (w[t] - d[e]);
+  } else {
+    const float d0 = __shfl_sync(0xffffffffu, d, 0), d1 = __shfl_sync(0xffffffffu, d, 8);
+    const float d2 = __shfl_sync(0xffffffffu, d, 16), d3 = __shfl_sync(0xffffffffu, d, 24);
+    if (lane == 0) {
+      if (dist) reinterpret_cast<float4*>(dist)[i] = make_float4(d0, d1, d2, d3);
+      if (boxes) {
+        const float4 pt = __ldg(reinterpret_cast<const float4*>(ref_init) + i);
+        // same operation order as arch/utils.py:134-142, :72
+        const float x1 = pt.x - (0.5f * rs + d0) * (pt.z / rs);
+        const float y1 = pt.y - (0.5f * rs + d1) * (pt.w / rs);
+        const float x2 = pt.x + (0.5f * rs + d2) * (pt.z / rs);
+        const float y2 = pt.y + (0.5f * rs + d3) * (pt.w / rs);
+        reinterpret_cast<float4*>(boxes)[i] =
+            make_float4((x1 + x2) / 2.0f, (y1 + y2) / 2.0f, x2 - x1, y2 - y1);
       }
-    }
-  }
-  if (!kBackward && lane == 0) {
-    if (dist) reinterpret_cast<float4*>(dist)[i] = make_float4(d[0], d[1], d[2], d[3]);
-    if (boxes) {
-      const float4 pt = __ldg(reinterpret_cast<const float4*>(ref_init) + i);
-      // same operation order as arch/utils.py:134-142, :72
-      const float x1 = pt.x - (0.5f * rs + d[0]) * (pt.z / rs);
-      const float y1 = pt.y - (0.5f * rs + d[1]) * (pt.w / rs);
-      const float x2 = pt.x + (0.5f * rs + d[2]) * (pt.z / rs);
-      const float y2 = pt.y + (0.5f * rs + d[3]) * (pt.w / rs);
-      reinterpret_cast<float4*>(boxes)[i] =
-          make_float4((x1 + x2) / 2.0f, (y1 + y2) / 2.0f, x2 - x1, y2 - y1);
     }
   }
 }
@@ -140,12 +135,12 @@ int launch_fdr(bool backward, const void* corners, int c_bf16, const float* ref_
   fdr_kernel<BPL, BWD><<<(unsigned)ctas, 256, 0, s>>>(corners, c_bf16, ref_init, project,      \
                                                       reg_scale, dist, boxes, grad_boxes,      \
                                                       grad_dist, grad_corners, N, nb)
-  if (nb <= 64) {
-    if (backward) DFINE_FDR_LAUNCH(2, true); else DFINE_FDR_LAUNCH(2, false);
+  if (nb <= 40) {  // reg_max = 32: five bins per lane
+    if (backward) DFINE_FDR_LAUNCH(5, true); else DFINE_FDR_LAUNCH(5, false);
   } else if (nb <= 128) {
-    if (backward) DFINE_FDR_LAUNCH(4, true); else DFINE_FDR_LAUNCH(4, false);
+    if (backward) DFINE_FDR_LAUNCH(16, true); else DFINE_FDR_LAUNCH(16, false);
   } else {
-    if (backward) DFINE_FDR_LAUNCH(8, true); else DFINE_FDR_LAUNCH(8, false);
+    if (backward) DFINE_FDR_LAUNCH(32, true); else DFINE_FDR_LAUNCH(32, false);
   }
 #undef DFINE_FDR_LAUNCH
   return (int)cudaGetLastError();

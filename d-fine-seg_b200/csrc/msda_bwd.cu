@@ -203,18 +203,26 @@ msda_bwd_kernel(const MsdaParams p) {
       gx = c.a * s_res[warp][slot_i][1][pl] * (float)c.lw;
       gy = c.a * s_res[warp][slot_i][2][pl] * (float)c.lh;
     }
-    const int s = (b * n_items + item0 + slot_i) * P + pl;
+    const int row = b * p.Lq + c.q;
+    const int hp = c.h * P + pl;
+    const int o_samp = row * p.gsamp_rs + 2 * hp, o_attn = row * p.gattn_rs + hp;
+    float g_attn = S, g_x = gx, g_y = gy;
     if (p.fused) {
       // softmax backward over the points of the head: g_logit = a * (S - sum_j a_j S_j)
       const float dot = group_sum<LPI>(c.active ? c.a * S : 0.f);
-      if (c.active) {
-        p.grad_attn[s] = c.a * (S - dot);
-        const float kx = p.offset_scale * c.ref.z * c.ps, ky = p.offset_scale * c.ref.w * c.ps;
-        reinterpret_cast<float2*>(p.grad_samp)[s] = make_float2(gx * kx, gy * ky);
+      g_attn = c.a * (S - dot);
+      g_x = gx * (p.offset_scale * c.ref.z * c.ps);
+      g_y = gy * (p.offset_scale * c.ref.w * c.ps);
+    }
+    if (c.active) {
+      if (p.gs_bf16) {
+        const __nv_bfloat162 xy = __floats2bfloat162_rn(g_x, g_y);
+        reinterpret_cast<uint32_t*>(p.grad_samp)[o_samp >> 1] = *reinterpret_cast<const uint32_t*>(&xy);
+        reinterpret_cast<__nv_bfloat16*>(p.grad_attn)[o_attn] = __float2bfloat16_rn(g_attn);
+      } else {
+        reinterpret_cast<float2*>(p.grad_samp)[o_samp >> 1] = make_float2(g_x, g_y);
+        p.grad_attn[o_attn] = g_attn;
       }
-    } else if (c.active) {
-      p.grad_attn[s] = S;
-      reinterpret_cast<float2*>(p.grad_samp)[s] = make_float2(gx, gy);
     }
   }
 }

@@ -58,8 +58,12 @@ __device__ __forceinline__ PointCtx point_phase(const MsdaParams& p, int P, int 
     c.q = item / p.H;
     c.h = item - c.q * p.H;
   }
-  // sample index inside [B, Lq, H, P] (the launcher guarantees it fits 31 bits)
-  const int s = (b * p.Lq * p.H + item) * P + pl;
+  // element offsets of this point inside samp / attn: row (b, q) with its own stride, then
+  // (h, p) inside the row (the launcher guarantees 31-bit offsets)
+  const int row = b * p.Lq + c.q;
+  const int hp = c.h * P + pl;
+  const int s_samp = row * p.samp_rs + 2 * hp;   // (x, y) pair
+  const int s_attn = row * p.attn_rs + hp;
   float lx = 0.f, ly = 0.f;
   c.a = 0.f;
   c.ps = 0.f;
@@ -69,17 +73,17 @@ __device__ __forceinline__ PointCtx point_phase(const MsdaParams& p, int P, int 
     if (c.active) {
       float rx, ry;
       if (p.samp_bf16) {
-        const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(p.samp) + s);
+        const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(p.samp) + (s_samp >> 1));
         rx = __uint_as_float(u << 16);
         ry = __uint_as_float(u & 0xffff0000u);
-        logit = __uint_as_float((uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p.attn) + s) << 16);
+        logit = __uint_as_float((uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p.attn) + s_attn) << 16);
       } else {
-        const float2 t = __ldg(reinterpret_cast<const float2*>(p.samp) + s);
+        const float2 t = __ldg(reinterpret_cast<const float2*>(p.samp) + (s_samp >> 1));
         rx = t.x;
         ry = t.y;
-        logit = __ldg(reinterpret_cast<const float*>(p.attn) + s);
+        logit = __ldg(reinterpret_cast<const float*>(p.attn) + s_attn);
       }
-      c.ref = __ldg(reinterpret_cast<const float4*>(p.ref) + b * p.Lq + c.q);
+      c.ref = __ldg(reinterpret_cast<const float4*>(p.ref) + row);
       c.ps = __ldg(p.pts_scale + pl);
       // ((raw * num_points_scale) * ref_wh) * offset_scale, then ref_xy + offset
       // (dfine_decoder.py:159-166), evaluated left to right without contraction.
@@ -92,10 +96,10 @@ __device__ __forceinline__ PointCtx point_phase(const MsdaParams& p, int P, int 
     const float sum = group_sum<LPI>(e);
     c.a = __fdividef(e, sum);
   } else if (c.active) {
-    const float2 l2 = __ldg(reinterpret_cast<const float2*>(p.samp) + s);
+    const float2 l2 = __ldg(reinterpret_cast<const float2*>(p.samp) + (s_samp >> 1));
     lx = l2.x;
     ly = l2.y;
-    c.a = __ldg(reinterpret_cast<const float*>(p.attn) + s);
+    c.a = __ldg(reinterpret_cast<const float*>(p.attn) + s_attn);
   }
   c.g = sample_geometry(lx, ly, c.lh, c.lw);
   return c;

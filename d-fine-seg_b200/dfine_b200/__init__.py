@@ -7,11 +7,12 @@ decode and the tcgen05 mask-prototype GEMM.  No CPU fallback exists.
 from . import _lib, build, ops
 from ._lib import DfineB200Error, library_path
 from .modules import Integral, MSDeformableAttention, patch_model, unpatch_model
-from .ops import (fdr_decode, fdr_integral, fdr_project, mask_logits, msda_core, msda_fused)
+from .ops import (fdr_decode, fdr_integral, fdr_project, mask_logits, msda_core, msda_fused,
+                  msda_fused_packed)
 
 __all__ = [
     "MSDeformableAttention", "Integral", "patch_model", "unpatch_model", "msda_core",
-    "msda_fused", "fdr_project", "fdr_integral", "fdr_decode", "mask_logits", "library_path",
+    "msda_fused", "msda_fused_packed", "fdr_project", "fdr_integral", "fdr_decode", "mask_logits", "library_path",
     "DfineB200Error", "ops", "build",
 ]
 __version__ = "0.1.0"

@@ -16,6 +16,7 @@ F32, BF16 = 0, 1
 MSDA_FUSED_INPUTS = 1
 MSDA_GRAD_VALUE_BF16 = 2
 MSDA_FORCE_ATOMIC = 4
+MSDA_GRAD_SAMP_BF16 = 8
 E_NULL, E_SHAPE, E_UNSUPPORTED, E_ALIGN = -1, -2, -3, -4
 
 _I32P = ctypes.POINTER(c_int32)
@@ -26,11 +27,13 @@ _SIGNATURES = {
     "dfine_last_error": (c_char_p, []),
     "dfine_msda_fwd": (c_int, [c_void_p, c_int64, c_int64, _I32P, _I32P, _I32P, c_int, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
-                               c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+                               c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int64,
+                               c_int64, c_void_p]),
     "dfine_msda_bwd": (c_int, [c_void_p, c_int64, c_int64, _I32P, _I32P, _I32P, c_int, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
-                               c_int, c_int, c_void_p, c_int64, c_void_p]),
+                               c_int, c_int, c_int64, c_int64, c_int64, c_int64, c_void_p, c_int64,
+                               c_void_p]),
     "dfine_msda_bwd_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
     "dfine_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "dfine_fdr_project": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),

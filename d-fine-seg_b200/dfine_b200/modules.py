@@ -35,10 +35,12 @@ def _fused_forward(self, query: torch.Tensor, reference_points: torch.Tensor, va
     P = sum(self.num_points_list)
     last = reference_points.shape[-1]
     if last == 4:
-        raw_off = self.sampling_offsets(query)
-        raw_logit = self.attention_weights(query)
-        return ops.msda_fused(value, value_spatial_shapes, raw_off, raw_logit, reference_points,
-                              self.num_points_scale, self.num_points_list, self.offset_scale)
+        # ONE concatenated Linear (N = 3*H*P) instead of two; its output feeds the kernel
+        # through row strides, its gradient is written by the backward kernel in one piece
+        so, aw = self.sampling_offsets, self.attention_weights
+        raw = ops.fused_linear(query, torch.cat([so.weight, aw.weight], 0), torch.cat([so.bias, aw.bias], 0))
+        return ops.msda_fused_packed(value, value_spatial_shapes, raw, reference_points,
+                                     self.num_points_scale, self.num_points_list, self.offset_scale)
     if last == 2:
         # legacy RT-DETR branch (dfine_decoder.py:149-155); not used by D-FINE.  Location
         # arithmetic stays in torch, sampling runs in the plain-mode kernel.

@@ -162,8 +162,9 @@ def _mem_strides(memory: torch.Tensor) -> Tuple[int, int]:
 
 def msda_forward_raw(memory, spec: LevelSpec, H: int, samp, attn, ref, pts_scale,
                      offset_scale: float, fused: bool, out_dtype: torch.dtype,
-                     want_idx: bool = False):
-    """Direct call of dfine_msda_fwd (no autograd).  Returns out [B, Lq, C] (, idx)."""
+                     want_idx: bool = False, samp_rs: int = 0, attn_rs: int = 0):
+    """Direct call of dfine_msda_fwd (no autograd).  Returns out [B, Lq, C] (, idx).
+    samp_rs / attn_rs: row strides (elements) when samp / attn alias a wider tensor."""
     _require_cuda(memory, samp, attn, ref, pts_scale)
     B, L, C = memory.shape
     c = C // H
@@ -177,14 +178,15 @@ def msda_forward_raw(memory, spec: LevelSpec, H: int, samp, attn, ref, pts_scale
             memory.data_ptr(), sb, sl, spec.hw_c, spec.start_c, spec.npts_c, spec.n_lvl,
             samp.data_ptr(), attn.data_ptr(), _ptr(ref), _ptr(pts_scale), float(offset_scale),
             out.data_ptr(), _ptr(idx), B, Lq, H, c, _dt(memory, "value"), _dt(samp, "samp"),
-            _dt(out, "out"), MSDA_FUSED_INPUTS if fused else 0, _stream(memory))
+            _dt(out, "out"), MSDA_FUSED_INPUTS if fused else 0, samp_rs, attn_rs, _stream(memory))
     check(rc, "dfine_msda_fwd")
     return (out, idx) if want_idx else out
 
 
 def msda_backward_raw(memory, spec: LevelSpec, H: int, samp, attn, ref, pts_scale,
                       offset_scale: float, fused: bool, grad_out,
-                      gv_dtype: torch.dtype = torch.float32, force_atomic: bool = False):
+                      gv_dtype: torch.dtype = torch.float32, force_atomic: bool = False,
+                      samp_rs: int = 0, attn_rs: int = 0, grad_raw: Optional[torch.Tensor] = None):
     """Direct call of dfine_msda_bwd.  Returns (grad_memory [B,L,C] in `gv_dtype`, fp32
     grad_samp, fp32 grad_attn).  The library normally produces grad_memory with its
     atomic-free gather path directly in `gv_dtype`; shapes it cannot take (or
@@ -195,9 +197,17 @@ def msda_backward_raw(memory, spec: LevelSpec, H: int, samp, attn, ref, pts_scal
     Lq = samp.shape[1]
     sb, sl = _mem_strides(memory)
     dev = memory.device
-    g_samp = torch.empty(samp.shape, dtype=torch.float32, device=dev)
-    g_attn = torch.empty(attn.shape, dtype=torch.float32, device=dev)
     base_flags = MSDA_FUSED_INPUTS if fused else 0
+    if grad_raw is not None:
+        # both gradients go into one [B, Lq, 3HP] buffer (concatenated Linear), in its dtype
+        g_samp, g_attn = grad_raw, grad_raw.reshape(-1)[2 * H * spec.P:]
+        gs_rs = ga_rs = grad_raw.shape[-1]
+        if grad_raw.dtype == torch.bfloat16:
+            base_flags |= _lib.MSDA_GRAD_SAMP_BF16
+    else:
+        g_samp = torch.empty(samp.shape, dtype=torch.float32, device=dev)
+        g_attn = torch.empty(attn.shape, dtype=torch.float32, device=dev)
+        gs_rs = ga_rs = 0
     ws, ws_bytes = None, 0
     if not force_atomic:
         ws_bytes = _lib.lib().dfine_msda_bwd_workspace_bytes(B, Lq, H, spec.P)
@@ -210,7 +220,7 @@ def msda_backward_raw(memory, spec: LevelSpec, H: int, samp, attn, ref, pts_scal
                 samp.data_ptr(), attn.data_ptr(), _ptr(ref), _ptr(pts_scale), float(offset_scale),
                 grad_out.data_ptr(), buf.data_ptr(), g_samp.data_ptr(), g_attn.data_ptr(),
                 B, Lq, H, c, _dt(memory, "value"), _dt(samp, "samp"), _dt(grad_out, "grad_out"),
-                flags, _ptr(ws), ws_bytes, _stream(memory))
+                flags, samp_rs, attn_rs, gs_rs, ga_rs, _ptr(ws), ws_bytes, _stream(memory))
 
     if gv_dtype == torch.bfloat16 and not force_atomic:
         g_mem = torch.empty((B, spec.L, C), dtype=torch.bfloat16, device=dev)
@@ -259,6 +269,109 @@ class _MsdaFn(torch.autograd.Function):
             g_samp = g_samp.to(samp.dtype)
             g_attn = g_attn.to(attn.dtype)
         return g_mem, g_samp, g_attn, None, None, None, None, None, None, None
+
+
+class _MsdaPackedFn(torch.autograd.Function):
+    """Fused-input kernels fed by ONE concatenated Linear output raw [B, Lq, 3HP]
+    ([..., :2HP] sampling offsets, [..., 2HP:] attention logits): no slicing copies, one
+    gradient tensor in raw's dtype written directly by the backward kernel."""
+
+    @staticmethod
+    def forward(ctx, memory, raw, ref, pts_scale, spec, H, offset_scale, out_dtype):
+        rs = raw.shape[-1]
+        attn_view = raw.reshape(-1)[2 * H * spec.P:]
+        out = msda_forward_raw(memory, spec, H, raw, attn_view, ref, pts_scale, offset_scale, True,
+                               out_dtype, samp_rs=rs, attn_rs=rs)
+        ctx.save_for_backward(memory, raw, ref, pts_scale)
+        ctx.spec, ctx.H, ctx.offset_scale = spec, H, offset_scale
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        memory, raw, ref, pts_scale = ctx.saved_tensors
+        if grad_out.dtype not in _DT:
+            grad_out = grad_out.float()
+        rs = raw.shape[-1]
+        g_raw = torch.empty_like(raw)
+        attn_view = raw.reshape(-1)[2 * ctx.H * ctx.spec.P:]
+        g_mem, _, _ = msda_backward_raw(memory, ctx.spec, ctx.H, raw, attn_view, ref, pts_scale,
+                                        ctx.offset_scale, True, grad_out.contiguous(),
+                                        gv_dtype=memory.dtype, samp_rs=rs, attn_rs=rs, grad_raw=g_raw)
+        return g_mem, g_raw, None, None, None, None, None, None
+
+
+_ONES = {}
+
+
+def _ones_row(n: int, dtype, device):
+    key = (n, dtype, device)
+    t = _ONES.get(key)
+    if t is None:
+        t = _ONES[key] = torch.ones(1, n, dtype=dtype, device=device)
+    return t
+
+
+class _LinearFn(torch.autograd.Function):
+    """y = x W^T + b as library GEMMs only (cuBLAS): under autocast the operands are cast to
+    the autocast dtype like F.linear would; the backward computes grad_bias as a
+    ones-row GEMV instead of a column reduction kernel."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        cdt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x.dtype
+        x2 = x.reshape(-1, x.shape[-1]).to(cdt)
+        w = weight.to(cdt)
+        y = torch.nn.functional.linear(x2, w, bias.to(cdt))
+        ctx.save_for_backward(x2, w)
+        ctx.x_shape, ctx.x_dtype, ctx.w_dtype, ctx.b_dtype = x.shape, x.dtype, weight.dtype, bias.dtype
+        return y.reshape(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        x2, w = ctx.saved_tensors
+        g2 = g.reshape(-1, g.shape[-1])
+        if g2.dtype != w.dtype:
+            g2 = g2.to(w.dtype)
+        gx = _mm(g2, w, ctx.x_dtype).reshape(ctx.x_shape)
+        gw = _mm(g2.t(), x2, ctx.w_dtype)
+        gb = _mm(_ones_row(g2.shape[0], g2.dtype, g2.device), g2, ctx.b_dtype).reshape(-1)
+        return gx, gw, gb
+
+
+def _mm(a, b, out_dtype):
+    """cuBLAS GEMM with the result written directly in out_dtype (no cast kernel)."""
+    if out_dtype == a.dtype:
+        return torch.mm(a, b)
+    try:
+        return torch.mm(a, b, out_dtype=out_dtype)
+    except (RuntimeError, TypeError, NotImplementedError):
+        return torch.mm(a, b).to(out_dtype)
+
+
+def fused_linear(x, weight, bias):
+    return _LinearFn.apply(x, weight, bias)
+
+
+def msda_fused_packed(value, value_spatial_shapes, raw, ref_boxes, pts_scale, num_points_list,
+                      offset_scale: float = 0.5) -> torch.Tensor:
+    """Like msda_fused, but both raw Linear outputs live in one tensor raw [B, Lq, 3HP]
+    (offsets first, then logits): the output of a single concatenated Linear."""
+    spec = level_spec(value_spatial_shapes, num_points_list)
+    memory, H, c, _ = memory_from_value(value, spec)
+    _require_cuda(memory, raw, ref_boxes, pts_scale)
+    B, Lq = raw.shape[:2]
+    if raw.shape[-1] != 3 * H * spec.P:
+        raise ValueError(f"raw last dim {raw.shape[-1]} != 3*H*P = {3 * H * spec.P}")
+    if raw.dtype not in _DT:
+        raw = raw.float()
+    ref = ref_boxes.reshape(B, Lq, 4).float().contiguous()
+    out_dtype = torch.promote_types(memory.dtype, raw.dtype)
+    if torch.is_autocast_enabled():
+        out_dtype = torch.float32
+    return _MsdaPackedFn.apply(memory, raw.contiguous(), ref, pts_scale.float().contiguous(), spec, H,
+                               float(offset_scale), out_dtype)
 
 
 def msda_core(value, value_spatial_shapes, sampling_locations, attention_weights,

@@ -52,6 +52,7 @@ extern "C" {
 #define DFINE_MSDA_FUSED_INPUTS 1    /* sampling inputs are raw Linear outputs + ref boxes */
 #define DFINE_MSDA_GRAD_VALUE_BF16 2 /* bwd: grad_value is a bf16 buffer (AMP) */
 #define DFINE_MSDA_FORCE_ATOMIC 4    /* bwd: force the fp32 vector-reduction fallback */
+#define DFINE_MSDA_GRAD_SAMP_BF16 8  /* bwd: grad_samp / grad_attn are bf16 buffers */
 
 DFINE_API int dfine_version(void);
 DFINE_API const char* dfine_last_error(void);
@@ -82,6 +83,10 @@ DFINE_API const char* dfine_last_error(void);
  *   ref_boxes float32 [B, Lq, 4]  (cx, cy, w, h)
  *   pts_scale float32 [P]         buffer num_points_scale (dfine_decoder.py:74-77)
  *   offset_scale                  MSDeformableAttention.offset_scale (0.5)
+ * samp_row_stride, attn_row_stride
+ *            elements between consecutive (b, q) rows of samp / attn; 0 = contiguous (2HP / HP).
+ *            Lets both tensors alias one concatenated Linear output [B, Lq, 3HP]
+ *            (samp = raw, attn = raw + 2HP, both strides 3HP).
  * out        out_dtype [B, Lq, H*c]   contiguous
  * idx_debug  optional int32 [B, Lq, H, P, 4]: flattened pixel index (lvl_start +
  *            y*w + x) of the nw, ne, sw, se corners, -1 where the corner is out of
@@ -92,7 +97,7 @@ DFINE_API int dfine_msda_fwd(const void* value, int64_t v_stride_b, int64_t v_st
                    int n_lvl, const void* samp, const void* attn, const float* ref_boxes,
                    const float* pts_scale, float offset_scale, void* out, int32_t* idx_debug,
                    int B, int Lq, int H, int c, int value_dtype, int samp_dtype, int out_dtype,
-                   int flags, void* stream);
+                   int flags, int64_t samp_row_stride, int64_t attn_row_stride, void* stream);
 
 /* --------------------------------------------------------------------------
  * K2  multi-scale deformable attention, backward.
@@ -109,10 +114,11 @@ DFINE_API int dfine_msda_fwd(const void* value, int64_t v_stride_b, int64_t v_st
  *             whose CSR does not fit shared memory, it falls back to fp32 vector reductions
  *             (float32 buffer only; a bf16 request then returns DFINE_E_UNSUPPORTED).
  * workspace   caller-owned device scratch of dfine_msda_bwd_workspace_bytes() bytes, or NULL
- * grad_samp   float32  [B, Lq, H, P, 2]  d/d sampling_locations (plain) or
- *             d/d raw offsets (fused)
- * grad_attn   float32  [B, Lq, H, P]     d/d attention weights (plain) or
- *             d/d raw logits (fused)
+ * grad_samp   float32 (bf16 with DFINE_MSDA_GRAD_SAMP_BF16) [B, Lq, H, P, 2]  d/d
+ *             sampling_locations (plain) or d/d raw offsets (fused)
+ * grad_attn   same dtype [B, Lq, H, P]   d/d attention weights (plain) or d/d raw logits (fused)
+ * gsamp_row_stride, gattn_row_stride: row strides of the two gradient buffers (0 = contiguous),
+ *             so that both can be written into one [B, Lq, 3HP] gradient of a concatenated Linear
  * No gradient is produced for ref_boxes: the reference detaches them
  * (dfine_decoder.py:465, :514).
  * -------------------------------------------------------------------------- */
@@ -120,9 +126,11 @@ DFINE_API int dfine_msda_bwd(const void* value, int64_t v_stride_b, int64_t v_st
                    const int32_t* lvl_hw, const int32_t* lvl_start, const int32_t* lvl_npts,
                    int n_lvl, const void* samp, const void* attn, const float* ref_boxes,
                    const float* pts_scale, float offset_scale, const void* grad_out,
-                   void* grad_value, float* grad_samp, float* grad_attn, int B, int Lq, int H,
+                   void* grad_value, void* grad_samp, void* grad_attn, int B, int Lq, int H,
                    int c, int value_dtype, int samp_dtype, int go_dtype, int flags,
-                   void* workspace, int64_t workspace_bytes, void* stream);
+                   int64_t samp_row_stride, int64_t attn_row_stride, int64_t gsamp_row_stride,
+                   int64_t gattn_row_stride, void* workspace, int64_t workspace_bytes,
+                   void* stream);
 
 /* Device scratch (bytes) the atomic-free grad_value path of dfine_msda_bwd needs: one
  * 16-byte record per sampling point.  Passing workspace == NULL (or too small) selects the

@@ -363,3 +363,50 @@ def test_error_behaviour(dev):
         dfine_b200.msda_core(torch.zeros(1, 16, 2, 16, device=dev), [[4, 4]],
                              torch.zeros(1, 1, 2, 2, 2, device=dev), torch.zeros(1, 1, 2, 2, device=dev),
                              [2], method="discrete")
+
+
+def test_packed_raw_and_fused_linear(dev):
+    """One concatenated Linear output [B, Lq, 3HP] through row strides, bf16 gradients written
+    by the kernel, cuBLAS-only Linear backward: against the separate-tensor path."""
+    import dfine_b200.ops as ops
+    g = golden("module_m_small")
+    H = int(g["H"])
+    shapes, npts = g["shapes"].tolist(), g["npts"].tolist()
+    spec = ops.level_spec(shapes, npts)
+    mem32 = bf16_bits_to_f32(g["memory_bf16"])
+    B, L, C = mem32.shape
+    Lq = g["raw_off"].shape[1]
+    go = _t(bf16_bits_to_f32(g["grad_out_bf16"]), dev)
+    ref = _t(g["ref_points"].reshape(B, -1, 4), dev)
+    nps = _t(g["num_points_scale"], dev)
+    for dt, tol in ((torch.float32, FP32_RTOL), (torch.bfloat16, BF16_RTOL)):
+        raw = torch.cat([_t(g["raw_off"], dev).reshape(B, Lq, -1), _t(g["raw_logit"], dev).reshape(B, Lq, -1)], -1)
+        raw = raw.to(dt).requires_grad_(True)
+        mem = _t(mem32, dev, dt).requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=dt == torch.bfloat16):
+            out = ops.msda_fused_packed(mem.reshape(B, L, H, C // H), shapes, raw, ref, nps, npts)
+        out.backward(go)
+        # reference: the two-tensor path on the same (rounded) inputs
+        off = raw.detach()[..., :2 * H * spec.P].reshape(B, Lq, H, spec.P, 2).contiguous()
+        logit = raw.detach()[..., 2 * H * spec.P:].reshape(B, Lq, H, spec.P).contiguous()
+        want = ops.msda_forward_raw(mem.detach(), spec, H, off, logit, ref, nps, 0.5, True, torch.float32)
+        gm, gs, ga = ops.msda_backward_raw(mem.detach(), spec, H, off, logit, ref, nps, 0.5, True, go)
+        assert torch.equal(out.detach(), want)
+        assert_close(mem.grad.float().cpu().numpy(), gm.cpu().numpy(), tol, "packed grad_memory")
+        assert_close(raw.grad[..., :2 * H * spec.P].float().cpu().numpy(),
+                     gs.reshape(B, Lq, -1).cpu().numpy(), tol, "packed grad offsets")
+        assert_close(raw.grad[..., 2 * H * spec.P:].float().cpu().numpy(),
+                     ga.reshape(B, Lq, -1).cpu().numpy(), tol, "packed grad logits")
+    # fused Linear (cuBLAS) against F.linear autograd
+    torch.manual_seed(0)
+    x = torch.randn(3, 50, 64, device=dev, requires_grad=True)
+    w = torch.randn(36, 64, device=dev, requires_grad=True)
+    b = torch.randn(36, device=dev, requires_grad=True)
+    gy = torch.randn(3, 50, 36, device=dev)
+    ops.fused_linear(x, w, b).backward(gy)
+    got = [t.grad.clone() for t in (x, w, b)]
+    for t in (x, w, b):
+        t.grad = None
+    torch.nn.functional.linear(x, w, b).backward(gy)
+    for a_, b_ in zip(got, (x.grad, w.grad, b.grad)):
+        assert rel_err(a_.cpu().numpy(), b_.cpu().numpy()) <= 5e-5
