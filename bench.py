@@ -353,6 +353,11 @@ def time_steps(fn, steps: int, warmup: int, device, dist_on: bool):
 # ------------------------------------------------------------------------------------------
 def cpu_reference_run(wl: dict, sample_b: int, steps: int, warmup: int, seed: int = 42):
     from oracle import torch_port as TP  # the only use of oracle/ in this file
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1)
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except (AttributeError, OSError):
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
     inp = make_inputs(wl, sample_b, seed, "cpu")
     H, P = wl["H"], sum(wl["npts"])
     nps = torch.tensor([1.0 / n for n in wl["npts"] for _ in range(n)])
@@ -386,9 +391,9 @@ def run_reference_arm(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = torch.get_num_threads()
     sample_b = args.cpu_sample
     v, ms = cpu_reference_run(wl, sample_b, args.steps, args.warmup)
+    cores = torch.get_num_threads()
     sample = (f"{sample_b} of {wl['B']} images per step, {args.steps} steps, fp32, torch "
               f"{torch.__version__} CPU, reference call sequence restated in oracle/torch_port.py")
     print(json.dumps({
@@ -524,8 +529,8 @@ def main():
         except Exception as exc:  # noqa: BLE001
             out["gpu_eager_reference"] = {"error": str(exc)[:200]}
     if world == 1 and not args.no_cpu_baseline:
-        cores = torch.get_num_threads()
         v, cms = cpu_reference_run(wl, args.cpu_sample, 2, 1)
+        cores = torch.get_num_threads()
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                "ms_per_step": cms,
                                "sample": f"{args.cpu_sample} of {wl['B']} images per step, 2 timed steps "

@@ -192,7 +192,8 @@ int dfine_msda_fwd(const void* value, int64_t v_stride_b, int64_t v_stride_l,
                    int n_lvl, const void* samp, const void* attn, const float* ref_boxes,
                    const float* pts_scale, float offset_scale, void* out, int32_t* idx_debug,
                    int B, int Lq, int H, int c, int value_dtype, int samp_dtype, int out_dtype,
-                   int flags, int64_t samp_row_stride, int64_t attn_row_stride, void* stream) {
+                   int flags, int64_t samp_row_stride, int64_t attn_row_stride, void* records,
+                   void* stream) {
   MsdaParams p;
   int rc = fill_msda(p, "dfine_msda_fwd", value, v_stride_b, v_stride_l, lvl_hw, lvl_start,
                      lvl_npts, n_lvl, samp, attn, ref_boxes, pts_scale, offset_scale, B, Lq, H, c,
@@ -210,6 +211,14 @@ int dfine_msda_fwd(const void* value, int64_t v_stride_b, int64_t v_stride_l,
   p.out = out;
   p.out_bf16 = out_dtype == DFINE_BF16;
   p.idx_debug = idx_debug;
+  if (records) {
+    if ((rc = require_device(records, "records", "dfine_msda_fwd"))) return rc;
+    if (!aligned16(records)) {
+      set_error("dfine_msda_fwd: records must be 16-byte aligned");
+      return DFINE_E_ALIGN;
+    }
+    p.rec = reinterpret_cast<uint4*>(records);
+  }
   return cuda_rc(launch_msda_fwd(p, value_dtype, (cudaStream_t)stream), "dfine_msda_fwd");
 }
 
@@ -270,6 +279,7 @@ int dfine_msda_bwd(const void* value, int64_t v_stride_b, int64_t v_stride_l,
       return DFINE_E_ALIGN;
     }
     p.rec = reinterpret_cast<uint4*>(workspace);
+    p.rec_valid = (flags & DFINE_MSDA_RECORDS_VALID) ? 1 : 0;
     // shape check first: nothing is launched if the gather path cannot take this shape
     rc = launch_msda_bwd_value(p, nullptr, gv_bf16, s);
     if (rc == 0) {
@@ -279,6 +289,7 @@ int dfine_msda_bwd(const void* value, int64_t v_stride_b, int64_t v_stride_l,
     }
     if (rc != DFINE_E_UNSUPPORTED) return cuda_rc(rc, "dfine_msda_bwd(value)");
     p.rec = nullptr;
+    p.rec_valid = 0;
   }
   if (gv_bf16) {
     set_error("dfine_msda_bwd: a bf16 grad_value needs the gather path (workspace of "

@@ -27,7 +27,8 @@ struct MsdaParams {
   float* grad_value;     // bwd: [B,L,H,c] fp32 contiguous
   float* grad_samp;      // bwd: [B,Lq,H,P,2]
   float* grad_attn;      // bwd: [B,Lq,H,P]
-  uint4* rec;            // bwd: optional [B,H,P,Lq] sample records for the gather path
+  uint4* rec;            // [B,H,P,Lq] sample records: fwd writes them (optional), bwd uses them
+  int rec_valid;         // bwd: the records were already written by the forward
   int B, Lq, H, c, n_lvl, P, L;
   int lvl_h[kMaxLevels], lvl_w[kMaxLevels], lvl_start[kMaxLevels], lvl_pend[kMaxLevels];
   int samp_bf16, out_bf16, go_bf16, fused;

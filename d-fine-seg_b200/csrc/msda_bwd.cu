@@ -49,7 +49,7 @@ __device__ __forceinline__ void load_go(const void* go, size_t i, int is_bf16, f
   }
 }
 
-template <typename VT, int LPC, bool kScatter, int kP>
+template <typename VT, int LPC, bool kScatter, int kP, bool kFromRec>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 3)
 msda_bwd_kernel(const MsdaParams p) {
   constexpr int VPL = Vec16<VT>::kElems;
@@ -76,7 +76,9 @@ msda_bwd_kernel(const MsdaParams p) {
 
   // ---- phase 1 ------------------------------------------------------------------------------
   const int slot_i = lane / LPI, pl = lane % LPI;
-  const PointCtx c = point_phase<LPI>(p, P, b, item0 + slot_i, pl, item0 + slot_i < n_items);
+  const PointCtx c = kFromRec
+                         ? point_from_record<LPI>(p, P, b, item0 + slot_i, pl, item0 + slot_i < n_items)
+                         : point_phase<LPI>(p, P, b, item0 + slot_i, pl, item0 + slot_i < n_items);
   if (c.active) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -86,13 +88,7 @@ msda_bwd_kernel(const MsdaParams p) {
       if (kScatter) s_pix[warp][slot_i][4 * pl + j] = pix >= 0 ? pix + c.lstart : -1;
     }
     s_pt[warp][slot_i][pl] = make_float4(c.g.fw, c.g.fn, c.a, 0.f);
-    if (p.rec) {
-      // compact record for msda_bwd_value.cu: {x0 | y0 << 16, fw, fn, attn}, laid out
-      // [b][h][point][query] so that one (b, h, level) is a contiguous run
-      const uint32_t xy = ((uint32_t)c.g.x0 & 0xffffu) | ((uint32_t)c.g.y0 << 16);
-      p.rec[(((size_t)b * p.H + c.h) * P + pl) * p.Lq + c.q] =
-          make_uint4(xy, __float_as_uint(c.g.fw), __float_as_uint(c.g.fn), __float_as_uint(c.a));
-    }
+    if (!kFromRec && p.rec) store_record(p, p.rec, P, b, pl, c);
   }
   __syncwarp();
 
@@ -246,11 +242,14 @@ static int launch_bwd_t(const MsdaParams& p, bool scatter, cudaStream_t s) {
   const dim3 grid((unsigned)ctas, (unsigned)p.B);
   constexpr int T = kWarpsPerCta * 32;
   if (scatter) {
-    msda_bwd_kernel<VT, LPC, true, 0><<<grid, T, 0, s>>>(p);
+    msda_bwd_kernel<VT, LPC, true, 0, false><<<grid, T, 0, s>>>(p);
+  } else if (p.rec_valid) {
+    if (p.P == 12) msda_bwd_kernel<VT, LPC, false, 12, true><<<grid, T, 0, s>>>(p);
+    else msda_bwd_kernel<VT, LPC, false, 0, true><<<grid, T, 0, s>>>(p);
   } else if (p.P == 12) {
-    msda_bwd_kernel<VT, LPC, false, 12><<<grid, T, 0, s>>>(p);
+    msda_bwd_kernel<VT, LPC, false, 12, false><<<grid, T, 0, s>>>(p);
   } else {
-    msda_bwd_kernel<VT, LPC, false, 0><<<grid, T, 0, s>>>(p);
+    msda_bwd_kernel<VT, LPC, false, 0, false><<<grid, T, 0, s>>>(p);
   }
   return (int)cudaGetLastError();
 }

@@ -25,6 +25,7 @@ namespace dfine {
 constexpr int kBvThreads = 1024;
 constexpr int kBvMaxChunks = 32;
 constexpr int kBvMaxChunkPx = 4096;  // chunk-local pixel ids use 13 bits
+constexpr int kBvWorkerSlots = 257;  // >= workers per CTA + 1 (c = 16: 32 warps x 8), odd
 
 struct BvChunks {
   int n;
@@ -137,7 +138,9 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
   int* s_off = reinterpret_cast<int*>(smem_raw);   // [max_px + 1]
   int* s_cur = s_off + (max_px + 1);               // [max_px]
   int* s_warp = s_cur + max_px;                    // [32]
-  BvEntry* s_ent = reinterpret_cast<BvEntry*>(s_warp + 32 + 1);  // (2*max_px + 34) ints: 8B aligned
+  int* s_wb = s_warp + 32;                         // [kBvWorkerSlots] worker pixel boundaries
+  // (2*max_px + 1 + 32 + kBvWorkerSlots) ints so far; kBvWorkerSlots is odd -> 8-byte aligned
+  BvEntry* s_ent = reinterpret_cast<BvEntry*>(s_wb + kBvWorkerSlots);
   // staged grad_out rows follow the entries, 16-byte aligned
   unsigned char* s_go = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(s_ent + cap) + 15) & ~static_cast<uintptr_t>(15));
@@ -196,8 +199,14 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
     }
     return lo;
   };
+  // worker w starts at the first pixel whose CSR offset reaches w/NWORK of the entries and
+  // ends where worker w+1 starts (one search per worker, the end comes through smem)
+  static_assert(NWORK + 1 <= kBvWorkerSlots, "worker boundary table too small");
   const int pa = worker == 0 ? 0 : first_px_at((int)((long long)total * worker / NWORK));
-  const int pb = worker == NWORK - 1 ? npx : first_px_at((int)((long long)total * (worker + 1) / NWORK));
+  if (sub == 0) s_wb[worker] = pa;
+  if (tid == 0) s_wb[NWORK] = npx;
+  __syncthreads();
+  const int pb = s_wb[worker + 1];
   // byte strides of one query row of grad_out / one pixel row of grad_value
   const uint32_t go_row = kStage ? (uint32_t)kRowBytes : (uint32_t)(p.H * kC) * (uint32_t)sizeof(GT);
   const uint32_t gv_row = (uint32_t)(p.H * kC) * (gv_bf16 ? 2u : 4u);
@@ -292,7 +301,8 @@ int launch_msda_bwd_value(const MsdaParams& p, void* grad_value, int gv_bf16, cu
     const long long c = 4LL * np * p.Lq;
     if (c > cap) cap = (int)(c > 0x3fffffff ? 0x3fffffff : c);
   }
-  const size_t base_smem = (size_t)(2 * max_px + 34) * sizeof(int) + (size_t)cap * sizeof(BvEntry) + 32;
+  const size_t base_smem = (size_t)(2 * max_px + 1 + 32 + kBvWorkerSlots) * sizeof(int) +
+                           (size_t)cap * sizeof(BvEntry) + 32;
   const size_t go_smem = (size_t)p.Lq * p.c * (p.go_bf16 ? 2 : 4);
   constexpr size_t kSmemLimit = 227 * 1024;
   if (base_smem > kSmemLimit) return DFINE_E_UNSUPPORTED;

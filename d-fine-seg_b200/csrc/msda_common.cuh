@@ -105,6 +105,57 @@ __device__ __forceinline__ PointCtx point_phase(const MsdaParams& p, int P, int 
   return c;
 }
 
+// Phase 1 of the backward when the forward left its sample records in the workspace: no
+// softmax, no location arithmetic, no floor -- the geometry is read back bit for bit.
+template <int LPI>
+__device__ __forceinline__ PointCtx point_from_record(const MsdaParams& p, int P, int b, int item,
+                                                      int pl, bool item_valid) {
+  PointCtx c;
+  c.active = item_valid && pl < P;
+  const int lvl = (pl >= p.lvl_pend[0]) + (pl >= p.lvl_pend[1]) + (pl >= p.lvl_pend[2]);
+  c.lw = sel3(lvl, p.lvl_w[0], p.lvl_w[1], p.lvl_w[2], p.lvl_w[3]);
+  c.lh = sel3(lvl, p.lvl_h[0], p.lvl_h[1], p.lvl_h[2], p.lvl_h[3]);
+  c.lstart = sel3(lvl, p.lvl_start[0], p.lvl_start[1], p.lvl_start[2], p.lvl_start[3]);
+  if (p.h_shift >= 0) {
+    c.q = item >> p.h_shift;
+    c.h = item & (p.H - 1);
+  } else {
+    c.q = item / p.H;
+    c.h = item - c.q * p.H;
+  }
+  c.a = 0.f;
+  c.ps = 0.f;
+  c.ref = make_float4(0.f, 0.f, 0.f, 0.f);
+  c.g.x0 = c.g.y0 = -4;
+  c.g.fw = c.g.fe = c.g.fn = c.g.fs = 0.f;
+  c.g.inrange = false;
+  if (c.active) {
+    const uint4 r = __ldg(p.rec + (((size_t)b * p.H + c.h) * P + pl) * p.Lq + c.q);
+    c.g.x0 = (int)(short)(r.x & 0xffffu);
+    c.g.y0 = (int)(short)(r.x >> 16);
+    c.g.inrange = c.g.x0 >= -2;
+    c.g.fw = __uint_as_float(r.y);
+    c.g.fn = __uint_as_float(r.z);
+    c.g.fe = __fsub_rn(1.0f, c.g.fw);
+    c.g.fs = __fsub_rn(1.0f, c.g.fn);
+    c.a = __uint_as_float(r.w);
+    if (p.fused) {
+      c.ref = __ldg(reinterpret_cast<const float4*>(p.ref) + b * p.Lq + c.q);
+      c.ps = __ldg(p.pts_scale + pl);
+    }
+  }
+  return c;
+}
+
+// writes the lane's sample record (see msda_bwd_value.cu): {x0 | y0 << 16, fw, fn, attn},
+// laid out [b][h][point][query] so that one (b, h, level) is a contiguous run
+__device__ __forceinline__ void store_record(const MsdaParams& p, uint4* rec, int P, int b, int pl,
+                                             const PointCtx& c) {
+  const uint32_t xy = ((uint32_t)c.g.x0 & 0xffffu) | ((uint32_t)c.g.y0 << 16);
+  rec[(((size_t)b * p.H + c.h) * P + pl) * p.Lq + c.q] =
+      make_uint4(xy, __float_as_uint(c.g.fw), __float_as_uint(c.g.fn), __float_as_uint(c.a));
+}
+
 // level-local pixel index y*w+x of corner j (0 nw, 1 ne, 2 sw, 3 se), -1 when out of bounds
 __device__ __forceinline__ int corner_pixel_local(const PointCtx& c, int j) {
   const int x = c.g.x0 + (j & 1), y = c.g.y0 + (j >> 1);

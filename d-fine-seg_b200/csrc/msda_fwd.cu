@@ -97,6 +97,7 @@ msda_fwd_kernel(const MsdaParams p) {
         const uint64_t a = corner_address<VT>(p, img, c.h, pix[j], c.lstart);
         dst[j] = make_uint4((uint32_t)a, (uint32_t)(a >> 32), __float_as_uint(wt[j] * c.a), 0u);
       }
+      if (p.rec) store_record(p, p.rec, P, b, pl, c);  // training: saves the backward its phase 1
       if (p.idx_debug) {
         const size_t s = ((size_t)b * n_items + item) * P + pl;
 #pragma unroll

@@ -17,6 +17,7 @@ MSDA_FUSED_INPUTS = 1
 MSDA_GRAD_VALUE_BF16 = 2
 MSDA_FORCE_ATOMIC = 4
 MSDA_GRAD_SAMP_BF16 = 8
+MSDA_RECORDS_VALID = 16
 E_NULL, E_SHAPE, E_UNSUPPORTED, E_ALIGN = -1, -2, -3, -4
 
 _I32P = ctypes.POINTER(c_int32)
@@ -28,7 +29,7 @@ _SIGNATURES = {
     "dfine_msda_fwd": (c_int, [c_void_p, c_int64, c_int64, _I32P, _I32P, _I32P, c_int, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
                                c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int64,
-                               c_int64, c_void_p]),
+                               c_int64, c_void_p, c_void_p]),
     "dfine_msda_bwd": (c_int, [c_void_p, c_int64, c_int64, _I32P, _I32P, _I32P, c_int, c_void_p,
                                c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
                                c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,

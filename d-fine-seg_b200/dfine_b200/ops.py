@@ -162,7 +162,8 @@ def _mem_strides(memory: torch.Tensor) -> Tuple[int, int]:
 
 def msda_forward_raw(memory, spec: LevelSpec, H: int, samp, attn, ref, pts_scale,
                      offset_scale: float, fused: bool, out_dtype: torch.dtype,
-                     want_idx: bool = False, samp_rs: int = 0, attn_rs: int = 0):
+                     want_idx: bool = False, samp_rs: int = 0, attn_rs: int = 0,
+                     records: Optional[torch.Tensor] = None):
     """Direct call of dfine_msda_fwd (no autograd).  Returns out [B, Lq, C] (, idx).
     samp_rs / attn_rs: row strides (elements) when samp / attn alias a wider tensor."""
     _require_cuda(memory, samp, attn, ref, pts_scale)
@@ -178,7 +179,8 @@ def msda_forward_raw(memory, spec: LevelSpec, H: int, samp, attn, ref, pts_scale
             memory.data_ptr(), sb, sl, spec.hw_c, spec.start_c, spec.npts_c, spec.n_lvl,
             samp.data_ptr(), attn.data_ptr(), _ptr(ref), _ptr(pts_scale), float(offset_scale),
             out.data_ptr(), _ptr(idx), B, Lq, H, c, _dt(memory, "value"), _dt(samp, "samp"),
-            _dt(out, "out"), MSDA_FUSED_INPUTS if fused else 0, samp_rs, attn_rs, _stream(memory))
+            _dt(out, "out"), MSDA_FUSED_INPUTS if fused else 0, samp_rs, attn_rs, _ptr(records),
+            _stream(memory))
     check(rc, "dfine_msda_fwd")
     return (out, idx) if want_idx else out
 
@@ -186,7 +188,8 @@ def msda_forward_raw(memory, spec: LevelSpec, H: int, samp, attn, ref, pts_scale
 def msda_backward_raw(memory, spec: LevelSpec, H: int, samp, attn, ref, pts_scale,
                       offset_scale: float, fused: bool, grad_out,
                       gv_dtype: torch.dtype = torch.float32, force_atomic: bool = False,
-                      samp_rs: int = 0, attn_rs: int = 0, grad_raw: Optional[torch.Tensor] = None):
+                      samp_rs: int = 0, attn_rs: int = 0, grad_raw: Optional[torch.Tensor] = None,
+                      records: Optional[torch.Tensor] = None):
     """Direct call of dfine_msda_bwd.  Returns (grad_memory [B,L,C] in `gv_dtype`, fp32
     grad_samp, fp32 grad_attn).  The library normally produces grad_memory with its
     atomic-free gather path directly in `gv_dtype`; shapes it cannot take (or
@@ -210,8 +213,12 @@ def msda_backward_raw(memory, spec: LevelSpec, H: int, samp, attn, ref, pts_scal
         gs_rs = ga_rs = 0
     ws, ws_bytes = None, 0
     if not force_atomic:
-        ws_bytes = _lib.lib().dfine_msda_bwd_workspace_bytes(B, Lq, H, spec.P)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        if records is not None:   # written by the forward: the backward skips its phase 1
+            ws, ws_bytes = records, records.numel()
+            base_flags |= _lib.MSDA_RECORDS_VALID
+        else:
+            ws_bytes = _lib.lib().dfine_msda_bwd_workspace_bytes(B, Lq, H, spec.P)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
 
     def call(buf, flags):
         with torch.cuda.device_of(memory), _timed("msda_bwd", memory, 2):
@@ -236,6 +243,12 @@ def msda_backward_raw(memory, spec: LevelSpec, H: int, samp, attn, ref, pts_scal
     return g_mem, g_samp, g_attn
 
 
+def new_records(memory: torch.Tensor, spec: LevelSpec, H: int, Lq: int) -> torch.Tensor:
+    """Workspace for the per-sample geometry records (16 bytes per sampling point)."""
+    n = _lib.lib().dfine_msda_bwd_workspace_bytes(memory.shape[0], Lq, H, spec.P)
+    return torch.empty(n, dtype=torch.uint8, device=memory.device)
+
+
 def cast_f32_to_bf16(src: torch.Tensor) -> torch.Tensor:
     dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
     with torch.cuda.device_of(src), _timed("cast_bf16", src):
@@ -250,8 +263,10 @@ class _MsdaFn(torch.autograd.Function):
     def forward(ctx, memory, samp, attn, ref, pts_scale, spec, H, offset_scale, fused, out_dtype):
         samp = samp.contiguous()
         attn = attn.contiguous()
+        rec = new_records(memory, spec, H, samp.shape[1]) if any(ctx.needs_input_grad[:3]) else None
         out = msda_forward_raw(memory, spec, H, samp, attn, ref, pts_scale, offset_scale, fused,
-                               out_dtype)
+                               out_dtype, records=rec)
+        ctx.rec = rec
         ctx.save_for_backward(memory, samp, attn, ref, pts_scale)
         ctx.spec, ctx.H, ctx.offset_scale, ctx.fused = spec, H, offset_scale, fused
         return out
@@ -264,7 +279,8 @@ class _MsdaFn(torch.autograd.Function):
             grad_out = grad_out.float()
         g_mem, g_samp, g_attn = msda_backward_raw(memory, ctx.spec, ctx.H, samp, attn, ref,
                                                   pts_scale, ctx.offset_scale, ctx.fused,
-                                                  grad_out.contiguous(), gv_dtype=memory.dtype)
+                                                  grad_out.contiguous(), gv_dtype=memory.dtype,
+                                                  records=ctx.rec)
         if g_samp.dtype != samp.dtype:
             g_samp = g_samp.to(samp.dtype)
             g_attn = g_attn.to(attn.dtype)
@@ -280,8 +296,10 @@ class _MsdaPackedFn(torch.autograd.Function):
     def forward(ctx, memory, raw, ref, pts_scale, spec, H, offset_scale, out_dtype):
         rs = raw.shape[-1]
         attn_view = raw.reshape(-1)[2 * H * spec.P:]
+        rec = new_records(memory, spec, H, raw.shape[1]) if any(ctx.needs_input_grad[:2]) else None
         out = msda_forward_raw(memory, spec, H, raw, attn_view, ref, pts_scale, offset_scale, True,
-                               out_dtype, samp_rs=rs, attn_rs=rs)
+                               out_dtype, samp_rs=rs, attn_rs=rs, records=rec)
+        ctx.rec = rec
         ctx.save_for_backward(memory, raw, ref, pts_scale)
         ctx.spec, ctx.H, ctx.offset_scale = spec, H, offset_scale
         return out
@@ -297,7 +315,8 @@ class _MsdaPackedFn(torch.autograd.Function):
         attn_view = raw.reshape(-1)[2 * ctx.H * ctx.spec.P:]
         g_mem, _, _ = msda_backward_raw(memory, ctx.spec, ctx.H, raw, attn_view, ref, pts_scale,
                                         ctx.offset_scale, True, grad_out.contiguous(),
-                                        gv_dtype=memory.dtype, samp_rs=rs, attn_rs=rs, grad_raw=g_raw)
+                                        gv_dtype=memory.dtype, samp_rs=rs, attn_rs=rs, grad_raw=g_raw,
+                                        records=ctx.rec)
         return g_mem, g_raw, None, None, None, None, None, None
 
 

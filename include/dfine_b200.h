@@ -53,6 +53,7 @@ extern "C" {
 #define DFINE_MSDA_GRAD_VALUE_BF16 2 /* bwd: grad_value is a bf16 buffer (AMP) */
 #define DFINE_MSDA_FORCE_ATOMIC 4    /* bwd: force the fp32 vector-reduction fallback */
 #define DFINE_MSDA_GRAD_SAMP_BF16 8  /* bwd: grad_samp / grad_attn are bf16 buffers */
+#define DFINE_MSDA_RECORDS_VALID 16  /* bwd: workspace holds the records dfine_msda_fwd wrote */
 
 DFINE_API int dfine_version(void);
 DFINE_API const char* dfine_last_error(void);
@@ -88,6 +89,10 @@ DFINE_API const char* dfine_last_error(void);
  *            Lets both tensors alias one concatenated Linear output [B, Lq, 3HP]
  *            (samp = raw, attn = raw + 2HP, both strides 3HP).
  * out        out_dtype [B, Lq, H*c]   contiguous
+ * records    optional device buffer of dfine_msda_bwd_workspace_bytes() bytes: the forward
+ *            leaves one 16-byte geometry record per sampling point there; passing the same
+ *            buffer as `workspace` of dfine_msda_bwd with DFINE_MSDA_RECORDS_VALID lets the
+ *            backward skip the softmax / location / floor arithmetic.  NULL for inference.
  * idx_debug  optional int32 [B, Lq, H, P, 4]: flattened pixel index (lvl_start +
  *            y*w + x) of the nw, ne, sw, se corners, -1 where the corner is out of
  *            bounds (zero padding).  NULL to skip.
@@ -97,7 +102,8 @@ DFINE_API int dfine_msda_fwd(const void* value, int64_t v_stride_b, int64_t v_st
                    int n_lvl, const void* samp, const void* attn, const float* ref_boxes,
                    const float* pts_scale, float offset_scale, void* out, int32_t* idx_debug,
                    int B, int Lq, int H, int c, int value_dtype, int samp_dtype, int out_dtype,
-                   int flags, int64_t samp_row_stride, int64_t attn_row_stride, void* stream);
+                   int flags, int64_t samp_row_stride, int64_t attn_row_stride, void* records,
+                   void* stream);
 
 /* --------------------------------------------------------------------------
  * K2  multi-scale deformable attention, backward.

@@ -34,16 +34,16 @@ def test_argument_validation_without_gpu():
     lib = _lib.lib()
     hw, st, npts = _lib.i32_array([4, 4]), _lib.i32_array([0]), _lib.i32_array([2])
     rc = lib.dfine_msda_fwd(None, 0, 0, hw, st, npts, 1, None, None, None, None, 0.5, None, None,
-                            0, 1, 1, 32, 0, 0, 0, 0, 0, 0, None)
+                            0, 1, 1, 32, 0, 0, 0, 0, 0, 0, None, None)
     assert rc == -2 and b"positive" in lib.dfine_last_error()
     rc = lib.dfine_msda_fwd(None, 0, 0, hw, st, npts, 9, None, None, None, None, 0.5, None, None,
-                            1, 1, 1, 32, 0, 0, 0, 0, 0, 0, None)
+                            1, 1, 1, 32, 0, 0, 0, 0, 0, 0, None, None)
     assert rc == -3 and b"n_lvl" in lib.dfine_last_error()
     rc = lib.dfine_msda_fwd(None, 0, 0, hw, st, _lib.i32_array([40]), 1, None, None, None, None, 0.5,
-                            None, None, 1, 1, 1, 32, 0, 0, 0, 0, 0, 0, None)
+                            None, None, 1, 1, 1, 32, 0, 0, 0, 0, 0, 0, None, None)
     assert rc == -3 and b"sampling points" in lib.dfine_last_error()
     rc = lib.dfine_msda_fwd(None, 0, 0, hw, st, npts, 1, None, None, None, None, 0.5, None, None,
-                            1, 1, 1, 32, 0, 0, 0, 0, 0, 0, None)
+                            1, 1, 1, 32, 0, 0, 0, 0, 0, 0, None, None)
     assert rc == -1 and b"NULL" in lib.dfine_last_error()
     assert lib.dfine_mask_gemm_fwd(None, None, None, 1, 8, 100, 64, 1, 0, None) == -3
     assert lib.dfine_fdr_project(None, None, None, 31, None) == -2
