@@ -59,7 +59,11 @@ msda_bwd_kernel(const MsdaParams p) {
   constexpr int SPI = SLOTS / IPW;       // slots per item
   static_assert(SPI >= 1, "head slice too wide for two items per warp");
 
-  __shared__ __align__(16) uint2 s_adr[kWarpsPerCta][IPW][4 * LPI];   // corner addresses
+  // corner addresses, [corner j][item][point] with padded item / row strides so that both
+  // the phase-1 stores (lanes = points) and the phase-2 loads (4 points of each item) are
+  // conflict free
+  constexpr int kAdrItem = LPI + 4, kAdrRow = IPW * kAdrItem + 4;
+  __shared__ __align__(16) uint2 s_adr[kWarpsPerCta][4 * kAdrRow];
   __shared__ __align__(16) float4 s_pt[kWarpsPerCta][IPW][LPI];       // {fw, fn, attn, -}
   __shared__ float s_res[kWarpsPerCta][IPW][3][LPI];                  // per-point sums
   __shared__ int s_pix[kScatter ? kWarpsPerCta : 1][IPW][kScatter ? 4 * LPI : 1];
@@ -84,7 +88,7 @@ msda_bwd_kernel(const MsdaParams p) {
     for (int j = 0; j < 4; ++j) {
       const int pix = corner_pixel_local(c, j);
       const uint64_t a = corner_address<VT>(p, img, c.h, pix, c.lstart);
-      s_adr[warp][slot_i][4 * pl + j] = make_uint2((uint32_t)a, (uint32_t)(a >> 32));
+      s_adr[warp][j * kAdrRow + slot_i * kAdrItem + pl] = make_uint2((uint32_t)a, (uint32_t)(a >> 32));
       if (kScatter) s_pix[warp][slot_i][4 * pl + j] = pix >= 0 ? pix + c.lstart : -1;
     }
     s_pt[warp][slot_i][pl] = make_float4(c.g.fw, c.g.fn, c.a, 0.f);
@@ -115,7 +119,7 @@ msda_bwd_kernel(const MsdaParams p) {
       typename Vec16<VT>::Raw raw[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const uint2 ad = s_adr[warp][it][4 * ptc + j];
+        const uint2 ad = s_adr[warp][j * kAdrRow + it * kAdrItem + ptc];
         const char* a = reinterpret_cast<const char*>(((uint64_t)ad.y << 32) | ad.x);
         if (!live) a = reinterpret_cast<const char*>(g_zero_row);
         raw[j] = Vec16<VT>::load_raw(reinterpret_cast<const VT*>(a + sub_bytes));
@@ -127,9 +131,12 @@ msda_bwd_kernel(const MsdaParams p) {
       for (int j = 0; j < 4; ++j) {
         float v[VPL];
         Vec16<VT>::unpack(raw[j], v);
-        d[j] = 0.f;  // <V_corner, grad_out> over this lane's channels
+        // <V_corner, grad_out> over this lane's channels, two channels per packed FFMA2
+        float2 d2 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < VPL; ++i) d[j] = fmaf(v[i], go[i], d[j]);
+        for (int i = 0; i < VPL / 2; ++i)
+          d2 = __ffma2_rn(make_float2(v[2 * i], v[2 * i + 1]), make_float2(go[2 * i], go[2 * i + 1]), d2);
+        d[j] = d2.x + d2.y;
       }
       if (kScatter && live) {
         const float wt[4] = {fs * fe, fs * fw, fn * fe, fn * fw};

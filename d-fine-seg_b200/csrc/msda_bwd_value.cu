@@ -172,17 +172,38 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
   }
   for (int i = tid; i < npx; i += kBvThreads) s_cur[i] = 0;
   __syncthreads();
-  // S1: count corners per pixel
-  for (int t = tid; t < nsamp; t += kBvThreads)
-    bv_visit<false>(__ldg(recs + t), t % p.Lq, lw, lh, px0, px1, s_cur, s_ent);
+  // S1: count corners per pixel (records of a batch are loaded before any is consumed)
+  constexpr int RB = 4;
+  for (int t0 = tid; t0 < nsamp; t0 += RB * kBvThreads) {
+    uint4 r[RB];
+#pragma unroll
+    for (int k = 0; k < RB; ++k) {
+      const int t = t0 + k * kBvThreads;
+      r[k] = make_uint4(0xfffcfffcu, 0u, 0u, 0u);  // x0 = y0 = -4: no corner in bounds
+      if (t < nsamp) r[k] = __ldg(recs + t);
+    }
+#pragma unroll
+    for (int k = 0; k < RB; ++k)
+      bv_visit<false>(r[k], (t0 + k * kBvThreads) % p.Lq, lw, lh, px0, px1, s_cur, s_ent);
+  }
   __syncthreads();
   // S2: CSR offsets
   block_exclusive_scan(s_cur, s_off, npx, s_warp);
   for (int i = tid; i < npx; i += kBvThreads) s_cur[i] = s_off[i];
   __syncthreads();
   // S3: fill
-  for (int t = tid; t < nsamp; t += kBvThreads)
-    bv_visit<true>(__ldg(recs + t), t % p.Lq, lw, lh, px0, px1, s_cur, s_ent);
+  for (int t0 = tid; t0 < nsamp; t0 += RB * kBvThreads) {
+    uint4 r[RB];
+#pragma unroll
+    for (int k = 0; k < RB; ++k) {
+      const int t = t0 + k * kBvThreads;
+      r[k] = make_uint4(0xfffcfffcu, 0u, 0u, 0u);
+      if (t < nsamp) r[k] = __ldg(recs + t);
+    }
+#pragma unroll
+    for (int k = 0; k < RB; ++k)
+      bv_visit<true>(r[k], (t0 + k * kBvThreads) % p.Lq, lw, lh, px0, px1, s_cur, s_ent);
+  }
   if (kStage) asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
@@ -235,10 +256,12 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
     const int px = (int)(en.qp & 0x1fffu);
     const bool fresh = px != cur;
     store_row(cur, acc, fresh && cur >= 0);
-    acc.x = fmaf(en.cw, g.x, fresh ? 0.f : acc.x);
-    acc.y = fmaf(en.cw, g.y, fresh ? 0.f : acc.y);
-    acc.z = fmaf(en.cw, g.z, fresh ? 0.f : acc.z);
-    acc.w = fmaf(en.cw, g.w, fresh ? 0.f : acc.w);
+    const float2 w2 = make_float2(en.cw, en.cw);
+    const float2 lo = __ffma2_rn(w2, make_float2(g.x, g.y),
+                                 make_float2(fresh ? 0.f : acc.x, fresh ? 0.f : acc.y));
+    const float2 hi = __ffma2_rn(w2, make_float2(g.z, g.w),
+                                 make_float2(fresh ? 0.f : acc.z, fresh ? 0.f : acc.w));
+    acc = make_float4(lo.x, lo.y, hi.x, hi.y);
     cur = px;
   };
 

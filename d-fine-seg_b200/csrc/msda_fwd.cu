@@ -69,8 +69,13 @@ msda_fwd_kernel(const MsdaParams p) {
   constexpr int LPI = 32 / IPW;            // lanes (= max points) per item in phase 1
   constexpr int U = 6;                     // loads in flight per lane
 
-  // per warp: IPW x (4*LPI) corner records {address lo, address hi, weight*attn, -}
-  __shared__ __align__(16) uint4 s_rec[kWarpsPerCta][128];
+  // per warp: corner records {address lo, address hi, weight*attn, -}, laid out
+  // [corner j][point lane] with a 2-record pad per row: the phase-1 stores (lanes = points,
+  // fixed j) and the phase-2 loads (8 consecutive corners = 2 points x 4 j) are both free of
+  // bank conflicts.  (A [point][corner] layout made every store 12-way conflicted and the
+  // kernel LSU-wavefront bound.)
+  constexpr int kRecRow = 32 + 2;
+  __shared__ __align__(16) uint4 s_rec[kWarpsPerCta][4 * kRecRow];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
@@ -90,12 +95,12 @@ msda_fwd_kernel(const MsdaParams p) {
     if (c.active) {
       const float wt[4] = {c.g.fs * c.g.fe, c.g.fs * c.g.fw, c.g.fn * c.g.fe, c.g.fn * c.g.fw};
       int pix[4];
-      uint4* dst = &s_rec[warp][slot_i * 4 * LPI + 4 * pl];
+      uint4* dst = &s_rec[warp][slot_i * LPI + pl];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         pix[j] = corner_pixel_local(c, j);
         const uint64_t a = corner_address<VT>(p, img, c.h, pix[j], c.lstart);
-        dst[j] = make_uint4((uint32_t)a, (uint32_t)(a >> 32), __float_as_uint(wt[j] * c.a), 0u);
+        dst[j * kRecRow] = make_uint4((uint32_t)a, (uint32_t)(a >> 32), __float_as_uint(wt[j] * c.a), 0u);
       }
       if (p.rec) store_record(p, p.rec, P, b, pl, c);  // training: saves the backward its phase 1
       if (p.idx_debug) {
@@ -115,10 +120,11 @@ msda_fwd_kernel(const MsdaParams p) {
   for (int it = 0; it < IPW; ++it) {
     const int item = item0 + it;
     if (item >= n_items) break;
-    const uint4* rec = &s_rec[warp][it * 4 * LPI];
-    float acc[VPL];
+    const uint4* rec = &s_rec[warp][it * LPI];
+    // accumulators as fp32 pairs: one packed FFMA2 (fma.rn.f32x2, sm_100) per two channels
+    float2 acc2[VPL / 2];
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) acc[i] = 0.f;
+    for (int i = 0; i < VPL / 2; ++i) acc2[i] = make_float2(0.f, 0.f);
 #pragma unroll 1
     for (int k0 = 0; k0 < ncorner; k0 += U * CPR) {
       typename Vec16<VT>::Raw raw[U];
@@ -128,7 +134,7 @@ msda_fwd_kernel(const MsdaParams p) {
         int k = k0 + u * CPR + slot;
         const bool live = k < ncorner;   // folds away when kP divides evenly
         k = live ? k : 0;
-        const uint4 r = rec[k];
+        const uint4 r = rec[(k & 3) * kRecRow + (k >> 2)];
         cw[u] = live ? __uint_as_float(r.z) : 0.f;
         const char* a = reinterpret_cast<const char*>(((uint64_t)r.y << 32) | r.x);
         if (!live) a = reinterpret_cast<const char*>(g_zero_row);  // idle slot of a ragged tail
@@ -139,9 +145,17 @@ msda_fwd_kernel(const MsdaParams p) {
       for (int u = 0; u < U; ++u) {
         float v[VPL];
         Vec16<VT>::unpack(raw[u], v);
+        const float2 w2 = make_float2(cw[u], cw[u]);
 #pragma unroll
-        for (int i = 0; i < VPL; ++i) acc[i] = fmaf(v[i], cw[u], acc[i]);
+        for (int i = 0; i < VPL / 2; ++i)
+          acc2[i] = __ffma2_rn(make_float2(v[2 * i], v[2 * i + 1]), w2, acc2[i]);
       }
+    }
+    float acc[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL / 2; ++i) {
+      acc[2 * i] = acc2[i].x;
+      acc[2 * i + 1] = acc2[i].y;
     }
     int base;
     bool writer;

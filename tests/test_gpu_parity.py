@@ -410,3 +410,74 @@ def test_packed_raw_and_fused_linear(dev):
     torch.nn.functional.linear(x, w, b).backward(gy)
     for a_, b_ in zip(got, (x.grad, w.grad, b.grad)):
         assert rel_err(a_.cpu().numpy(), b_.cpu().numpy()) <= 5e-5
+
+
+ZOO = [
+    # name, B, Lq, H, c, shapes, npts, value dtype
+    ("n_model_c16_two_levels", 2, 300, 8, 16, [[40, 40], [20, 20]], [6, 6], torch.bfloat16),
+    ("n_model_c16_fp32", 1, 77, 8, 16, [[40, 40], [20, 20]], [6, 6], torch.float32),
+    ("rectangular_multiscale_aug", 2, 123, 8, 32, [[72, 88], [36, 44], [18, 22]], [3, 6, 3], torch.bfloat16),
+    ("four_levels_16_points", 1, 50, 8, 32, [[32, 32], [16, 16], [8, 8], [4, 4]], [4, 4, 4, 4], torch.float32),
+    ("many_points_single_item_per_warp", 1, 33, 4, 32, [[16, 16], [8, 8]], [10, 10], torch.float32),
+    ("odd_heads_runtime_division", 1, 41, 6, 32, [[12, 12], [6, 6]], [4, 4], torch.bfloat16),
+    ("wide_heads_c64", 1, 29, 4, 64, [[20, 20], [10, 10], [5, 5]], [3, 6, 3], torch.bfloat16),
+    ("wide_heads_c64_fp32", 1, 29, 4, 64, [[20, 20], [10, 10]], [4, 4], torch.float32),
+    ("one_level_one_point", 3, 7, 2, 16, [[9, 5]], [1], torch.float32),
+    ("x_model_1024", 1, 500, 8, 32, [[128, 128], [64, 64], [32, 32]], [4, 4, 4], torch.bfloat16),
+]
+
+
+@pytest.mark.parametrize("case", ZOO, ids=[z[0] for z in ZOO])
+def test_shape_zoo_against_oracle(case, dev):
+    """Every template instantiation / runtime path (head widths 16/32/64, fp32 and bf16 value,
+    compile-time and runtime P, one or two items per warp, non-power-of-two head counts,
+    rectangular and 4-level pyramids, chunked level 0) against the CPU oracle: forward,
+    corner indices, and all three gradients in plain and fused input mode."""
+    import dfine_b200.ops as ops
+    from oracle import cpu_oracle as O
+    name, B, Lq, H, c, shapes, npts, vdt = case
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(name.encode()))
+    spec = ops.level_spec(shapes, npts)
+    P = spec.P
+    mem = torch.from_numpy(rng.standard_normal((B, spec.L, H * c), dtype=np.float32)).to(torch.bfloat16)
+    raw_off = torch.from_numpy(rng.standard_normal((B, Lq, H, P, 2), dtype=np.float32) * 1.5).to(torch.bfloat16).float()
+    raw_log = torch.from_numpy(rng.standard_normal((B, Lq, H, P), dtype=np.float32)).to(torch.bfloat16).float()
+    ref = np.concatenate([rng.uniform(-0.1, 1.1, (B, Lq, 2)), rng.uniform(0.02, 1.0, (B, Lq, 2))], -1).astype(np.float32)
+    nps = np.asarray([1.0 / n for n in npts for _ in range(n)], np.float32)
+    go = rng.standard_normal((B, Lq, H * c), dtype=np.float32)
+    m32 = mem.float().numpy().reshape(B, spec.L, H, c)
+    memd = mem.to(dev).to(vdt)
+    # fused mode
+    args = (spec, H, raw_off.to(dev), raw_log.to(dev), _t(ref, dev), _t(nps, dev), 0.5, True)
+    out, idx = ops.msda_forward_raw(memd, *args, torch.float32, want_idx=True)
+    loc = O.msda_locations(raw_off.numpy(), ref, nps, 0.5)
+    attn = O.softmax(raw_log.numpy())
+    o_out, o_idx, _ = O.msda_fwd(m32, shapes, npts, loc, attn, want_idx=True)
+    assert np.array_equal(idx.cpu().numpy(), o_idx), "corner indices"
+    assert_close(out.cpu().numpy(), o_out, FP32_RTOL, "fused out")
+    o_gv, o_gs, o_ga = O.msda_fused_bwd(m32, shapes, npts, raw_off.numpy(), raw_log.numpy(), ref, nps, go, 0.5)
+    if P <= 16:
+        for atomic in (False, True):
+            gm, gs, ga = ops.msda_backward_raw(memd, *args, _t(go, dev), force_atomic=atomic)
+            assert_close(gm.cpu().numpy().reshape(o_gv.shape), o_gv, FP32_RTOL, f"grad_value atomic={atomic}")
+            assert_close(gs.cpu().numpy(), o_gs, FP32_RTOL, "grad_offsets")
+            assert_close(ga.cpu().numpy(), o_ga, FP32_RTOL, "grad_logits")
+        # records written by the forward, consumed by the backward
+        rec = ops.new_records(memd, spec, H, Lq)
+        out2 = ops.msda_forward_raw(memd, *args, torch.float32, records=rec)
+        assert torch.equal(out2, out)
+        gm, gs, ga = ops.msda_backward_raw(memd, *args, _t(go, dev), records=rec)
+        assert_close(gm.cpu().numpy().reshape(o_gv.shape), o_gv, FP32_RTOL, "grad_value (records)")
+        assert_close(gs.cpu().numpy(), o_gs, FP32_RTOL, "grad_offsets (records)")
+        assert_close(ga.cpu().numpy(), o_ga, FP32_RTOL, "grad_logits (records)")
+    # plain mode
+    locd, attnd = _t(loc, dev), _t(attn, dev)
+    outp = ops.msda_forward_raw(memd, spec, H, locd, attnd, None, None, 0.5, False, torch.float32)
+    assert_close(outp.cpu().numpy(), o_out, FP32_RTOL, "plain out")
+    if P <= 16:
+        p_gv, p_gl, p_ga = O.msda_bwd(m32, shapes, npts, loc, attn, go)
+        gm, gl, ga = ops.msda_backward_raw(memd, spec, H, locd, attnd, None, None, 0.5, False, _t(go, dev))
+        assert_close(gm.cpu().numpy().reshape(p_gv.shape), p_gv, FP32_RTOL, "plain grad_value")
+        assert_close(gl.cpu().numpy(), p_gl, FP32_RTOL, "plain grad_loc")
+        assert_close(ga.cpu().numpy(), p_ga, FP32_RTOL, "plain grad_attn")
