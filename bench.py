@@ -416,6 +416,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=4, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager", action="store_true", help="skip the eager-PyTorch GPU bar")
+    ap.add_argument("--launch-list", action="store_true",
+                    help="profiling aid: run W+K eager steps of the B200 path and exit (for an ncu launch list)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -444,6 +446,13 @@ def main():
     hp = HotPath(wl, inp, device)
     hp.load_device(inp)
     hp.pin_host(inp)
+
+    if args.launch_list:
+        for _ in range(args.warmup + args.steps):
+            hp.step(hp.d)
+        torch.cuda.synchronize(device)
+        print(json.dumps({"launch_list": True, "steps": args.warmup + args.steps}))
+        return
 
     sampler = ClockSampler(local) if rank == 0 else None
     # ---- headline: device-resident step, replayed from a CUDA graph ----

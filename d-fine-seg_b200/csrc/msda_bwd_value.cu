@@ -172,38 +172,33 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
   }
   for (int i = tid; i < npx; i += kBvThreads) s_cur[i] = 0;
   __syncthreads();
-  // S1: count corners per pixel (records of a batch are loaded before any is consumed)
+  // S1: count corners per pixel.  Each thread owns up to RB records; they are loaded once
+  // (all loads in flight together) and stay in registers for the fill pass S3.  Shapes with
+  // more than RB*blockDim records per (b, h, level) stream the remainder from memory twice.
   constexpr int RB = 4;
-  for (int t0 = tid; t0 < nsamp; t0 += RB * kBvThreads) {
-    uint4 r[RB];
+  uint4 r[RB];
 #pragma unroll
-    for (int k = 0; k < RB; ++k) {
-      const int t = t0 + k * kBvThreads;
-      r[k] = make_uint4(0xfffcfffcu, 0u, 0u, 0u);  // x0 = y0 = -4: no corner in bounds
-      if (t < nsamp) r[k] = __ldg(recs + t);
-    }
-#pragma unroll
-    for (int k = 0; k < RB; ++k)
-      bv_visit<false>(r[k], (t0 + k * kBvThreads) % p.Lq, lw, lh, px0, px1, s_cur, s_ent);
+  for (int k = 0; k < RB; ++k) {
+    const int t = tid + k * kBvThreads;
+    r[k] = make_uint4(0xfffcfffcu, 0u, 0u, 0u);  // x0 = y0 = -4: no corner in bounds
+    if (t < nsamp) r[k] = __ldg(recs + t);
   }
+#pragma unroll
+  for (int k = 0; k < RB; ++k)
+    bv_visit<false>(r[k], (tid + k * kBvThreads) % p.Lq, lw, lh, px0, px1, s_cur, s_ent);
+  for (int t = tid + RB * kBvThreads; t < nsamp; t += kBvThreads)
+    bv_visit<false>(__ldg(recs + t), t % p.Lq, lw, lh, px0, px1, s_cur, s_ent);
   __syncthreads();
   // S2: CSR offsets
   block_exclusive_scan(s_cur, s_off, npx, s_warp);
   for (int i = tid; i < npx; i += kBvThreads) s_cur[i] = s_off[i];
   __syncthreads();
   // S3: fill
-  for (int t0 = tid; t0 < nsamp; t0 += RB * kBvThreads) {
-    uint4 r[RB];
 #pragma unroll
-    for (int k = 0; k < RB; ++k) {
-      const int t = t0 + k * kBvThreads;
-      r[k] = make_uint4(0xfffcfffcu, 0u, 0u, 0u);
-      if (t < nsamp) r[k] = __ldg(recs + t);
-    }
-#pragma unroll
-    for (int k = 0; k < RB; ++k)
-      bv_visit<true>(r[k], (t0 + k * kBvThreads) % p.Lq, lw, lh, px0, px1, s_cur, s_ent);
-  }
+  for (int k = 0; k < RB; ++k)
+    bv_visit<true>(r[k], (tid + k * kBvThreads) % p.Lq, lw, lh, px0, px1, s_cur, s_ent);
+  for (int t = tid + RB * kBvThreads; t < nsamp; t += kBvThreads)
+    bv_visit<true>(__ldg(recs + t), t % p.Lq, lw, lh, px0, px1, s_cur, s_ent);
   if (kStage) asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 

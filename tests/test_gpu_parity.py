@@ -481,3 +481,66 @@ def test_shape_zoo_against_oracle(case, dev):
         assert_close(gm.cpu().numpy().reshape(p_gv.shape), p_gv, FP32_RTOL, "plain grad_value")
         assert_close(gl.cpu().numpy(), p_gl, FP32_RTOL, "plain grad_loc")
         assert_close(ga.cpu().numpy(), p_ga, FP32_RTOL, "plain grad_attn")
+
+
+def test_decoder_loop_integration(dev):
+    """A decoder-shaped graph on the GPU: `memory` -> value_op views (once) -> 3 cross-attention
+    layers (patched mirror modules, fused path) chained through their queries, FDR decode per
+    layer, one backward.  Compared with the same graph built from the reference call
+    sequence (oracle/torch_port.py, eager PyTorch fp32) with identical parameters: outputs,
+    boxes and the gradients w.r.t. memory (accumulated over the layers through the zero-copy
+    route), the first query and every Linear parameter."""
+    import dfine_b200
+    from oracle import torch_port as TP
+    torch.manual_seed(5)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    B, Lq, C, H = 2, 60, 256, 8
+    shapes, npts, n_layers = [[20, 20], [10, 10], [5, 5]], [3, 6, 3], 3
+    L = sum(h * w for h, w in shapes)
+    mods = []
+    for _ in range(n_layers):
+        m = dfine_b200.MSDeformableAttention(C, H, len(shapes), npts).to(dev)
+        with torch.no_grad():
+            m.sampling_offsets.weight.normal_(0, 0.02)
+            m.attention_weights.weight.normal_(0, 0.05)
+            m.attention_weights.bias.normal_(0, 0.1)
+        mods.append(m)
+    memory0 = torch.randn(B, L, C, device=dev)
+    query0 = torch.randn(B, Lq, C, device=dev)
+    ref = torch.cat([torch.rand(B, Lq, 2, device=dev), torch.rand(B, Lq, 2, device=dev) * 0.5 + 0.05], -1)
+    corners = torch.randn(n_layers, B, Lq, 132, device=dev)
+    up, rs = torch.tensor([0.5], device=dev), torch.tensor([4.0], device=dev)
+    g_out = torch.randn(B, Lq, C, device=dev)
+    g_box = torch.randn(n_layers, B, Lq, 4, device=dev)
+
+    def run(ours: bool):
+        mem = memory0.clone().requires_grad_(True)
+        q = query0.clone().requires_grad_(True)
+        pc = corners.clone().requires_grad_(True)
+        for m in mods:
+            m.zero_grad(set_to_none=True)
+        value = TP.value_views(mem, H, shapes)   # the reference's value_op layout, built once
+        project = dfine_b200.fdr_project(up, rs) if ours else TP.weighting_function(32, up, rs)
+        x, boxes = q, []
+        for i, m in enumerate(mods):
+            if ours:
+                y = m(x, ref.unsqueeze(2), value, shapes)
+                boxes.append(dfine_b200.fdr_decode(pc[i], ref, project, rs))
+            else:
+                y = TP.msda_module(x, ref.unsqueeze(2), value, shapes, m.sampling_offsets.weight,
+                                   m.sampling_offsets.bias, m.attention_weights.weight,
+                                   m.attention_weights.bias, m.num_points_scale, npts, H)
+                boxes.append(TP.distance2bbox(ref, TP.integral(pc[i], project), rs))
+            x = x + torch.tanh(y)                # the next layer's query depends on this layer
+        boxes = torch.stack(boxes)
+        torch.autograd.backward([x, boxes], [g_out, g_box])
+        grads = [mem.grad, q.grad, pc.grad] + [p.grad for m in mods for p in m.parameters()]
+        return [x.detach(), boxes.detach()] + [g.clone() for g in grads]
+
+    got, want = run(True), run(False)
+    names = ["out", "boxes", "grad_memory", "grad_query", "grad_corners"] + \
+            [f"layer{i}.{n}" for i in range(n_layers) for n, _ in mods[0].named_parameters()]
+    for n, a, b in zip(names, got, want):
+        assert rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 1e-4, n
+    assert rel_err(got[0].cpu().numpy(), want[0].cpu().numpy()) <= 2e-5
+    assert rel_err(got[2].cpu().numpy(), want[2].cpu().numpy()) <= 2e-5
