@@ -35,7 +35,9 @@ struct BvChunks {
 };
 
 struct BvEntry {  // 8 bytes
-  uint32_t qp;    // query index << 13 | chunk-local pixel
+  // bits [0,18): byte offset / 16 of the query's grad_out row (relative to the worker's row
+  // base); [18,31): chunk-local pixel; bit 31: this is the LAST entry of its pixel
+  uint32_t x;
   float cw;       // bilinear weight * attention weight
 };
 
@@ -78,8 +80,8 @@ __device__ __forceinline__ void block_exclusive_scan(const int* s_cnt, int* s_of
 
 // One sample record -> its in-chunk corners.  kFill=false counts, kFill=true writes entries.
 template <bool kFill>
-__device__ __forceinline__ void bv_visit(const uint4 r, int q, int lw, int lh, int px0, int px1,
-                                         int* s_cur, BvEntry* s_ent) {
+__device__ __forceinline__ void bv_visit(const uint4 r, uint32_t q_off16, int lw, int lh, int px0,
+                                         int px1, int* s_cur, const int* s_off, BvEntry* s_ent) {
   const int x0 = (int)(short)(r.x & 0xffffu), y0 = (int)(short)(r.x >> 16);
   if (x0 < -1 || y0 < -1 || x0 >= lw || y0 >= lh) return;  // every corner out of bounds
   const float fw = __uint_as_float(r.y), fn = __uint_as_float(r.z), a = __uint_as_float(r.w);
@@ -94,30 +96,40 @@ __device__ __forceinline__ void bv_visit(const uint4 r, int q, int lw, int lh, i
     const int slot = atomicAdd(&s_cur[px - px0], 1);
     if (kFill) {
       BvEntry e;
-      e.qp = ((uint32_t)q << 13) | (uint32_t)(px - px0);
+      const uint32_t last = slot == s_off[px - px0 + 1] - 1 ? 0x80000000u : 0u;
+      e.x = q_off16 | ((uint32_t)(px - px0) << 18) | last;
       e.cw = wt[j] * a;
       s_ent[slot] = e;
     }
   }
 }
 
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a));
+  return r;
+}
+__device__ __forceinline__ uint2 lds_u2(uint32_t a) {
+  uint2 r;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(a));
+  return r;
+}
+
 template <typename GT> struct GoRow;  // 4 consecutive channels of grad_out
 template <> struct GoRow<float> {
   using Raw = float4;
-  template <bool kSmem>
   __device__ static __forceinline__ Raw load(const float* p) {
-    if (kSmem) return *reinterpret_cast<const float4*>(p);
     return __ldg(reinterpret_cast<const float4*>(p));
   }
+  __device__ static __forceinline__ Raw load_shared(uint32_t a) { return lds_f4(a); }
   __device__ static __forceinline__ float4 widen(const Raw& r) { return r; }
 };
 template <> struct GoRow<__nv_bfloat16> {
   using Raw = uint2;
-  template <bool kSmem>
   __device__ static __forceinline__ Raw load(const __nv_bfloat16* p) {
-    if (kSmem) return *reinterpret_cast<const uint2*>(p);
     return __ldg(reinterpret_cast<const uint2*>(p));
   }
+  __device__ static __forceinline__ Raw load_shared(uint32_t a) { return lds_u2(a); }
   __device__ static __forceinline__ float4 widen(const Raw& r) {
     return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u),
                        __uint_as_float(r.y << 16), __uint_as_float(r.y & 0xffff0000u));
@@ -126,10 +138,11 @@ template <> struct GoRow<__nv_bfloat16> {
 
 // kStage: the grad_out slice of this (image, head) -- Lq rows of c channels -- is staged in
 // shared memory with cp.async while the CSR is being built, so that S4 gathers from smem.
-template <int kC, typename GT, bool kStage>
+template <int kC, typename GT, bool kStage, bool kGvBf16>
 __global__ void __launch_bounds__(kBvThreads, 1)
 msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ grad_value,
-                      int gv_bf16, int max_px, int cap) {
+                      int max_px, int cap) {
+  constexpr bool gv_bf16 = kGvBf16;
   constexpr int LPR = kC / 4;          // lanes per row (4 channels each)
   constexpr int WPW = 32 / LPR;        // workers per warp
   constexpr int NWORK = (kBvThreads / 32) * WPW;
@@ -176,6 +189,9 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
   // (all loads in flight together) and stay in registers for the fill pass S3.  Shapes with
   // more than RB*blockDim records per (b, h, level) stream the remainder from memory twice.
   constexpr int RB = 4;
+  // grad_out row stride in 16-byte units: staged rows are packed, global rows span all heads
+  const uint32_t row16 = kStage ? (uint32_t)(kRowBytes / 16)
+                                : (uint32_t)(p.H * kC) * (uint32_t)sizeof(GT) / 16u;
   uint4 r[RB];
 #pragma unroll
   for (int k = 0; k < RB; ++k) {
@@ -185,9 +201,9 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
   }
 #pragma unroll
   for (int k = 0; k < RB; ++k)
-    bv_visit<false>(r[k], (tid + k * kBvThreads) % p.Lq, lw, lh, px0, px1, s_cur, s_ent);
+    bv_visit<false>(r[k], 0u, lw, lh, px0, px1, s_cur, s_off, s_ent);
   for (int t = tid + RB * kBvThreads; t < nsamp; t += kBvThreads)
-    bv_visit<false>(__ldg(recs + t), t % p.Lq, lw, lh, px0, px1, s_cur, s_ent);
+    bv_visit<false>(__ldg(recs + t), 0u, lw, lh, px0, px1, s_cur, s_off, s_ent);
   __syncthreads();
   // S2: CSR offsets
   block_exclusive_scan(s_cur, s_off, npx, s_warp);
@@ -196,9 +212,10 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
   // S3: fill
 #pragma unroll
   for (int k = 0; k < RB; ++k)
-    bv_visit<true>(r[k], (tid + k * kBvThreads) % p.Lq, lw, lh, px0, px1, s_cur, s_ent);
+    bv_visit<true>(r[k], (uint32_t)((tid + k * kBvThreads) % p.Lq) * row16, lw, lh, px0, px1, s_cur,
+                   s_off, s_ent);
   for (int t = tid + RB * kBvThreads; t < nsamp; t += kBvThreads)
-    bv_visit<true>(__ldg(recs + t), t % p.Lq, lw, lh, px0, px1, s_cur, s_ent);
+    bv_visit<true>(__ldg(recs + t), (uint32_t)(t % p.Lq) * row16, lw, lh, px0, px1, s_cur, s_off, s_ent);
   if (kStage) asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
@@ -223,13 +240,12 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
   if (tid == 0) s_wb[NWORK] = npx;
   __syncthreads();
   const int pb = s_wb[worker + 1];
-  // byte strides of one query row of grad_out / one pixel row of grad_value
-  const uint32_t go_row = kStage ? (uint32_t)kRowBytes : (uint32_t)(p.H * kC) * (uint32_t)sizeof(GT);
+  // byte stride of one pixel row of grad_value
   const uint32_t gv_row = (uint32_t)(p.H * kC) * (gv_bf16 ? 2u : 4u);
-  const char* gob = kStage ? reinterpret_cast<const char*>(s_go) + 4 * sub * sizeof(GT)
-                           : reinterpret_cast<const char*>(reinterpret_cast<const GT*>(p.grad_out) +
-                                                           (size_t)b * p.Lq * p.H * kC +
-                                                           (size_t)h * kC + 4 * sub);
+  // this lane's 4 channels of a grad_out row: shared-window address when staged, else global
+  const uint32_t gos = static_cast<uint32_t>(__cvta_generic_to_shared(s_go)) + 4 * sub * (uint32_t)sizeof(GT);
+  const char* gob = reinterpret_cast<const char*>(reinterpret_cast<const GT*>(p.grad_out) +
+                                                  (size_t)b * p.Lq * p.H * kC + (size_t)h * kC + 4 * sub);
   char* gvb = reinterpret_cast<char*>(grad_value) +
               (((size_t)b * p.L + p.lvl_start[lvl] + px0) * p.H * kC + (size_t)h * kC + 4 * sub) *
                   (gv_bf16 ? 2 : 4);
@@ -246,24 +262,25 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
       if (pred) *reinterpret_cast<float4*>(o) = v;
     }
   };
-  // one CSR entry: flush the finished row when the pixel changes (predicated, no branch)
-  auto consume = [&](const BvEntry& en, const float4& g, float4& acc, int& cur) {
-    const int px = (int)(en.qp & 0x1fffu);
-    const bool fresh = px != cur;
-    store_row(cur, acc, fresh && cur >= 0);
+  // one CSR entry: accumulate; the last entry of a pixel stores the finished row and resets
+  auto consume = [&](const BvEntry& en, const float4& g, float4& acc) {
     const float2 w2 = make_float2(en.cw, en.cw);
-    const float2 lo = __ffma2_rn(w2, make_float2(g.x, g.y),
-                                 make_float2(fresh ? 0.f : acc.x, fresh ? 0.f : acc.y));
-    const float2 hi = __ffma2_rn(w2, make_float2(g.z, g.w),
-                                 make_float2(fresh ? 0.f : acc.z, fresh ? 0.f : acc.w));
+    const float2 lo = __ffma2_rn(w2, make_float2(g.x, g.y), make_float2(acc.x, acc.y));
+    const float2 hi = __ffma2_rn(w2, make_float2(g.z, g.w), make_float2(acc.z, acc.w));
     acc = make_float4(lo.x, lo.y, hi.x, hi.y);
-    cur = px;
+    const bool last = (int)en.x < 0;
+    store_row((int)((en.x >> 18) & 0x1fffu), acc, last);
+    if (last) acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  auto load_go_row = [&](const BvEntry& en) {
+    const uint32_t off = (en.x & 0x3ffffu) << 4;
+    if constexpr (kStage) return GoRow<GT>::load_shared(gos + off);
+    else return GoRow<GT>::load(reinterpret_cast<const GT*>(gob + off));
   };
 
   if (pa < pb) {
     const int e1 = s_off[pb];
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    int cur = -1;
     int e = s_off[pa];
     for (; e + U <= e1; e += U) {
       BvEntry ent[U];
@@ -271,18 +288,16 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         ent[u] = s_ent[e + u];
-        raw[u] = GoRow<GT>::template load<kStage>(reinterpret_cast<const GT*>(gob + (ent[u].qp >> 13) * go_row));
+        raw[u] = load_go_row(ent[u]);
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u) consume(ent[u], GoRow<GT>::widen(raw[u]), acc, cur);
+      for (int u = 0; u < U; ++u) consume(ent[u], GoRow<GT>::widen(raw[u]), acc);
     }
     for (; e < e1; ++e) {
       const BvEntry en = s_ent[e];
-      const typename GoRow<GT>::Raw raw =
-          GoRow<GT>::template load<kStage>(reinterpret_cast<const GT*>(gob + (en.qp >> 13) * go_row));
-      consume(en, GoRow<GT>::widen(raw), acc, cur);
+      const typename GoRow<GT>::Raw raw = load_go_row(en);
+      consume(en, GoRow<GT>::widen(raw), acc);
     }
-    store_row(cur, acc, cur >= 0);
   }
   // pixels that no sample touched: explicit zeros (this replaces the memset pass)
   for (int px = worker; px < npx; px += NWORK)
@@ -327,22 +342,32 @@ int launch_msda_bwd_value(const MsdaParams& p, void* grad_value, int gv_bf16, cu
   const bool stage = base_smem + go_smem <= kSmemLimit;
   const size_t smem = base_smem + (stage ? go_smem : 0);
   if (p.c != 16 && p.c != 32 && p.c != 64) return DFINE_E_UNSUPPORTED;
+  // entry field: (grad_out row offset / 16) must fit 18 bits
+  {
+    const long long row16 = stage ? (long long)p.c * (p.go_bf16 ? 2 : 4) / 16
+                                  : (long long)p.H * p.c * (p.go_bf16 ? 2 : 4) / 16;
+    if (row16 * p.Lq >= (1LL << 18)) return DFINE_E_UNSUPPORTED;
+  }
   if (!grad_value) return 0;
   const dim3 grid((unsigned)ch.n, (unsigned)p.H, (unsigned)p.B);
   cudaError_t e = cudaSuccess;
   // the opt-in shared-memory ceiling is raised once per instantiation (not per launch, so that
   // nothing but the launch itself happens under CUDA-graph capture)
-#define DFINE_BV_LAUNCH2(C, GT, ST)                                                              \
+#define DFINE_BV_LAUNCH3(C, GT, ST, OB)                                                          \
   do {                                                                                           \
     static bool configured = false;                                                              \
     if (!configured) {                                                                           \
-      e = cudaFuncSetAttribute(msda_bwd_value_kernel<C, GT, ST>,                                 \
+      e = cudaFuncSetAttribute(msda_bwd_value_kernel<C, GT, ST, OB>,                             \
                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit);    \
       configured = e == cudaSuccess;                                                             \
     }                                                                                            \
     if (e == cudaSuccess)                                                                        \
-      msda_bwd_value_kernel<C, GT, ST><<<grid, kBvThreads, smem, s>>>(p, ch, grad_value,         \
-                                                                      gv_bf16, max_px, cap);     \
+      msda_bwd_value_kernel<C, GT, ST, OB><<<grid, kBvThreads, smem, s>>>(p, ch, grad_value,     \
+                                                                          max_px, cap);          \
+  } while (0)
+#define DFINE_BV_LAUNCH2(C, GT, ST)                                                              \
+  do {                                                                                           \
+    if (gv_bf16) DFINE_BV_LAUNCH3(C, GT, ST, true); else DFINE_BV_LAUNCH3(C, GT, ST, false);     \
   } while (0)
 #define DFINE_BV_LAUNCH(C, GT)                                                                   \
   do {                                                                                           \
@@ -359,6 +384,7 @@ int launch_msda_bwd_value(const MsdaParams& p, void* grad_value, int gv_bf16, cu
   }
 #undef DFINE_BV_LAUNCH
 #undef DFINE_BV_LAUNCH2
+#undef DFINE_BV_LAUNCH3
   if (e != cudaSuccess) return (int)e;
   return (int)cudaGetLastError();
 }
