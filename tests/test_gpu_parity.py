@@ -544,3 +544,80 @@ def test_decoder_loop_integration(dev):
         assert rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 1e-4, n
     assert rel_err(got[0].cpu().numpy(), want[0].cpu().numpy()) <= 2e-5
     assert rel_err(got[2].cpu().numpy(), want[2].cpu().numpy()) <= 2e-5
+
+
+def test_no_out_of_bounds_writes(dev):
+    """compute-sanitizer is closed on this pool, so writes are checked with canaries: every
+    output / workspace of the C-ABI calls sits between guard zones that must stay intact."""
+    import dfine_b200.ops as ops
+    from dfine_b200 import _lib
+    torch.manual_seed(3)
+    B, Lq, H, c = 2, 37, 8, 32
+    shapes, npts = [[13, 17], [7, 9], [4, 5]], [3, 6, 3]
+    spec = ops.level_spec(shapes, npts)
+    P = spec.P
+    GUARD = 4096
+
+    def guarded(nbytes, dtype):
+        raw = torch.full((nbytes + 2 * GUARD,), 0xA5, dtype=torch.uint8, device=dev)
+        view = raw[GUARD:GUARD + nbytes].view(dtype)
+        return raw, view
+
+    def intact(raw, nbytes):
+        return bool((raw[:GUARD] == 0xA5).all() and (raw[GUARD + nbytes:] == 0xA5).all())
+
+    mem = torch.randn(B, spec.L, H * c, device=dev).to(torch.bfloat16)
+    rawin = torch.randn(B, Lq, 3 * H * P, device=dev).to(torch.bfloat16)
+    ref = torch.cat([torch.rand(B, Lq, 2, device=dev) * 1.4 - 0.2, torch.rand(B, Lq, 2, device=dev)], -1)
+    nps = torch.tensor([1.0 / n for n in npts for _ in range(n)], device=dev)
+    go = torch.randn(B, Lq, H * c, device=dev)
+    lib = _lib.lib()
+    n_out, n_rec = B * Lq * H * c * 4, lib.dfine_msda_bwd_workspace_bytes(B, Lq, H, P)
+    n_gv, n_graw = B * spec.L * H * c * 2, B * Lq * 3 * H * P * 2
+    r_out, out = guarded(n_out, torch.float32)
+    r_rec, rec = guarded(n_rec, torch.uint8)
+    r_gv, gv = guarded(n_gv, torch.bfloat16)
+    r_graw, graw = guarded(n_graw, torch.bfloat16)
+    attn_view = rawin.reshape(-1)[2 * H * P:]
+    s = torch.cuda.current_stream().cuda_stream
+    rs = 3 * H * P
+    rc = lib.dfine_msda_fwd(mem.data_ptr(), mem.stride(0), mem.stride(1), spec.hw_c, spec.start_c,
+                            spec.npts_c, spec.n_lvl, rawin.data_ptr(), attn_view.data_ptr(), ref.data_ptr(),
+                            nps.data_ptr(), 0.5, out.data_ptr(), None, B, Lq, H, c, _lib.BF16, _lib.BF16,
+                            _lib.F32, _lib.MSDA_FUSED_INPUTS, rs, rs, rec.data_ptr(), s)
+    _lib.check(rc, "fwd")
+    flags = (_lib.MSDA_FUSED_INPUTS | _lib.MSDA_GRAD_VALUE_BF16 | _lib.MSDA_GRAD_SAMP_BF16 |
+             _lib.MSDA_RECORDS_VALID)
+    graw_attn = graw.reshape(-1)[2 * H * P:]
+    rc = lib.dfine_msda_bwd(mem.data_ptr(), mem.stride(0), mem.stride(1), spec.hw_c, spec.start_c,
+                            spec.npts_c, spec.n_lvl, rawin.data_ptr(), attn_view.data_ptr(), ref.data_ptr(),
+                            nps.data_ptr(), 0.5, go.data_ptr(), gv.data_ptr(), graw.data_ptr(),
+                            graw_attn.data_ptr(), B, Lq, H, c, _lib.BF16, _lib.BF16, _lib.F32, flags,
+                            rs, rs, rs, rs, rec.data_ptr(), n_rec, s)
+    _lib.check(rc, "bwd")
+    torch.cuda.synchronize()
+    assert intact(r_out, n_out) and intact(r_rec, n_rec) and intact(r_gv, n_gv) and intact(r_graw, n_graw)
+    assert torch.isfinite(out).all() and torch.isfinite(gv.float()).all() and torch.isfinite(graw.float()).all()
+    # FDR and mask GEMM outputs
+    N = 61
+    corners = torch.randn(N, 132, device=dev)
+    refi = torch.rand(N, 4, device=dev)
+    proj = ops.fdr_project(torch.tensor([0.5], device=dev), torch.tensor([4.0], device=dev))
+    rsd = torch.tensor([4.0], device=dev)
+    r_b, boxes = guarded(N * 16, torch.float32)
+    r_gc, gc = guarded(N * 132 * 4, torch.float32)
+    _lib.check(lib.dfine_fdr_fwd(corners.data_ptr(), _lib.F32, refi.data_ptr(), proj.data_ptr(), rsd.data_ptr(),
+                                 None, boxes.data_ptr(), N, 32, s), "fdr_fwd")
+    gb = torch.randn(N, 4, device=dev)
+    _lib.check(lib.dfine_fdr_bwd(corners.data_ptr(), _lib.F32, refi.data_ptr(), proj.data_ptr(), rsd.data_ptr(),
+                                 gb.data_ptr(), None, gc.data_ptr(), N, 32, s), "fdr_bwd")
+    Bm, M, K, Nn = 2, 77, 64, 264
+    a = torch.randn(Bm, M, K, device=dev).to(torch.bfloat16)
+    bmat = torch.randn(Bm, K, Nn, device=dev).to(torch.bfloat16)
+    r_mo, mo = guarded(Bm * M * Nn * 2, torch.bfloat16)
+    _lib.check(lib.dfine_mask_gemm_fwd(a.data_ptr(), bmat.data_ptr(), mo.data_ptr(), Bm, M, K, Nn, _lib.BF16, 0, s),
+               "mask")
+    torch.cuda.synchronize()
+    assert intact(r_b, N * 16) and intact(r_gc, N * 132 * 4) and intact(r_mo, Bm * M * Nn * 2)
+    want = torch.bmm(a.float(), bmat.float())
+    assert rel_err(mo.view(Bm, M, Nn).float().cpu().numpy(), want.cpu().numpy()) <= BF16_RTOL
