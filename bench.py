@@ -300,6 +300,16 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def load_traffic(kernel: str):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (or None)."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f).get(kernel)
+    except (OSError, ValueError):
+        return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -495,7 +505,8 @@ def main():
     fwd4, bwd4 = algorithmic_bytes(wl, wl["B"], e_g=4)
     roofline = {
         "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "frac": achieved / peak, "traffic": load_traffic(dom), "peak_source": peak_src,
+        "traffic_source": "profiles/r1_traffic.json (ncu --set full, dram read + write per launch)",
         "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": kernel_ms[dom],
         "msda_fwd_bwd": {"algorithmic_bytes": fwd_b + bwd_b, "ms": fb_ms,
                          "achieved": (fwd_b + bwd_b) / (fb_ms / 1e3) / 1e9,

@@ -47,11 +47,20 @@ def main():
     go = torch.randn(B, Lq, H * c, device=dev)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     tf, tb = [], []
+    # the layout bench.py / the patched module use: one concatenated Linear output, geometry
+    # records written by the forward, gradients in the inputs' dtypes
+    raw = torch.cat([raw_off.reshape(B, Lq, -1), raw_log.reshape(B, Lq, -1)], -1).contiguous()
+    attn_view = raw.reshape(-1)[2 * H * spec.P:]
+    rs = raw.shape[-1]
+    g_raw = torch.empty_like(raw)
     for _ in range(a.iters):
+        rec = ops.new_records(mem, spec, H, Lq)
         ev[0].record()
-        ops.msda_forward_raw(mem, spec, H, raw_off, raw_log, ref, nps, 0.5, True, torch.float32)
+        ops.msda_forward_raw(mem, spec, H, raw, attn_view, ref, nps, 0.5, True, torch.float32,
+                             samp_rs=rs, attn_rs=rs, records=rec)
         ev[1].record()
-        ops.msda_backward_raw(mem, spec, H, raw_off, raw_log, ref, nps, 0.5, True, go)
+        ops.msda_backward_raw(mem, spec, H, raw, attn_view, ref, nps, 0.5, True, go, gv_dtype=mem.dtype,
+                              samp_rs=rs, attn_rs=rs, grad_raw=g_raw, records=rec)
         ev[2].record()
         torch.cuda.synchronize()
         tf.append(ev[0].elapsed_time(ev[1]))
