@@ -269,6 +269,7 @@ int dfine_msda_bwd(const void* value, int64_t v_stride_b, int64_t v_stride_l,
   p.grad_attn = reinterpret_cast<float*>(grad_attn);
   cudaStream_t s = (cudaStream_t)stream;
   const int gv_bf16 = (flags & DFINE_MSDA_GRAD_VALUE_BF16) ? 1 : 0;
+  const int accumulate = (flags & DFINE_MSDA_GRAD_VALUE_ACCUMULATE) ? 1 : 0;
   const size_t ws_need = msda_bwd_workspace_bytes(B, Lq, H, p.P);
   if (!(flags & DFINE_MSDA_FORCE_ATOMIC) && workspace && (size_t)workspace_bytes >= ws_need) {
     // preferred: the dots kernel leaves per-sample records in the workspace, then grad_value
@@ -281,11 +282,11 @@ int dfine_msda_bwd(const void* value, int64_t v_stride_b, int64_t v_stride_l,
     p.rec = reinterpret_cast<uint4*>(workspace);
     p.rec_valid = (flags & DFINE_MSDA_RECORDS_VALID) ? 1 : 0;
     // shape check first: nothing is launched if the gather path cannot take this shape
-    rc = launch_msda_bwd_value(p, nullptr, gv_bf16, s);
+    rc = launch_msda_bwd_value(p, nullptr, gv_bf16, accumulate, s);
     if (rc == 0) {
       if ((rc = launch_msda_bwd(p, value_dtype, /*scatter=*/false, s)))
         return cuda_rc(rc, "dfine_msda_bwd");
-      return cuda_rc(launch_msda_bwd_value(p, grad_value, gv_bf16, s), "dfine_msda_bwd(value)");
+      return cuda_rc(launch_msda_bwd_value(p, grad_value, gv_bf16, accumulate, s), "dfine_msda_bwd(value)");
     }
     if (rc != DFINE_E_UNSUPPORTED) return cuda_rc(rc, "dfine_msda_bwd(value)");
     p.rec = nullptr;
@@ -297,10 +298,13 @@ int dfine_msda_bwd(const void* value, int64_t v_stride_b, int64_t v_stride_l,
               "memory, no DFINE_MSDA_FORCE_ATOMIC); pass a float32 buffer and cast instead");
     return DFINE_E_UNSUPPORTED;
   }
-  // fallback: fp32 vector reductions into a zero-filled buffer
-  const size_t bytes = (size_t)B * p.L * H * c * sizeof(float);
-  cudaError_t e = cudaMemsetAsync(grad_value, 0, bytes, s);
-  if (e != cudaSuccess) return cuda_rc((int)e, "dfine_msda_bwd(memset)");
+  // fallback: fp32 vector reductions into a zero-filled buffer (accumulate mode: into the
+  // caller's running gradient as it is)
+  if (!accumulate) {
+    const size_t bytes = (size_t)B * p.L * H * c * sizeof(float);
+    cudaError_t e = cudaMemsetAsync(grad_value, 0, bytes, s);
+    if (e != cudaSuccess) return cuda_rc((int)e, "dfine_msda_bwd(memset)");
+  }
   return cuda_rc(launch_msda_bwd(p, value_dtype, /*scatter=*/true, s), "dfine_msda_bwd");
 }
 

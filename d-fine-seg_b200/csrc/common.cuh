@@ -124,7 +124,8 @@ void set_error(const char* fmt, ...);
 
 int launch_msda_fwd(const MsdaParams& p, int value_dtype, cudaStream_t s);
 int launch_msda_bwd(const MsdaParams& p, int value_dtype, bool scatter, cudaStream_t s);
-int launch_msda_bwd_value(const MsdaParams& p, void* grad_value, int gv_bf16, cudaStream_t s);
+int launch_msda_bwd_value(const MsdaParams& p, void* grad_value, int gv_bf16, int accumulate,
+                          cudaStream_t s);
 size_t msda_bwd_workspace_bytes(int B, int Lq, int H, int P);
 
 }  // namespace dfine

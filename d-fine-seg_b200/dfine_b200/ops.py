@@ -4,6 +4,7 @@ pointers, streams).  All compute happens in libdfine_b200.so; CPU tensors are re
 from __future__ import annotations
 
 import functools
+import weakref
 from typing import List, Optional, Sequence, Tuple, Union
 
 import torch
@@ -189,11 +190,15 @@ def msda_backward_raw(memory, spec: LevelSpec, H: int, samp, attn, ref, pts_scal
                       offset_scale: float, fused: bool, grad_out,
                       gv_dtype: torch.dtype = torch.float32, force_atomic: bool = False,
                       samp_rs: int = 0, attn_rs: int = 0, grad_raw: Optional[torch.Tensor] = None,
-                      records: Optional[torch.Tensor] = None):
+                      records: Optional[torch.Tensor] = None,
+                      accumulate_into: Optional[torch.Tensor] = None):
     """Direct call of dfine_msda_bwd.  Returns (grad_memory [B,L,C] in `gv_dtype`, fp32
     grad_samp, fp32 grad_attn).  The library normally produces grad_memory with its
     atomic-free gather path directly in `gv_dtype`; shapes it cannot take (or
-    force_atomic=True) use fp32 vector reductions, followed by a cast if bf16 was asked."""
+    force_atomic=True) use fp32 vector reductions, followed by a cast if bf16 was asked.
+    accumulate_into: a running [B,L,C] gradient of `memory` (float32 or bfloat16) that this
+    layer's grad_value is ADDED to in place (DFINE_MSDA_GRAD_VALUE_ACCUMULATE); it is returned
+    as grad_memory."""
     _require_cuda(memory, samp, attn, grad_out)
     B, L, C = memory.shape
     c = C // H
@@ -229,6 +234,17 @@ def msda_backward_raw(memory, spec: LevelSpec, H: int, samp, attn, ref, pts_scal
                 B, Lq, H, c, _dt(memory, "value"), _dt(samp, "samp"), _dt(grad_out, "grad_out"),
                 flags, samp_rs, attn_rs, gs_rs, ga_rs, _ptr(ws), ws_bytes, _stream(memory))
 
+    if accumulate_into is not None:
+        g_mem = accumulate_into
+        if tuple(g_mem.shape) != (B, spec.L, C) or not g_mem.is_contiguous() or g_mem.dtype not in _DT:
+            raise ValueError("accumulate_into must be a contiguous [B, L, C] float32 / bfloat16 tensor")
+        flags = base_flags | _lib.MSDA_GRAD_VALUE_ACCUMULATE
+        if g_mem.dtype == torch.bfloat16:
+            flags |= _lib.MSDA_GRAD_VALUE_BF16
+        if force_atomic:
+            flags |= _lib.MSDA_FORCE_ATOMIC
+        check(call(g_mem, flags), "dfine_msda_bwd")
+        return g_mem, g_samp, g_attn
     if gv_dtype == torch.bfloat16 and not force_atomic:
         g_mem = torch.empty((B, spec.L, C), dtype=torch.bfloat16, device=dev)
         rc = call(g_mem, base_flags | _lib.MSDA_GRAD_VALUE_BF16)
@@ -258,15 +274,99 @@ def cast_f32_to_bf16(src: torch.Tensor) -> torch.Tensor:
     return dst
 
 
+# --------------------------------------------------------------------------------------
+# one gradient buffer for `memory` across the decoder layers
+# --------------------------------------------------------------------------------------
+# All decoder layers sample the SAME `memory` (TransformerDecoder.value_op is called once,
+# reference dfine_decoder.py:454, and its views feed every layer, :483).  Autograd would
+# receive one [B, L, C] gradient per layer and add them pairwise (N_l - 1 full-size add
+# kernels).  Instead the layers' backward kernels accumulate into ONE buffer
+# (DFINE_MSDA_GRAD_VALUE_ACCUMULATE) and a hub node, which autograd runs after every layer that
+# took part in the graph, hands that buffer to `memory` once.
+_SHARE_MEMORY_GRAD = True
+
+
+def share_memory_grad(enabled: bool = True) -> bool:
+    """Switch the shared `memory` gradient buffer on/off (default on); returns the old value."""
+    global _SHARE_MEMORY_GRAD
+    old, _SHARE_MEMORY_GRAD = _SHARE_MEMORY_GRAD, bool(enabled)
+    return old
+
+
+# id(anchor tensor) -> (weakref(anchor), token, session).  Kept OFF the tensor objects: a token
+# stored on a leaf `memory` would close a reference cycle through its AccumulateGrad node that
+# Python's GC cannot see.  Entries leave when their hub runs backward, when the anchor dies,
+# or when more than _MAX_HUBS forward-only graphs are pending.
+_HUBS = {}
+_MAX_HUBS = 2
+
+
+class _MemoryHubFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, memory, sess, key):
+        ctx.sess, ctx.key = sess, key
+        ctx.set_materialize_grads(False)
+        return memory.new_empty(0, dtype=torch.float32)   # token: carries the graph edge only
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, _g_token):
+        ent = _HUBS.get(ctx.key)
+        if ent is not None and ent[2] is ctx.sess:
+            del _HUBS[ctx.key]
+        buf, ctx.sess["buf"] = ctx.sess.get("buf"), None
+        return buf, None, None
+
+
+def _memory_token(memory: torch.Tensor, anchor: Optional[torch.Tensor] = None):
+    """(token, session) of the gradient hub of `memory`, shared by every layer that samples
+    the same tensor object `anchor` (default: `memory` itself) in one forward pass;
+    (None, None) when sharing is off or memory needs no gradient."""
+    if not (_SHARE_MEMORY_GRAD and memory.requires_grad and torch.is_grad_enabled()):
+        return None, None
+    anchor = memory if anchor is None else anchor
+    key = id(anchor)
+    ent = _HUBS.get(key)
+    if ent is not None and ent[0]() is anchor and ent[1].requires_grad:
+        return ent[1], ent[2]
+    for k in [k for k, e in _HUBS.items() if e[0]() is None]:
+        del _HUBS[k]
+    while len(_HUBS) >= _MAX_HUBS:
+        del _HUBS[next(iter(_HUBS))]
+    sess = {"buf": None}
+    token = _MemoryHubFn.apply(memory, sess, key)
+    _HUBS[key] = (weakref.ref(anchor), token, sess)
+    return token, sess
+
+
+def _grad_memory(ctx, memory, *args, **kw):
+    """Runs dfine_msda_bwd for one layer.  With a hub session the layer's grad_value lands in
+    the shared buffer (first layer writes it, later ones accumulate) and None is returned for
+    the per-layer gradient; otherwise the layer's own gradient is returned."""
+    sess = ctx.sess
+    if sess is None:
+        return msda_backward_raw(memory, *args, gv_dtype=memory.dtype, **kw)
+    if sess["buf"] is None:
+        g_mem, g_samp, g_attn = msda_backward_raw(memory, *args, gv_dtype=memory.dtype, **kw)
+        sess["buf"] = g_mem
+    else:
+        _, g_samp, g_attn = msda_backward_raw(memory, *args, accumulate_into=sess["buf"], **kw)
+    return None, g_samp, g_attn
+
+
 class _MsdaFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, memory, samp, attn, ref, pts_scale, spec, H, offset_scale, fused, out_dtype):
+    def forward(ctx, memory, samp, attn, ref, pts_scale, spec, H, offset_scale, fused, out_dtype,
+                token=None, sess=None):
+        # token / sess: hub of the shared `memory` gradient (then `memory` arrives detached)
         samp = samp.contiguous()
         attn = attn.contiguous()
-        rec = new_records(memory, spec, H, samp.shape[1]) if any(ctx.needs_input_grad[:3]) else None
+        need = any(ctx.needs_input_grad[:3]) or ctx.needs_input_grad[10]
+        rec = new_records(memory, spec, H, samp.shape[1]) if need else None
         out = msda_forward_raw(memory, spec, H, samp, attn, ref, pts_scale, offset_scale, fused,
                                out_dtype, records=rec)
         ctx.rec = rec
+        ctx.sess = sess if ctx.needs_input_grad[10] else None
         ctx.save_for_backward(memory, samp, attn, ref, pts_scale)
         ctx.spec, ctx.H, ctx.offset_scale, ctx.fused = spec, H, offset_scale, fused
         return out
@@ -277,14 +377,13 @@ class _MsdaFn(torch.autograd.Function):
         memory, samp, attn, ref, pts_scale = ctx.saved_tensors
         if grad_out.dtype not in _DT:
             grad_out = grad_out.float()
-        g_mem, g_samp, g_attn = msda_backward_raw(memory, ctx.spec, ctx.H, samp, attn, ref,
-                                                  pts_scale, ctx.offset_scale, ctx.fused,
-                                                  grad_out.contiguous(), gv_dtype=memory.dtype,
-                                                  records=ctx.rec)
+        g_mem, g_samp, g_attn = _grad_memory(ctx, memory, ctx.spec, ctx.H, samp, attn, ref,
+                                             pts_scale, ctx.offset_scale, ctx.fused,
+                                             grad_out.contiguous(), records=ctx.rec)
         if g_samp.dtype != samp.dtype:
             g_samp = g_samp.to(samp.dtype)
             g_attn = g_attn.to(attn.dtype)
-        return g_mem, g_samp, g_attn, None, None, None, None, None, None, None
+        return g_mem, g_samp, g_attn, None, None, None, None, None, None, None, None, None
 
 
 class _MsdaPackedFn(torch.autograd.Function):
@@ -293,13 +392,16 @@ class _MsdaPackedFn(torch.autograd.Function):
     gradient tensor in raw's dtype written directly by the backward kernel."""
 
     @staticmethod
-    def forward(ctx, memory, raw, ref, pts_scale, spec, H, offset_scale, out_dtype):
+    def forward(ctx, memory, raw, ref, pts_scale, spec, H, offset_scale, out_dtype, token=None,
+                sess=None):
         rs = raw.shape[-1]
         attn_view = raw.reshape(-1)[2 * H * spec.P:]
-        rec = new_records(memory, spec, H, raw.shape[1]) if any(ctx.needs_input_grad[:2]) else None
+        need = any(ctx.needs_input_grad[:2]) or ctx.needs_input_grad[8]
+        rec = new_records(memory, spec, H, raw.shape[1]) if need else None
         out = msda_forward_raw(memory, spec, H, raw, attn_view, ref, pts_scale, offset_scale, True,
                                out_dtype, samp_rs=rs, attn_rs=rs, records=rec)
         ctx.rec = rec
+        ctx.sess = sess if ctx.needs_input_grad[8] else None
         ctx.save_for_backward(memory, raw, ref, pts_scale)
         ctx.spec, ctx.H, ctx.offset_scale = spec, H, offset_scale
         return out
@@ -313,11 +415,10 @@ class _MsdaPackedFn(torch.autograd.Function):
         rs = raw.shape[-1]
         g_raw = torch.empty_like(raw)
         attn_view = raw.reshape(-1)[2 * ctx.H * ctx.spec.P:]
-        g_mem, _, _ = msda_backward_raw(memory, ctx.spec, ctx.H, raw, attn_view, ref, pts_scale,
-                                        ctx.offset_scale, True, grad_out.contiguous(),
-                                        gv_dtype=memory.dtype, samp_rs=rs, attn_rs=rs, grad_raw=g_raw,
-                                        records=ctx.rec)
-        return g_mem, g_raw, None, None, None, None, None, None
+        g_mem, _, _ = _grad_memory(ctx, memory, ctx.spec, ctx.H, raw, attn_view, ref, pts_scale,
+                                   ctx.offset_scale, True, grad_out.contiguous(), samp_rs=rs,
+                                   attn_rs=rs, grad_raw=g_raw, records=ctx.rec)
+        return g_mem, g_raw, None, None, None, None, None, None, None, None
 
 
 _ONES = {}
@@ -389,8 +490,10 @@ def msda_fused_packed(value, value_spatial_shapes, raw, ref_boxes, pts_scale, nu
     out_dtype = torch.promote_types(memory.dtype, raw.dtype)
     if torch.is_autocast_enabled():
         out_dtype = torch.float32
-    return _MsdaPackedFn.apply(memory, raw.contiguous(), ref, pts_scale.float().contiguous(), spec, H,
-                               float(offset_scale), out_dtype)
+    token, sess = _memory_token(memory, value if isinstance(value, torch.Tensor) else None)
+    return _MsdaPackedFn.apply(memory if token is None else memory.detach(), raw.contiguous(), ref,
+                               pts_scale.float().contiguous(), spec, H, float(offset_scale),
+                               out_dtype, token, sess)
 
 
 def msda_core(value, value_spatial_shapes, sampling_locations, attention_weights,
@@ -412,8 +515,9 @@ def msda_core(value, value_spatial_shapes, sampling_locations, attention_weights
         out_dtype = torch.float32  # grid_sampler is an autocast-to-fp32 op
     loc = sampling_locations.float()
     attn = attention_weights.float()
-    out = _MsdaFn.apply(memory, loc, attn, None, None, spec, H, 0.5, False, out_dtype)
-    return out
+    token, sess = _memory_token(memory, value if isinstance(value, torch.Tensor) else None)
+    return _MsdaFn.apply(memory if token is None else memory.detach(), loc, attn, None, None, spec,
+                         H, 0.5, False, out_dtype, token, sess)
 
 
 def msda_fused(value, value_spatial_shapes, raw_offsets, raw_logits, ref_boxes, pts_scale,
@@ -439,8 +543,10 @@ def msda_fused(value, value_spatial_shapes, raw_offsets, raw_logits, ref_boxes, 
     out_dtype = torch.promote_types(memory.dtype, raw_offsets.dtype)
     if torch.is_autocast_enabled():
         out_dtype = torch.float32
-    return _MsdaFn.apply(memory, samp, attn, ref, pts_scale.float().contiguous(), spec, H,
-                         float(offset_scale), True, out_dtype)
+    token, sess = _memory_token(memory, value if isinstance(value, torch.Tensor) else None)
+    return _MsdaFn.apply(memory if token is None else memory.detach(), samp, attn, ref,
+                         pts_scale.float().contiguous(), spec, H, float(offset_scale), True,
+                         out_dtype, token, sess)
 
 
 # --------------------------------------------------------------------------------------

@@ -54,6 +54,8 @@ extern "C" {
 #define DFINE_MSDA_FORCE_ATOMIC 4    /* bwd: force the fp32 vector-reduction fallback */
 #define DFINE_MSDA_GRAD_SAMP_BF16 8  /* bwd: grad_samp / grad_attn are bf16 buffers */
 #define DFINE_MSDA_RECORDS_VALID 16  /* bwd: workspace holds the records dfine_msda_fwd wrote */
+#define DFINE_MSDA_GRAD_VALUE_ACCUMULATE 32 /* bwd: grad_value += (the caller's running gradient of
+                                               `memory` over the decoder layers, dfine_decoder.py:470-515) */
 
 DFINE_API int dfine_version(void);
 DFINE_API const char* dfine_last_error(void);
@@ -115,10 +117,14 @@ DFINE_API int dfine_msda_fwd(const void* value, int64_t v_stride_b, int64_t v_st
  * grad_out    go_dtype [B, Lq, H*c] contiguous
  * grad_value  float32 (or bf16 with DFINE_MSDA_GRAD_VALUE_BF16) [B, L, H, c] contiguous
  *             (L = sum h_l*w_l); every element is written (no pre-zeroing needed).  With a
- *             workspace the library builds a per-(image, head, level) pixel CSR in shared
- *             memory and gathers, so no float atomics are used; without one, or for shapes
- *             whose CSR does not fit shared memory, it falls back to fp32 vector reductions
- *             (float32 buffer only; a bf16 request then returns DFINE_E_UNSUPPORTED).
+ *             workspace the library builds per-pixel sample lists for every (image, head,
+ *             level chunk) in shared memory and gathers, so no float atomics are used; without
+ *             one, or for shapes whose lists do not fit shared memory, it falls back to fp32
+ *             vector reductions (float32 buffer only; a bf16 request then returns
+ *             DFINE_E_UNSUPPORTED).  With DFINE_MSDA_GRAD_VALUE_ACCUMULATE the result is ADDED
+ *             to the buffer's contents (rows no sample touches are neither read nor written):
+ *             all decoder layers share one `memory`, so their gradients can be summed in place
+ *             instead of by autograd's per-layer add.
  * workspace   caller-owned device scratch of dfine_msda_bwd_workspace_bytes() bytes, or NULL
  * grad_samp   float32 (bf16 with DFINE_MSDA_GRAD_SAMP_BF16) [B, Lq, H, P, 2]  d/d
  *             sampling_locations (plain) or d/d raw offsets (fused)

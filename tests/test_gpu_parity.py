@@ -78,6 +78,32 @@ def test_core_backward_golden(name, vdtype, atomic, dev):
     assert np.abs(gm3.float().cpu().numpy()[fin] - want[fin]).max() <= 2 ** -7 * np.abs(want[fin]).max()
 
 
+@pytest.mark.parametrize("atomic", [False, True], ids=["gather", "atomic"])
+@pytest.mark.parametrize("gdtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("name", CORE_CASES)
+def test_core_backward_accumulate(name, gdtype, atomic, dev):
+    """DFINE_MSDA_GRAD_VALUE_ACCUMULATE: grad_value is added to the caller's running gradient
+    (what autograd's accumulation over the decoder layers does, dfine_decoder.py:470-515);
+    rows no sample touches keep their bits."""
+    if atomic and gdtype == torch.bfloat16:
+        pytest.skip("the vector-reduction fallback accumulates in float32 only")
+    g, ops, spec, H, mem, loc, attn, go = _core_case(name, dev, torch.float32)
+    want = g["grad_memory"]
+    fin = np.isfinite(want)
+    rng = np.random.default_rng(7)
+    base = rng.standard_normal(want.shape).astype(np.float32) * max(float(np.abs(want[fin]).max()), 1e-3)
+    run = torch.from_numpy(base).to(dev).to(gdtype).contiguous()
+    base_q = run.float().cpu().numpy()
+    gm, _, _ = ops.msda_backward_raw(mem, spec, H, loc, attn, None, None, 0.5, False, go,
+                                     force_atomic=atomic, accumulate_into=run)
+    assert gm.data_ptr() == run.data_ptr()
+    got = gm.float().cpu().numpy()
+    tol = FP32_RTOL if gdtype == torch.float32 else BF16_RTOL
+    assert_close(got, base_q + want, tol, "accumulated grad_value")
+    untouched = fin & (want == 0)
+    assert np.array_equal(got[untouched], base_q[untouched]), "untouched rows must keep their bits"
+
+
 def test_core_autograd_through_value_views(dev):
     """The drop-in core called exactly like the reference does: value = tuple of strided
     views from value_op; gradients must reach `memory` through the zero-copy route."""
@@ -544,6 +570,59 @@ def test_decoder_loop_integration(dev):
         assert rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 1e-4, n
     assert rel_err(got[0].cpu().numpy(), want[0].cpu().numpy()) <= 2e-5
     assert rel_err(got[2].cpu().numpy(), want[2].cpu().numpy()) <= 2e-5
+
+
+@pytest.mark.parametrize("amp", [False, True], ids=["fp32", "amp_bf16"])
+def test_shared_memory_gradient_hub(amp, dev):
+    """All layers sample one `memory`; their grad_value kernels accumulate into ONE buffer that
+    a hub node hands to autograd once (ops.share_memory_grad).  Must equal autograd's own
+    per-layer accumulation -- also when a layer is left out of the loss and for a second
+    backward over a retained graph."""
+    import dfine_b200
+    from dfine_b200 import ops
+    from oracle import torch_port as TP
+    torch.manual_seed(11)
+    B, Lq, C, H = 2, 50, 256, 8
+    shapes, npts, n_layers = [[16, 12], [8, 6], [4, 3]], [3, 6, 3], 4
+    L = sum(h * w for h, w in shapes)
+    mods = []
+    for _ in range(n_layers):
+        m = dfine_b200.MSDeformableAttention(C, H, len(shapes), npts).to(dev)
+        with torch.no_grad():
+            m.sampling_offsets.weight.normal_(0, 0.02)
+            m.attention_weights.weight.normal_(0, 0.05)
+        mods.append(m)
+    enc = torch.randn(B, L, C, device=dev)
+    qs = [torch.randn(B, Lq, C, device=dev) for _ in range(n_layers)]
+    ref = torch.cat([torch.rand(B, Lq, 2, device=dev), torch.rand(B, Lq, 2, device=dev) * 0.5 + 0.05], -1)
+    gos = [torch.randn(B, Lq, C, device=dev) for _ in range(n_layers)]
+
+    def run(share, used, twice=False):
+        old = ops.share_memory_grad(share)
+        try:
+            leaf = enc.clone().requires_grad_(True)
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+                mem = (leaf * 1.5).to(torch.bfloat16) if amp else leaf * 1.5  # non-leaf, like the encoder output
+                value = TP.value_views(mem, H, shapes)
+                outs = [m(q, ref.unsqueeze(2), value, shapes) for m, q in zip(mods, qs)]
+            sel = [o for o, u in zip(outs, used) if u]
+            gsel = [g for g, u in zip(gos, used) if u]
+            torch.autograd.backward(sel, gsel, retain_graph=twice)
+            if twice:
+                torch.autograd.backward(sel, gsel)
+            return leaf.grad.clone()
+        finally:
+            ops.share_memory_grad(old)
+
+    tol = BF16_RTOL if amp else FP32_RTOL
+    for used in ([True] * 4, [True, False, True, True], [False, False, True, False]):
+        want = run(False, used)
+        got = run(True, used)
+        assert_close(got.cpu().numpy(), want.cpu().numpy(), tol, f"grad through hub, layers {used}")
+    want2 = run(False, [True] * 4, twice=True)
+    got2 = run(True, [True] * 4, twice=True)
+    assert_close(got2.cpu().numpy(), want2.cpu().numpy(), tol, "second backward over a retained graph")
+    assert len(ops._HUBS) <= ops._MAX_HUBS
 
 
 def test_no_out_of_bounds_writes(dev):
