@@ -8,9 +8,15 @@
 //       in-bounds corner onto a per-pixel linked list in shared memory: the node id is implied
 //       by (record, corner), one native shared-memory integer exchange on the pixel's head
 //       links it: node = {next | query << 15, weight*attn}.  No count pass, no scan.
-//   S2  "workers" of c/VPL lanes (VPL channels per lane) own pixels round-robin; a worker
-//       walks its pixel's list, gathers grad_out[b, q, h, :] (staged in shared memory by
-//       cp.async while S1 runs) and accumulates in registers; the finished row is stored once.
+//       A second integer atomic counts the pixel's corners.
+//   S2  counting sort of the chunk's pixels by corner count, descending (64 bins): the pixels a
+//       warp walks together then have (nearly) equal list lengths -- without it the warp waits
+//       for the longest of its lists, 2.7x the mean on the bench inputs -- and the heaviest
+//       pixels start first.
+//   S3  "workers" of c/VPL lanes (VPL channels per lane) take pixels from the sorted order
+//       round-robin; a worker walks its pixel's list, gathers grad_out[b, q, h, :] (staged in
+//       shared memory by cp.async while S1 runs) and accumulates in registers; the finished
+//       row is stored once.
 // grad_value is written exactly once, coalesced per row, directly in its final dtype (fp32,
 // or bf16 under AMP): no zero-fill pass, no float atomics, no cast pass.  In accumulate mode
 // (DFINE_MSDA_GRAD_VALUE_ACCUMULATE) touched rows are read-modify-written and untouched rows
@@ -25,8 +31,28 @@ namespace dfine {
 
 constexpr int kBvThreads = 1024;
 constexpr int kBvMaxChunks = 64;
-constexpr int kBvNodeBits = 15;                      // node ids 1..32767, 0 = end of list
+constexpr int kBvNodeBits = 16;                      // node ids 1..65535, 0 = end of list
 constexpr uint32_t kBvNodeMask = (1u << kBvNodeBits) - 1u;
+constexpr int kBvBins = 64;                          // pixel sort: corner counts >= 63 share a bin
+
+#ifdef DFINE_BV_PROF
+// per-CTA phase timestamps (globaltimer ns): {start, lists built, sorted, done, smid, chunk}
+__device__ unsigned long long g_bv_prof[8192][6];
+__device__ __forceinline__ unsigned long long bv_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define BV_STAMP(k)                                                                              \
+  do {                                                                                           \
+    if (threadIdx.x == 0) {                                                                      \
+      const unsigned cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);       \
+      if (cta < 8192) g_bv_prof[cta][k] = bv_now();                                              \
+    }                                                                                            \
+  } while (0)
+#else
+#define BV_STAMP(k) do {} while (0)
+#endif
 
 struct BvChunks {
   int n;
@@ -97,11 +123,16 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
   constexpr int WPW = 32 / LPR;        // workers per warp
   constexpr int NWORK = (kBvThreads / 32) * WPW;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint32_t* s_head = reinterpret_cast<uint32_t*>(smem_raw);            // [max_px], padded to even
-  uint2* s_node = reinterpret_cast<uint2*>(s_head + ((max_px + 1) & ~1));  // [cap + 1], [0] = end
+  const int mpx = (max_px + 3) & ~3;
+  uint32_t* s_head = reinterpret_cast<uint32_t*>(smem_raw);            // [mpx] list heads
+  uint32_t* s_cnt = s_head + mpx;                                      // [mpx] corners per pixel
+  uint32_t* s_bin = s_cnt + mpx;                                       // [kBvBins] histogram -> cursors
+  uint2* s_node = reinterpret_cast<uint2*>(s_bin + kBvBins);           // [cap + 1], [0] = end
+  unsigned short* s_order = reinterpret_cast<unsigned short*>(s_node + cap + 1);  // [mpx] sorted pixels
   unsigned char* s_go = reinterpret_cast<unsigned char*>(
-      (reinterpret_cast<uintptr_t>(s_node + cap + 1) + 15) & ~static_cast<uintptr_t>(15));
+      (reinterpret_cast<uintptr_t>(s_order + mpx) + 15) & ~static_cast<uintptr_t>(15));
 
+  BV_STAMP(0);
   const int lvl = ch.lvl[blockIdx.x], px0 = ch.px0[blockIdx.x], px1 = ch.px1[blockIdx.x];
   const int npx = px1 - px0;
   const int h = blockIdx.y, b = blockIdx.z;
@@ -113,55 +144,137 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
   const uint4* recs = p.rec + (((size_t)b * p.H + h) * p.P + p0) * p.Lq;
 
   constexpr int kRowBytes = kC * (int)sizeof(GT);
+  // the mbarrier sits in the 16 bytes that end the dynamic region (no static shared memory:
+  // the opt-in ceiling counts static + dynamic)
+  const uint32_t mbar = static_cast<uint32_t>(__cvta_generic_to_shared(
+      reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(s_go) + (kStage ? (size_t)p.Lq * kRowBytes : 0) + 15) &
+                                       ~static_cast<uintptr_t>(15))));
+  if (kStage && tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // this thread's first RB sample records: the loads are in flight while the arrays are cleared
+  constexpr int RB = 4;
+  uint4 rcd[RB];
+#pragma unroll
+  for (int k = 0; k < RB; ++k) {
+    const int t = tid + k * kBvThreads;
+    rcd[k] = make_uint4(0xfffcfffcu, 0u, 0u, 0u);  // x0 = y0 = -4: no corner in bounds
+    if (t < nsamp) rcd[k] = __ldg(recs + t);
+  }
+  for (int i = tid; i < npx; i += kBvThreads) {
+    s_head[i] = 0u;
+    s_cnt[i] = 0u;
+  }
+  if (tid < kBvBins) s_bin[tid] = 0u;
+  if (tid == 0) s_node[0] = make_uint2(0u, 0u);  // end marker: target of the look-ahead load
+  __syncthreads();
   if (kStage) {
-    // cp.async: 16 bytes per thread, rows of kRowBytes (global row stride H*c elements)
-    constexpr int CPRW = kRowBytes / 16;  // chunks per row
+    // one bulk copy (TMA engine, no LSU traffic) per grad_out row of this head: kRowBytes
+    // contiguous bytes, global row stride H*c elements; completion is counted on s_mbar
     const char* src = reinterpret_cast<const char*>(
         reinterpret_cast<const GT*>(p.grad_out) + (size_t)b * p.Lq * p.H * kC + (size_t)h * kC);
     const size_t src_row = (size_t)p.H * kC * sizeof(GT);
-    for (int i = tid; i < p.Lq * CPRW; i += kBvThreads) {
-      const int q = i / CPRW, k = i % CPRW;
-      const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(s_go + q * kRowBytes + k * 16));
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + q * src_row + k * 16)
-                   : "memory");
+    if (tid == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar),
+                   "r"((uint32_t)(p.Lq * kRowBytes)) : "memory");
+    // (a warp issues its bulk copies one lane at a time: spread the rows over all warps)
+    for (int q = (tid & 31) * (kBvThreads / 32) + (tid >> 5); q < p.Lq; q += kBvThreads) {
+      const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(s_go + q * kRowBytes));
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(dst), "l"(src + q * src_row), "r"((uint32_t)kRowBytes), "r"(mbar) : "memory");
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  for (int i = tid; i < npx; i += kBvThreads) s_head[i] = 0u;
-  if (tid == 0) s_node[0] = make_uint2(0u, 0u);  // end marker: target of the look-ahead load
-  __syncthreads();
 
   // S1: push every in-chunk corner onto its pixel's list
   {
-    int q = tid % p.Lq;
-    const int qstep = kBvThreads % p.Lq;
-    for (int t = tid; t < nsamp; t += kBvThreads) {
-      const uint4 r = __ldg(recs + t);
+    auto visit = [&](const uint4 r, int t, int q) {
       const int x0 = (int)(short)(r.x & 0xffffu), y0 = (int)(short)(r.x >> 16);
-      if (x0 >= -1 && y0 >= -1 && x0 < lw && y0 < lh) {  // else: every corner out of bounds
-        const float fw = __uint_as_float(r.y), fn = __uint_as_float(r.z), a = __uint_as_float(r.w);
-        const float fe = __fsub_rn(1.0f, fw), fs = __fsub_rn(1.0f, fn);
-        const float wt[4] = {fs * fe, fs * fw, fn * fe, fn * fw};
-        const uint32_t qbits = (uint32_t)q << kBvNodeBits;
+      if (x0 < -1 || y0 < -1 || x0 >= lw || y0 >= lh) return;  // every corner out of bounds
+      const float fw = __uint_as_float(r.y), fn = __uint_as_float(r.z), a = __uint_as_float(r.w);
+      const float fe = __fsub_rn(1.0f, fw), fs = __fsub_rn(1.0f, fn);
+      const float wt[4] = {fs * fe, fs * fw, fn * fe, fn * fw};
+      const uint32_t qbits = (uint32_t)q << kBvNodeBits;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int x = x0 + (j & 1), y = y0 + (j >> 1);
-          const int px = y * lw + x - px0;
-          if (x >= 0 && x < lw && y >= 0 && y < lh && px >= 0 && px < npx) {
-            const uint32_t node = 4u * (uint32_t)t + (uint32_t)j + 1u;
-            const uint32_t prev = atomicExch(&s_head[px], node);
-            s_node[node] = make_uint2(prev | qbits, __float_as_uint(wt[j] * a));
-          }
+      for (int j = 0; j < 4; ++j) {
+        const int x = x0 + (j & 1), y = y0 + (j >> 1);
+        const int px = y * lw + x - px0;
+        if (x >= 0 && x < lw && y >= 0 && y < lh && px >= 0 && px < npx) {
+          // [corner][sample] numbering: the lanes of a warp store consecutive 8-byte nodes
+          const uint32_t node = (uint32_t)(j * nsamp + t) + 1u;
+          const uint32_t prev = atomicExch(&s_head[px], node);
+#ifndef DFINE_BV_NOSORT
+          atomicAdd(&s_cnt[px], 1u);
+#endif
+          s_node[node] = make_uint2(prev | qbits, __float_as_uint(wt[j] * a));
         }
       }
+    };
+    int q = tid % p.Lq;
+    const int qstep = kBvThreads % p.Lq;
+#pragma unroll
+    for (int k = 0; k < RB; ++k) {
+      visit(rcd[k], tid + k * kBvThreads, q);
+      q += qstep;
+      if (q >= p.Lq) q -= p.Lq;
+    }
+    for (int t = tid + RB * kBvThreads; t < nsamp; t += kBvThreads) {
+      visit(__ldg(recs + t), t, q);
       q += qstep;
       if (q >= p.Lq) q -= p.Lq;
     }
   }
-  if (kStage) asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
+  BV_STAMP(1);
 
-  // S2: gather
+#ifdef DFINE_BV_NOSORT
+  const int n_touched = npx;
+#else
+  // S2: counting sort of the pixels by corner count, descending
+  for (int i = tid; i < npx; i += kBvThreads) atomicAdd(&s_bin[min(s_cnt[i], (uint32_t)(kBvBins - 1))], 1u);
+  __syncthreads();
+  const int n_touched = npx - (int)s_bin[0];
+  __syncthreads();
+  if (tid < 32) {
+    // exclusive prefix over the bins in DESCENDING count order: cursor[c] = #pixels with a larger bin
+    static_assert(kBvBins == 64, "two bins per lane");
+    const uint32_t hi = s_bin[kBvBins - 1 - tid], lo = s_bin[31 - tid];  // lane 0 holds bins 63 and 31
+    uint32_t a = hi, b2 = lo;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t ta = __shfl_up_sync(0xffffffffu, a, o), tb = __shfl_up_sync(0xffffffffu, b2, o);
+      if (tid >= o) { a += ta; b2 += tb; }
+    }
+    const uint32_t tot_hi = __shfl_sync(0xffffffffu, a, 31);
+    s_bin[kBvBins - 1 - tid] = a - hi;
+    s_bin[31 - tid] = tot_hi + b2 - lo;
+  }
+  __syncthreads();
+  for (int i0 = 0; i0 < npx; i0 += kBvThreads) {   // uniform trip count: match_any is warp-wide
+    const int i = i0 + tid;
+    const uint32_t bin = i < npx ? min(s_cnt[i], (uint32_t)(kBvBins - 1)) : (uint32_t)kBvBins;
+    // lanes of a warp with the same bin take consecutive slots from ONE atomic
+    const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0u;
+    if ((tid & 31) == leader && i < npx) base = atomicAdd(&s_bin[bin], (uint32_t)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (i < npx) s_order[base + __popc(peers & ((1u << (tid & 31)) - 1u))] = (unsigned short)i;
+  }
+#endif
+  if (kStage) {  // grad_out rows have landed
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "BV_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+        "@p bra BV_DONE;\n\t"
+        "bra BV_WAIT;\n\t"
+        "BV_DONE:\n\t}" ::"r"(mbar) : "memory");
+  }
+  __syncthreads();
+  BV_STAMP(2);
+
+  // S3: gather
   const int lane = tid & 31;
   const int worker = (tid >> 5) * WPW + lane / LPR;
   const int sub = lane % LPR;
@@ -179,14 +292,27 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
               (((size_t)b * p.L + p.lvl_start[lvl] + px0) * p.H * kC + (size_t)h * kC + VPL * sub) * kGvE;
   const uint32_t nodes = static_cast<uint32_t>(__cvta_generic_to_shared(s_node));
 
-  for (int px = worker; px < npx; px += NWORK) {
+  // accumulate mode: untouched pixels (the tail of the order) keep their running gradient
+#ifdef DFINE_BV_NOSORT
+  const int n_walk = npx;
+#else
+  const int n_walk = n_touched;  // the untouched tail of the order is zero-filled below
+#endif
+  for (int k = worker; k < n_walk; k += NWORK) {
+#ifdef DFINE_BV_NOSORT
+    const int px = k;
+#else
+    const int px = s_order[k];
+#endif
     uint32_t n = s_head[px];
     char* o = gvb + (uint32_t)px * gv_row;
     float acc[VPL];
 #pragma unroll
     for (int i = 0; i < VPL; ++i) acc[i] = 0.f;
     if (kAccum) {
-      if (n == 0u) continue;  // untouched pixel: the accumulated gradient does not change
+#ifdef DFINE_BV_NOSORT
+      if (n == 0u) continue;
+#endif
       if constexpr (kGvBf16) {
         uint32_t u[VPL / 2];
         if constexpr (VPL == 8) {
@@ -248,6 +374,30 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
             make_float4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]);
     }
   }
+#ifndef DFINE_BV_NOSORT
+  if (!kAccum) {
+    // pixels no sample touched (the tail of the order): explicit zeros, 16 bytes per thread --
+    // this replaces the memset pass of the scatter formulation
+    constexpr int kRowChunks = kC * kGvE / 16;
+    char* gz = reinterpret_cast<char*>(grad_value) +
+               (((size_t)b * p.L + p.lvl_start[lvl] + px0) * p.H * kC + (size_t)h * kC) * kGvE;
+    const int nz = (npx - n_touched) * kRowChunks;
+    for (int i = tid; i < nz; i += kBvThreads) {
+      const int px = s_order[n_touched + i / kRowChunks];
+      *reinterpret_cast<uint4*>(gz + (uint32_t)px * gv_row + (i % kRowChunks) * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+#endif
+#ifdef DFINE_BV_PROF
+  __syncthreads();
+  BV_STAMP(3);
+  if (threadIdx.x == 0) {
+    const unsigned cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    unsigned smid;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    if (cta < 8192) { g_bv_prof[cta][4] = smid; g_bv_prof[cta][5] = blockIdx.x; }
+  }
+#endif
 }
 
 size_t msda_bwd_workspace_bytes(int B, int Lq, int H, int P) {
@@ -265,7 +415,7 @@ int launch_msda_bwd_value(const MsdaParams& p, void* grad_value, int gv_bf16, in
   static const int chunk_px = [] {
     const char* e = getenv("DFINE_BV_CHUNK_PX");
     const int v = e ? atoi(e) : 0;
-    return v >= 64 && v <= 16384 ? v : 4096;
+    return v >= 64 && v <= 16384 ? v : 4096;  // <= 65535: sorted pixel ids are 16-bit
   }();
   BvChunks ch;
   ch.n = 0;
@@ -289,7 +439,9 @@ int launch_msda_bwd_value(const MsdaParams& p, void* grad_value, int gv_bf16, in
     if (c > (long long)kBvNodeMask) return DFINE_E_UNSUPPORTED;
     if (c > cap) cap = (int)c;
   }
-  const size_t base_smem = (size_t)((max_px + 1) & ~1) * sizeof(uint32_t) + (size_t)(cap + 1) * sizeof(uint2) + 16;
+  const size_t mpx = (size_t)((max_px + 3) & ~3);
+  const size_t base_smem = mpx * (2 * sizeof(uint32_t) + sizeof(unsigned short)) + kBvBins * sizeof(uint32_t) +
+                           (size_t)(cap + 1) * sizeof(uint2) + 16 /*align s_go*/ + 32 /*mbarrier*/;
   const size_t go_smem = (size_t)p.Lq * p.c * (p.go_bf16 ? 2 : 4);
   constexpr size_t kSmemLimit = 227 * 1024;
   if (base_smem > kSmemLimit) return DFINE_E_UNSUPPORTED;
@@ -348,3 +500,9 @@ int launch_msda_bwd_value(const MsdaParams& p, void* grad_value, int gv_bf16, in
 }
 
 }  // namespace dfine
+
+#ifdef DFINE_BV_PROF
+extern "C" __attribute__((visibility("default"))) int dfine_debug_bv_prof(void* dst, int n_cta) {
+  return (int)cudaMemcpyFromSymbol(dst, dfine::g_bv_prof, (size_t)n_cta * 6 * sizeof(unsigned long long));
+}
+#endif

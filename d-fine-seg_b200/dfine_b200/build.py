@@ -57,6 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src in sources():
         obj = os.path.join(LIB_DIR, os.path.basename(src).replace(".cu", ".o"))
         cmd = [nvcc, "-ccbin", host, *[f for f in NVCC_FLAGS if f != "--use_fast_math=false"],
+               *os.environ.get("DFINE_NVCC_EXTRA", "").split(),   # e.g. -DDFINE_BV_PROF (debug builds)
                "-I", INCLUDE, "-I", CSRC, "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
