@@ -24,8 +24,11 @@
 // The summation order inside a pixel follows the exchange order (like the reference's
 // atomics, results are reproducible up to fp32 rounding only).
 #include <cstdlib>
+#include <cstring>
+#include <utility>
 
 #include "msda_common.cuh"
+#include "tma_util.cuh"
 
 namespace dfine {
 
@@ -37,7 +40,7 @@ constexpr int kBvBins = 64;                          // pixel sort: corner count
 
 #ifdef DFINE_BV_PROF
 // per-CTA phase timestamps (globaltimer ns): {start, lists built, sorted, done, smid, chunk}
-__device__ unsigned long long g_bv_prof[8192][6];
+__device__ unsigned long long g_bv_prof[8192][10];
 __device__ __forceinline__ unsigned long long bv_now() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -118,7 +121,8 @@ __device__ __forceinline__ void load_go_vec(uint32_t saddr, const char* gaddr, u
 template <int kC, typename GT, int VPL, bool kStage, bool kGvBf16, bool kAccum>
 __global__ void __launch_bounds__(kBvThreads, 1)
 msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ grad_value,
-                      int max_px, int cap) {
+                      int max_px, int cap, const __grid_constant__ CUtensorMap go_map, int go_rows,
+                      int go_loads) {
   constexpr int LPR = kC / VPL;        // lanes per row
   constexpr int WPW = 32 / LPR;        // workers per warp
   constexpr int NWORK = (kBvThreads / 32) * WPW;
@@ -129,13 +133,15 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
   uint32_t* s_bin = s_cnt + mpx;                                       // [kBvBins] histogram -> cursors
   uint2* s_node = reinterpret_cast<uint2*>(s_bin + kBvBins);           // [cap + 1], [0] = end
   unsigned short* s_order = reinterpret_cast<unsigned short*>(s_node + cap + 1);  // [mpx] sorted pixels
-  unsigned char* s_go = reinterpret_cast<unsigned char*>(
-      (reinterpret_cast<uintptr_t>(s_order + mpx) + 15) & ~static_cast<uintptr_t>(15));
+  unsigned char* s_go = reinterpret_cast<unsigned char*>(   // [go_loads * go_rows][c] staged rows
+      (reinterpret_cast<uintptr_t>(s_order + mpx) + 127) & ~static_cast<uintptr_t>(127));
 
   BV_STAMP(0);
-  const int lvl = ch.lvl[blockIdx.x], px0 = ch.px0[blockIdx.x], px1 = ch.px1[blockIdx.x];
+  // grid (H, B, chunks): the chunk index is the SLOWEST grid dimension and the chunks are sorted by
+  // estimated cost, so the heaviest CTAs of every (image, head) are dispatched first
+  const int lvl = ch.lvl[blockIdx.z], px0 = ch.px0[blockIdx.z], px1 = ch.px1[blockIdx.z];
   const int npx = px1 - px0;
-  const int h = blockIdx.y, b = blockIdx.z;
+  const int h = blockIdx.x, b = blockIdx.y;
   const int p0 = lvl == 0 ? 0 : p.lvl_pend[lvl - 1];
   const int np = p.lvl_pend[lvl] - p0;
   const int lw = p.lvl_w[lvl], lh = p.lvl_h[lvl];
@@ -144,14 +150,18 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
   const uint4* recs = p.rec + (((size_t)b * p.H + h) * p.P + p0) * p.Lq;
 
   constexpr int kRowBytes = kC * (int)sizeof(GT);
-  // the mbarrier sits in the 16 bytes that end the dynamic region (no static shared memory:
-  // the opt-in ceiling counts static + dynamic)
-  const uint32_t mbar = static_cast<uint32_t>(__cvta_generic_to_shared(
-      reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(s_go) + (kStage ? (size_t)p.Lq * kRowBytes : 0) + 15) &
-                                       ~static_cast<uintptr_t>(15))));
+  // the mbarrier sits behind the staged rows (no static shared memory: the opt-in ceiling
+  // counts static + dynamic)
+  const uint32_t go_bytes = kStage ? (uint32_t)(go_loads * go_rows * kRowBytes) : 0u;
+  const uint32_t mbar = tma::smem_u32(s_go + go_bytes);
   if (kStage && tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // TMA: go_loads boxes of [go_rows queries][c channels] of grad_out[b, :, h, :] -> s_go.
+    // Issued before anything else: the copy runs under the whole list-building phase.
+    tma::mbar_init(mbar, 1);
+    tma::mbar_expect_tx(mbar, go_bytes);
+    for (int i = 0; i < go_loads; ++i)
+      tma::load_3d(&go_map, tma::smem_u32(s_go + (size_t)i * go_rows * kRowBytes), mbar, h * kC,
+                   i * go_rows, b);
   }
   // this thread's first RB sample records: the loads are in flight while the arrays are cleared
   constexpr int RB = 4;
@@ -169,23 +179,8 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
   if (tid < kBvBins) s_bin[tid] = 0u;
   if (tid == 0) s_node[0] = make_uint2(0u, 0u);  // end marker: target of the look-ahead load
   __syncthreads();
-  if (kStage) {
-    // one bulk copy (TMA engine, no LSU traffic) per grad_out row of this head: kRowBytes
-    // contiguous bytes, global row stride H*c elements; completion is counted on s_mbar
-    const char* src = reinterpret_cast<const char*>(
-        reinterpret_cast<const GT*>(p.grad_out) + (size_t)b * p.Lq * p.H * kC + (size_t)h * kC);
-    const size_t src_row = (size_t)p.H * kC * sizeof(GT);
-    if (tid == 0)
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar),
-                   "r"((uint32_t)(p.Lq * kRowBytes)) : "memory");
-    // (a warp issues its bulk copies one lane at a time: spread the rows over all warps)
-    for (int q = (tid & 31) * (kBvThreads / 32) + (tid >> 5); q < p.Lq; q += kBvThreads) {
-      const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(s_go + q * kRowBytes));
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                   ::"r"(dst), "l"(src + q * src_row), "r"((uint32_t)kRowBytes), "r"(mbar) : "memory");
-    }
-  }
-
+  BV_STAMP(6);
+  BV_STAMP(7);
   // S1: push every in-chunk corner onto its pixel's list
   {
     auto visit = [&](const uint4 r, int t, int q) {
@@ -214,6 +209,9 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
     const int qstep = kBvThreads % p.Lq;
 #pragma unroll
     for (int k = 0; k < RB; ++k) {
+#ifdef DFINE_BV_PROF
+      if (k == 1 && tid == 0) { g_bv_prof[blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)][8] = bv_now() + (rcd[0].x & 1); }
+#endif
       visit(rcd[k], tid + k * kBvThreads, q);
       q += qstep;
       if (q >= p.Lq) q -= p.Lq;
@@ -262,15 +260,7 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
     if (i < npx) s_order[base + __popc(peers & ((1u << (tid & 31)) - 1u))] = (unsigned short)i;
   }
 #endif
-  if (kStage) {  // grad_out rows have landed
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "BV_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
-        "@p bra BV_DONE;\n\t"
-        "bra BV_WAIT;\n\t"
-        "BV_DONE:\n\t}" ::"r"(mbar) : "memory");
-  }
+  if (kStage) tma::mbar_wait(mbar, 0);  // grad_out rows have landed
   __syncthreads();
   BV_STAMP(2);
 
@@ -395,7 +385,7 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
     const unsigned cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
     unsigned smid;
     asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
-    if (cta < 8192) { g_bv_prof[cta][4] = smid; g_bv_prof[cta][5] = blockIdx.x; }
+    if (cta < 8192) { g_bv_prof[cta][4] = smid; g_bv_prof[cta][5] = blockIdx.z; }
   }
 #endif
 }
@@ -411,44 +401,88 @@ int launch_msda_bwd_value(const MsdaParams& p, void* grad_value, int gv_bf16, in
                           cudaStream_t s) {
   if (p.Lq >= (1 << (32 - kBvNodeBits)) || p.B > 65535 || p.H > 65535 || !p.rec) return DFINE_E_UNSUPPORTED;
   if (p.c != 16 && p.c != 32 && p.c != 64) return DFINE_E_UNSUPPORTED;
-  // pixels per chunk: tunable for experiments (DFINE_BV_CHUNK_PX), default 4096
-  static const int chunk_px = [] {
+  // pixels per chunk: the largest power-of-two fraction of 8192 (DFINE_BV_CHUNK_PX overrides the
+  // start, for experiments) whose lists fit shared memory TOGETHER with the staged grad_out
+  // rows; if none does, the largest that fits without staging (rows then come through L1)
+  static const int chunk_px0 = [] {
     const char* e = getenv("DFINE_BV_CHUNK_PX");
     const int v = e ? atoi(e) : 0;
-    return v >= 64 && v <= 16384 ? v : 4096;  // <= 65535: sorted pixel ids are 16-bit
+    return v >= 64 && v <= 16384 ? v : 8192;  // <= 65535: sorted pixel ids are 16-bit
   }();
-  BvChunks ch;
-  ch.n = 0;
-  int max_px = 0, cap = 0;
+  // grad_out[b, :, h, :] arrives as go_loads TMA boxes of go_rows (<= 256) query rows each
+  const int go_loads = (p.Lq + 255) / 256, go_rows = (p.Lq + go_loads - 1) / go_loads;
+  const size_t go_smem = (size_t)go_loads * go_rows * p.c * (p.go_bf16 ? 2 : 4);
+  constexpr size_t kSmemLimit = 227 * 1024;
+  int cap = 0;
   for (int l = 0; l < p.n_lvl; ++l) {
-    const int npx = p.lvl_h[l] * p.lvl_w[l];
     if (p.lvl_h[l] > 32767 || p.lvl_w[l] > 32767) return DFINE_E_UNSUPPORTED;
-    const int np = p.lvl_pend[l] - (l ? p.lvl_pend[l - 1] : 0);
-    const int nchunk = (npx + chunk_px - 1) / chunk_px;
-    const int per = (npx + nchunk - 1) / nchunk;
-    for (int k = 0; k < nchunk; ++k) {
-      if (ch.n >= kBvMaxChunks) return DFINE_E_UNSUPPORTED;
-      ch.lvl[ch.n] = l;
-      ch.px0[ch.n] = k * per;
-      ch.px1[ch.n] = (k + 1) * per < npx ? (k + 1) * per : npx;
-      if (ch.px1[ch.n] - ch.px0[ch.n] > max_px) max_px = ch.px1[ch.n] - ch.px0[ch.n];
-      ++ch.n;
-    }
     // node ids are implied by (record of the level, corner): 4 per sample
-    const long long c = 4LL * np * p.Lq;
+    const long long c = 4LL * (p.lvl_pend[l] - (l ? p.lvl_pend[l - 1] : 0)) * p.Lq;
     if (c > (long long)kBvNodeMask) return DFINE_E_UNSUPPORTED;
     if (c > cap) cap = (int)c;
   }
-  const size_t mpx = (size_t)((max_px + 3) & ~3);
-  const size_t base_smem = mpx * (2 * sizeof(uint32_t) + sizeof(unsigned short)) + kBvBins * sizeof(uint32_t) +
-                           (size_t)(cap + 1) * sizeof(uint2) + 16 /*align s_go*/ + 32 /*mbarrier*/;
-  const size_t go_smem = (size_t)p.Lq * p.c * (p.go_bf16 ? 2 : 4);
-  constexpr size_t kSmemLimit = 227 * 1024;
-  if (base_smem > kSmemLimit) return DFINE_E_UNSUPPORTED;
-  const bool stage = base_smem + go_smem <= kSmemLimit;
+  BvChunks ch;
+  int max_px = 0;
+  size_t base_smem = 0;
+  bool stage = false, planned = false;
+  for (int pass = 0; pass < 2 && !planned; ++pass) {   // pass 0: with staging, pass 1: without
+    for (int chunk_px = chunk_px0; chunk_px >= 64 && !planned; chunk_px >>= 1) {
+      ch.n = 0;
+      max_px = 0;
+      bool ok = true;
+      for (int l = 0; l < p.n_lvl && ok; ++l) {
+        const int npx = p.lvl_h[l] * p.lvl_w[l];
+        const int nchunk = (npx + chunk_px - 1) / chunk_px;
+        const int per = (npx + nchunk - 1) / nchunk;
+        for (int k = 0; k < nchunk; ++k) {
+          if (ch.n >= kBvMaxChunks) { ok = false; break; }
+          ch.lvl[ch.n] = l;
+          ch.px0[ch.n] = k * per;
+          ch.px1[ch.n] = (k + 1) * per < npx ? (k + 1) * per : npx;
+          if (ch.px1[ch.n] - ch.px0[ch.n] > max_px) max_px = ch.px1[ch.n] - ch.px0[ch.n];
+          ++ch.n;
+        }
+      }
+      if (!ok) break;   // smaller chunks only make more of them
+      const size_t mpx = (size_t)((max_px + 3) & ~3);
+      base_smem = mpx * (2 * sizeof(uint32_t) + sizeof(unsigned short)) + kBvBins * sizeof(uint32_t) +
+                  (size_t)(cap + 1) * sizeof(uint2) + 128 /*align s_go*/ + 16 /*mbarrier*/;
+      if (base_smem + (pass == 0 ? go_smem : 0) <= kSmemLimit) {
+        planned = true;
+        stage = pass == 0;
+      }
+    }
+  }
+  if (!planned) return DFINE_E_UNSUPPORTED;
   const size_t smem = base_smem + (stage ? go_smem : 0);
   if (!grad_value) return 0;
-  const dim3 grid((unsigned)ch.n, (unsigned)p.H, (unsigned)p.B);
+  alignas(64) CUtensorMap go_map;
+  memset(&go_map, 0, sizeof go_map);
+  if (stage) {
+    const uint64_t esz = p.go_bf16 ? 2 : 4, row = (uint64_t)p.H * p.c * esz;
+    const int rc = tma::encode_3d_plain(&go_map, p.go_bf16 != 0, p.grad_out, (uint64_t)p.H * p.c,
+                                        (uint64_t)p.Lq, (uint64_t)p.B, row, row * p.Lq, (uint32_t)p.c,
+                                        (uint32_t)go_rows, "msda_bwd(grad_out map)");
+    if (rc) return rc;
+  }
+  // heaviest chunks first (cost ~ expected list nodes + a share per pixel row stored)
+  {
+    double cost[kBvMaxChunks];
+    for (int i = 0; i < ch.n; ++i) {
+      const int l = ch.lvl[i];
+      const int np = p.lvl_pend[l] - (l ? p.lvl_pend[l - 1] : 0);
+      const double px = ch.px1[i] - ch.px0[i];
+      cost[i] = 4.0 * np * p.Lq * px / ((double)p.lvl_h[l] * p.lvl_w[l]) + 0.6 * px;
+    }
+    for (int i = 1; i < ch.n; ++i)
+      for (int j = i; j > 0 && cost[j] > cost[j - 1]; --j) {
+        std::swap(cost[j], cost[j - 1]);
+        std::swap(ch.lvl[j], ch.lvl[j - 1]);
+        std::swap(ch.px0[j], ch.px0[j - 1]);
+        std::swap(ch.px1[j], ch.px1[j - 1]);
+      }
+  }
+  const dim3 grid((unsigned)p.H, (unsigned)p.B, (unsigned)ch.n);
   cudaError_t e = cudaSuccess;
   // the opt-in shared-memory ceiling is raised once per instantiation (not per launch, so that
   // nothing but the launch itself happens under CUDA-graph capture)
@@ -461,8 +495,8 @@ int launch_msda_bwd_value(const MsdaParams& p, void* grad_value, int gv_bf16, in
       configured = e == cudaSuccess;                                                             \
     }                                                                                            \
     if (e == cudaSuccess)                                                                        \
-      msda_bwd_value_kernel<C, GT, V, ST, OB, AC><<<grid, kBvThreads, smem, s>>>(p, ch, grad_value, \
-                                                                                  max_px, cap);  \
+      msda_bwd_value_kernel<C, GT, V, ST, OB, AC><<<grid, kBvThreads, smem, s>>>(                \
+          p, ch, grad_value, max_px, cap, go_map, go_rows, go_loads);                            \
   } while (0)
 #define DFINE_BV_LAUNCH4(C, GT, V, ST, OB)                                                       \
   do {                                                                                           \
@@ -503,6 +537,6 @@ int launch_msda_bwd_value(const MsdaParams& p, void* grad_value, int gv_bf16, in
 
 #ifdef DFINE_BV_PROF
 extern "C" __attribute__((visibility("default"))) int dfine_debug_bv_prof(void* dst, int n_cta) {
-  return (int)cudaMemcpyFromSymbol(dst, dfine::g_bv_prof, (size_t)n_cta * 6 * sizeof(unsigned long long));
+  return (int)cudaMemcpyFromSymbol(dst, dfine::g_bv_prof, (size_t)n_cta * 10 * sizeof(unsigned long long));
 }
 #endif

@@ -40,7 +40,8 @@ def is_stale() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps = sources() + [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "msda_common.cuh"), os.path.join(INCLUDE, "dfine_b200.h")]
+    deps = sources() + [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "msda_common.cuh"), os.path.join(CSRC, "tma_util.cuh"),
+            os.path.join(INCLUDE, "dfine_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

@@ -41,18 +41,25 @@ def main():
                               samp_rs=rs, attn_rs=rs, grad_raw=g_raw, records=rec)
     torch.cuda.synchronize()
     lib = _lib.lib()
-    n = 4 * H * B
-    buf = np.zeros((n, 6), dtype=np.uint64)
+    n = 8192
+    buf = np.zeros((n, 10), dtype=np.uint64)
     fn = lib.dfine_debug_bv_prof
     fn.argtypes = [ctypes.c_void_p, ctypes.c_int]
     rc = fn(buf.ctypes.data, n)
     assert rc == 0, rc
+    # CTAs of the LAST launch: stamps within 1 ms of the newest one
+    newest = buf[:, 3].max()
+    buf = buf[(buf[:, 3] > 0) & (newest - buf[:, 3] < 1_000_000)]
+    n = len(buf)
     t = buf[:, :4].astype(np.int64)
     t0 = t[:, 0].min()
     print(f"kernel span {(t[:, 3].max() - t0) / 1e3:.1f} us, {n} CTAs")
     d = np.diff(t, axis=1) / 1e3
+    t6 = buf[:, 6:9].astype(np.int64)
     for chunk in sorted(set(buf[:, 5].tolist())):
         m = buf[:, 5] == chunk
+        print(f"   chunk {chunk}: start->cleared {(t6[m, 0] - t[m, 0]).mean() / 1e3:.2f}, ->bulk issued {(t6[m, 1] - t[m, 0]).mean() / 1e3:.2f}, "
+              f"->first record done {(t6[m, 2] - t[m, 0]).mean() / 1e3:.2f}, ->lists built {(t[m, 1] - t[m, 0]).mean() / 1e3:.2f}")
         print(f"chunk {chunk}: n={m.sum()} build {d[m, 0].mean():.2f} sort {d[m, 1].mean():.2f} walk {d[m, 2].mean():.2f} "
               f"total {(t[m, 3] - t[m, 0]).mean() / 1e3:.2f} us (max {(t[m, 3] - t[m, 0]).max() / 1e3:.2f})")
     # per-SM timeline: gaps between consecutive CTAs on the same SM
