@@ -211,6 +211,7 @@ int dfine_msda_fwd(const void* value, int64_t v_stride_b, int64_t v_stride_l,
   p.out = out;
   p.out_bf16 = out_dtype == DFINE_BF16;
   p.idx_debug = idx_debug;
+  p.tiled = (flags & DFINE_MSDA_TILED) ? 1 : 0;
   if (records) {
     if ((rc = require_device(records, "records", "dfine_msda_fwd"))) return rc;
     if (!aligned16(records)) {

@@ -410,7 +410,8 @@ int launch_msda_bwd_value(const MsdaParams& p, void* grad_value, int gv_bf16, in
     return v >= 64 && v <= 16384 ? v : 8192;  // <= 65535: sorted pixel ids are 16-bit
   }();
   // grad_out[b, :, h, :] arrives as go_loads TMA boxes of go_rows (<= 256) query rows each
-  const int go_loads = (p.Lq + 255) / 256, go_rows = (p.Lq + go_loads - 1) / go_loads;
+  // (a multiple of 4 rows keeps every box's shared-memory destination 128-byte aligned)
+  const int go_loads = (p.Lq + 255) / 256, go_rows = (((p.Lq + go_loads - 1) / go_loads) + 3) & ~3;
   const size_t go_smem = (size_t)go_loads * go_rows * p.c * (p.go_bf16 ? 2 : 4);
   constexpr size_t kSmemLimit = 227 * 1024;
   int cap = 0;

@@ -15,9 +15,10 @@ static __device__ __align__(256) unsigned char g_zero_row[256];
 
 struct PointCtx {
   float a;            // attention weight of this lane's point (after softmax in fused mode)
+  float lx, ly;       // sampling location in [0, 1] (plain: input; fused: ref + scaled offset)
   float ps;           // fused: num_points_scale of the point
   float4 ref;         // fused: reference box (cx, cy, w, h)
-  int lw, lh, lstart; // level of the point
+  int lvl, lw, lh, lstart; // level of the point
   int q, h;           // query / head of the lane's item
   Geometry g;
   bool active;        // lane owns a real point of a real item
@@ -40,24 +41,17 @@ __device__ __forceinline__ int sel3(int lvl, int v0, int v1, int v2, int v3) {
   return lvl == 0 ? v0 : (lvl == 1 ? v1 : (lvl == 2 ? v2 : v3));
 }
 
-// item : flattened (q * H + h) index of this lane's item (uniform per LPI group)
+// Input arithmetic of one sampling point: loads, (fused) sampling location and softmax.  Fills
+// q, h, a, ps, ref, lx, ly, active; the level fields and the geometry are left to the caller.
+// q, h : query / head of this lane's item (uniform per LPI group)
 // pl   : point index of this lane inside its item;  P: points per head
 template <int LPI>
-__device__ __forceinline__ PointCtx point_phase(const MsdaParams& p, int P, int b, int item, int pl,
-                                                bool item_valid) {
+__device__ __forceinline__ PointCtx point_inputs(const MsdaParams& p, int P, int b, int q, int h, int pl,
+                                                 bool item_valid) {
   PointCtx c;
   c.active = item_valid && pl < P;
-  const int lvl = (pl >= p.lvl_pend[0]) + (pl >= p.lvl_pend[1]) + (pl >= p.lvl_pend[2]);
-  c.lw = sel3(lvl, p.lvl_w[0], p.lvl_w[1], p.lvl_w[2], p.lvl_w[3]);
-  c.lh = sel3(lvl, p.lvl_h[0], p.lvl_h[1], p.lvl_h[2], p.lvl_h[3]);
-  c.lstart = sel3(lvl, p.lvl_start[0], p.lvl_start[1], p.lvl_start[2], p.lvl_start[3]);
-  if (p.h_shift >= 0) {  // H is a power of two in every D-FINE config (8)
-    c.q = item >> p.h_shift;
-    c.h = item & (p.H - 1);
-  } else {
-    c.q = item / p.H;
-    c.h = item - c.q * p.H;
-  }
+  c.q = q;
+  c.h = h;
   // element offsets of this point inside samp / attn: row (b, q) with its own stride, then
   // (h, p) inside the row (the launcher guarantees 31-bit offsets)
   const int row = b * p.Lq + c.q;
@@ -101,8 +95,37 @@ __device__ __forceinline__ PointCtx point_phase(const MsdaParams& p, int P, int 
     ly = l2.y;
     c.a = __ldg(reinterpret_cast<const float*>(p.attn) + s_attn);
   }
-  c.g = sample_geometry(lx, ly, c.lh, c.lw);
+  c.lx = lx;
+  c.ly = ly;
   return c;
+}
+
+template <int LPI>
+__device__ __forceinline__ PointCtx point_phase_qh(const MsdaParams& p, int P, int b, int q, int h,
+                                                   int pl, bool item_valid) {
+  PointCtx c = point_inputs<LPI>(p, P, b, q, h, pl, item_valid);
+  const int lvl = (pl >= p.lvl_pend[0]) + (pl >= p.lvl_pend[1]) + (pl >= p.lvl_pend[2]);
+  c.lvl = lvl;
+  c.lw = sel3(lvl, p.lvl_w[0], p.lvl_w[1], p.lvl_w[2], p.lvl_w[3]);
+  c.lh = sel3(lvl, p.lvl_h[0], p.lvl_h[1], p.lvl_h[2], p.lvl_h[3]);
+  c.lstart = sel3(lvl, p.lvl_start[0], p.lvl_start[1], p.lvl_start[2], p.lvl_start[3]);
+  c.g = sample_geometry(c.lx, c.ly, c.lh, c.lw);
+  return c;
+}
+
+// item : flattened (q * H + h) index of this lane's item (uniform per LPI group)
+template <int LPI>
+__device__ __forceinline__ PointCtx point_phase(const MsdaParams& p, int P, int b, int item, int pl,
+                                                bool item_valid) {
+  int q, h;
+  if (p.h_shift >= 0) {  // H is a power of two in every D-FINE config (8)
+    q = item >> p.h_shift;
+    h = item & (p.H - 1);
+  } else {
+    q = item / p.H;
+    h = item - q * p.H;
+  }
+  return point_phase_qh<LPI>(p, P, b, q, h, pl, item_valid);
 }
 
 // Phase 1 of the backward when the forward left its sample records in the workspace: no
@@ -113,6 +136,7 @@ __device__ __forceinline__ PointCtx point_from_record(const MsdaParams& p, int P
   PointCtx c;
   c.active = item_valid && pl < P;
   const int lvl = (pl >= p.lvl_pend[0]) + (pl >= p.lvl_pend[1]) + (pl >= p.lvl_pend[2]);
+  c.lvl = lvl;
   c.lw = sel3(lvl, p.lvl_w[0], p.lvl_w[1], p.lvl_w[2], p.lvl_w[3]);
   c.lh = sel3(lvl, p.lvl_h[0], p.lvl_h[1], p.lvl_h[2], p.lvl_h[3]);
   c.lstart = sel3(lvl, p.lvl_start[0], p.lvl_start[1], p.lvl_start[2], p.lvl_start[3]);
@@ -172,5 +196,41 @@ __device__ __forceinline__ uint64_t corner_address(const MsdaParams& p, const ch
   const char* a = img + (size_t)off * sizeof(VT);
   return reinterpret_cast<uint64_t>(pix_local >= 0 ? a : reinterpret_cast<const char*>(g_zero_row));
 }
+
+// Phase 3 of the forward kernels: sum over the corner slots of a warp, scattering channels.
+template <int LPC, int VPL>
+struct SlotReduce {
+  static constexpr int kSteps = LPC == 1 ? 5 : LPC == 2 ? 4 : LPC == 4 ? 3 : LPC == 8 ? 2 : 1;
+  // channels a lane holds after the reduction
+  static constexpr int kOut = (VPL >> kSteps) > 0 ? (VPL >> kSteps) : 1;
+  // Sums `acc` over the lanes that share (lane % LPC); afterwards the lane holds kOut
+  // consecutive channels starting at `base` (relative to its VPL group).
+  __device__ static __forceinline__ void run(float (&acc)[VPL], int lane, int& base,
+                                             bool& writer) {
+    base = 0;
+    writer = true;
+    int live = VPL;
+#pragma unroll
+    for (int off = 16; off >= LPC; off >>= 1) {
+      const bool upper = (lane & off) != 0;
+      if (live > 1) {
+        const int half = live / 2;
+#pragma unroll
+        for (int i = 0; i < VPL / 2; ++i) {
+          if (i < half) {
+            const float send = upper ? acc[i] : acc[i + half];
+            const float keep = upper ? acc[i + half] : acc[i];
+            acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+          }
+        }
+        base += upper ? half : 0;
+        live = half;
+      } else {
+        acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], off);
+        writer = writer && !upper;
+      }
+    }
+  }
+};
 
 }  // namespace dfine

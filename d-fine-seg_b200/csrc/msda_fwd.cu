@@ -19,44 +19,11 @@
 //
 // value is read in place from `memory [B, L, H*c]` (no NCHW repack, no per-level copies,
 // no [B*H, c, Lq, P] intermediate as in the reference path).
+#include <cstdlib>
+
 #include "msda_common.cuh"
 
 namespace dfine {
-
-template <int LPC, int VPL>
-struct SlotReduce {
-  static constexpr int kSteps = LPC == 1 ? 5 : LPC == 2 ? 4 : LPC == 4 ? 3 : LPC == 8 ? 2 : 1;
-  // channels a lane holds after the reduction
-  static constexpr int kOut = (VPL >> kSteps) > 0 ? (VPL >> kSteps) : 1;
-  // Sums `acc` over the lanes that share (lane % LPC); afterwards the lane holds kOut
-  // consecutive channels starting at `base` (relative to its VPL group).
-  __device__ static __forceinline__ void run(float (&acc)[VPL], int lane, int& base,
-                                             bool& writer) {
-    base = 0;
-    writer = true;
-    int live = VPL;
-#pragma unroll
-    for (int off = 16; off >= LPC; off >>= 1) {
-      const bool upper = (lane & off) != 0;
-      if (live > 1) {
-        const int half = live / 2;
-#pragma unroll
-        for (int i = 0; i < VPL / 2; ++i) {
-          if (i < half) {
-            const float send = upper ? acc[i] : acc[i + half];
-            const float keep = upper ? acc[i + half] : acc[i];
-            acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-          }
-        }
-        base += upper ? half : 0;
-        live = half;
-      } else {
-        acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], off);
-        writer = writer && !upper;
-      }
-    }
-  }
-};
 
 // kP: points per head known at compile time (12 in every D-FINE config), 0 = runtime.
 // IPW: items per warp (2 when P <= 16).
@@ -67,7 +34,8 @@ msda_fwd_kernel(const MsdaParams p) {
   constexpr int VPL = Vec16<VT>::kElems;   // channels per lane
   constexpr int CPR = 32 / LPC;            // corners per warp-wide load
   constexpr int LPI = 32 / IPW;            // lanes (= max points) per item in phase 1
-  constexpr int U = 6;                     // loads in flight per lane
+  constexpr int U = 6;                     // loads in flight per lane (5 / 6 / 8 resident CTAs and
+                                           // U = 6 / 3 / 2 were measured: 56-63 us, no trend)
 
   // per warp: corner records {address lo, address hi, weight*attn, -}, laid out
   // [corner j][point lane] with a 2-record pad per row: the phase-1 stores (lanes = points,
@@ -201,6 +169,11 @@ static int launch_fwd_t(const MsdaParams& p, cudaStream_t s) {
 }
 
 int launch_msda_fwd(const MsdaParams& p, int value_dtype, cudaStream_t s) {
+  // opt-in (DFINE_MSDA_TILED): persistent CTAs with the small levels resident in shared memory
+  if (p.tiled) {
+    const int rt = launch_msda_fwd_tiled(p, value_dtype, s);
+    if (rt != DFINE_E_UNSUPPORTED) return rt;
+  }
   // lanes per corner = bytes of one head slice / 16
   const int lpc = p.c * (value_dtype == DFINE_BF16 ? 2 : 4) / 16;
   if (value_dtype == DFINE_BF16) {

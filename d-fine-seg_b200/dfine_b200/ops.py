@@ -164,9 +164,10 @@ def _mem_strides(memory: torch.Tensor) -> Tuple[int, int]:
 def msda_forward_raw(memory, spec: LevelSpec, H: int, samp, attn, ref, pts_scale,
                      offset_scale: float, fused: bool, out_dtype: torch.dtype,
                      want_idx: bool = False, samp_rs: int = 0, attn_rs: int = 0,
-                     records: Optional[torch.Tensor] = None):
+                     records: Optional[torch.Tensor] = None, tiled: bool = False):
     """Direct call of dfine_msda_fwd (no autograd).  Returns out [B, Lq, C] (, idx).
-    samp_rs / attn_rs: row strides (elements) when samp / attn alias a wider tensor."""
+    samp_rs / attn_rs: row strides (elements) when samp / attn alias a wider tensor.
+    tiled: ask for the TMA-staged persistent kernel (DFINE_MSDA_TILED)."""
     _require_cuda(memory, samp, attn, ref, pts_scale)
     B, L, C = memory.shape
     c = C // H
@@ -180,7 +181,8 @@ def msda_forward_raw(memory, spec: LevelSpec, H: int, samp, attn, ref, pts_scale
             memory.data_ptr(), sb, sl, spec.hw_c, spec.start_c, spec.npts_c, spec.n_lvl,
             samp.data_ptr(), attn.data_ptr(), _ptr(ref), _ptr(pts_scale), float(offset_scale),
             out.data_ptr(), _ptr(idx), B, Lq, H, c, _dt(memory, "value"), _dt(samp, "samp"),
-            _dt(out, "out"), MSDA_FUSED_INPUTS if fused else 0, samp_rs, attn_rs, _ptr(records),
+            _dt(out, "out"), (MSDA_FUSED_INPUTS if fused else 0) | (_lib.MSDA_TILED if tiled else 0),
+            samp_rs, attn_rs, _ptr(records),
             _stream(memory))
     check(rc, "dfine_msda_fwd")
     return (out, idx) if want_idx else out

@@ -54,6 +54,9 @@ extern "C" {
 #define DFINE_MSDA_FORCE_ATOMIC 4    /* bwd: force the fp32 vector-reduction fallback */
 #define DFINE_MSDA_GRAD_SAMP_BF16 8  /* bwd: grad_samp / grad_attn are bf16 buffers */
 #define DFINE_MSDA_RECORDS_VALID 16  /* bwd: workspace holds the records dfine_msda_fwd wrote */
+#define DFINE_MSDA_TILED 64          /* fwd: persistent CTAs, small pyramid levels staged in shared
+                                       memory by TMA (measured slower than the default kernel at
+                                       D-FINE shapes; kept selectable) */
 #define DFINE_MSDA_GRAD_VALUE_ACCUMULATE 32 /* bwd: grad_value += (the caller's running gradient of
                                                `memory` over the decoder layers, dfine_decoder.py:470-515) */
 

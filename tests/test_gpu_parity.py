@@ -343,6 +343,41 @@ def test_full_size_properties(cfg, dev):
     assert (got - 1.0).abs().max().item() <= 1e-5
 
 
+@pytest.mark.parametrize("vdtype", [torch.bfloat16, torch.float32], ids=["bf16", "f32"])
+def test_tiled_forward_matches_plain(vdtype, dev):
+    """DFINE_MSDA_TILED (persistent CTAs, small levels staged in shared memory by TMA): same
+    corner indices bit for bit, same records, outputs equal to the default kernel up to the
+    fp32 summation order.  Shapes: config 3 with ragged segment boundaries (Lq odd), a
+    two-level head_dim-16 model and the 1024^2 pyramid where only the smallest level fits."""
+    import dfine_b200.ops as ops
+    torch.manual_seed(21)
+    for (B, Lq, H, c, shapes, npts) in [
+        (16, 301, 8, 32, [[80, 80], [40, 40], [20, 20]], [3, 6, 3]),
+        (24, 300, 8, 16, [[40, 40], [20, 20]], [6, 6]),
+        (4, 500, 8, 32, [[128, 128], [64, 64], [32, 32]], [4, 4, 4]),
+    ]:
+        spec = ops.level_spec(shapes, npts)
+        P = spec.P
+        mem = torch.randn(B, spec.L, H * c, device=dev).to(vdtype)
+        ref = torch.cat([torch.rand(B, Lq, 2, device=dev) * 1.1 - 0.05,
+                         torch.rand(B, Lq, 2, device=dev) * 0.5 + 0.02], -1)
+        raw_off = torch.randn(B, Lq, H, P, 2, device=dev).to(vdtype)
+        raw_log = torch.randn(B, Lq, H, P, device=dev).to(vdtype)
+        nps = torch.tensor([1.0 / n for n in npts for _ in range(n)], device=dev)
+        outs = []
+        for tiled in (False, True):
+            rec = ops.new_records(mem, spec, H, Lq)
+            rec.zero_()
+            out, idx = ops.msda_forward_raw(mem, spec, H, raw_off, raw_log, ref, nps, 0.5, True,
+                                            torch.float32, want_idx=True, records=rec, tiled=tiled)
+            outs.append((out, idx, rec))
+        (o0, i0, r0), (o1, i1, r1) = outs
+        assert torch.equal(i0, i1), "corner indices differ"
+        assert (i0 < 0).float().mean() > 0.005, "test should exercise out-of-bounds corners"
+        assert torch.equal(r0, r1), "geometry records differ"
+        assert rel_err(o1.cpu().numpy(), o0.cpu().numpy()) <= FP32_RTOL, (B, Lq, c, shapes)
+
+
 def test_mask_gemm(dev):
     """tcgen05 GEMM vs golden (reference einsum on bf16-representable inputs) and vs
     torch.bmm at the config-4 shape; bf16 products are exact in fp32, so only the
