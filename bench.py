@@ -252,6 +252,62 @@ class HotPath:
         return self.boxes_host
 
 
+def kernel_leg(wl: dict, hp: "HotPath", device, reps: int = 20):
+    """Per-kernel durations behind the roofline figures: every C-ABI kernel of one decoder layer
+    launched `reps` times back to back on the current stream (the device never idles between
+    launches, so the CUDA-event bracket measures kernel time, not host launch gaps), on the
+    step's own layer-0 tensors.  Between timed kernels of the same kind nothing is flushed: the
+    working set of one launch (memory 137.6 MB + gradient 137.6 MB + ...) is larger than L2."""
+    from dfine_b200 import ops
+    import torch.nn.functional as F
+    d, m = hp.d, hp.mods[0]
+    H = wl["H"]
+    spec = ops.level_spec(wl["shapes"], wl["npts"])
+    mem = d["memory"]
+    B, Lq = d["queries"][0].shape[:2]
+    with torch.no_grad():
+        w = torch.cat([m.sampling_offsets.weight, m.attention_weights.weight], 0).to(torch.bfloat16)
+        bias = torch.cat([m.sampling_offsets.bias, m.attention_weights.bias], 0).to(torch.bfloat16)
+        raw = F.linear(d["queries"][0].to(torch.bfloat16), w, bias).contiguous()
+    attn_view = raw.reshape(-1)[2 * H * spec.P:]
+    rs = raw.shape[-1]
+    ref = d["refs"][0].reshape(B, Lq, 4).float().contiguous()
+    nps = m.num_points_scale.float().contiguous()
+    go = d["grad_outs"][0].contiguous()
+    g_raw = torch.empty_like(raw)
+    rec = ops.new_records(mem, spec, H, Lq)
+    run = torch.zeros((B, spec.L, mem.shape[-1]), dtype=mem.dtype, device=device)
+    corners, ref_init, gb = d["corners"][0], d["ref_init"], d["grad_boxes"][0]
+    project = hp.api.fdr_project(hp.up, hp.reg_scale, wl["reg_max"])
+
+    def fwd():
+        ops.msda_forward_raw(mem, spec, H, raw, attn_view, ref, nps, 0.5, True, torch.float32,
+                             samp_rs=rs, attn_rs=rs, records=rec)
+
+    def bwd(acc):
+        ops.msda_backward_raw(mem, spec, H, raw, attn_view, ref, nps, 0.5, True, go, gv_dtype=mem.dtype,
+                              samp_rs=rs, attn_rs=rs, grad_raw=g_raw, records=rec, accumulate_into=acc)
+
+    def fdr():
+        hp.api.fdr_decode(corners, ref_init, project, hp.reg_scale, wl["reg_max"])
+
+    legs = {"msda_fwd": fwd, "msda_bwd": lambda: bwd(None), "msda_bwd_accumulate": lambda: bwd(run),
+            "fdr_fwd": fdr}
+    out = {}
+    for name, fn in legs.items():
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(device)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(reps):
+            fn()
+        e.record()
+        torch.cuda.synchronize(device)
+        out[name] = s.elapsed_time(e) / reps
+    return out
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
 
@@ -486,6 +542,8 @@ def main():
     kernel_ms = {k: sum(s.elapsed_time(e) for s, e in v) / len(v) for k, v in timers.items()}
     kernel_calls = {k: len(v) // args.steps for k, v in timers.items()}
     ops.enable_kernel_timers(False)
+    # ---- kernel leg: each kernel of a layer launched back to back (device-bound timing) ----
+    kms = kernel_leg(wl, hp, device)
     clocks = sampler.stop() if sampler else None
 
     value = job_throughput(wl["B"], world, args.steps, ms)
@@ -498,26 +556,30 @@ def main():
 
     peak, peak_src = load_peaks()
     fwd_b, bwd_b = algorithmic_bytes(wl, wl["B"])
-    dom = "msda_bwd" if kernel_ms.get("msda_bwd", 0) >= kernel_ms.get("msda_fwd", 0) else "msda_fwd"
+    dom = "msda_bwd" if kms["msda_bwd"] >= kms["msda_fwd"] else "msda_fwd"
     dom_bytes = bwd_b if dom == "msda_bwd" else fwd_b
-    achieved = dom_bytes / (kernel_ms[dom] / 1e3) / 1e9
-    fb_ms = kernel_ms.get("msda_fwd", 0) + kernel_ms.get("msda_bwd", 0) + kernel_ms.get("cast_bf16", 0)
+    achieved = dom_bytes / (kms[dom] / 1e3) / 1e9
+    fb_ms = kms["msda_fwd"] + kms["msda_bwd"]
     fwd4, bwd4 = algorithmic_bytes(wl, wl["B"], e_g=4)
     roofline = {
         "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": load_traffic(dom), "peak_source": peak_src,
         "traffic_source": "profiles/r1_traffic.json (ncu --set full, dram read + write per launch)",
-        "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": kernel_ms[dom],
+        "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": kms[dom],
         "msda_fwd_bwd": {"algorithmic_bytes": fwd_b + bwd_b, "ms": fb_ms,
                          "achieved": (fwd_b + bwd_b) / (fb_ms / 1e3) / 1e9,
                          "frac": (fwd_b + bwd_b) / (fb_ms / 1e3) / 1e9 / peak,
                          "frac_with_survey_bytes_e_g4": (fwd4 + bwd4) / (fb_ms / 1e3) / 1e9 / peak,
                          "note": "per decoder layer: dfine_msda_fwd + dfine_msda_bwd (dots kernel + "
-                                 "atomic-free grad_value kernel, bf16 grad written directly); event "
-                                 "brackets include the host-side launch gap of the eager pass"},
-        "kernel_ms": kernel_ms, "kernel_calls_per_step": kernel_calls,
-        "measured_in": "eager pass after the timed region (CUDA events around each C-ABI launch on "
-                       "the launching stream); the timed region itself replays a CUDA graph",
+                                 "atomic-free grad_value kernel writing every row of a bf16 gradient: "
+                                 "the first layer of a backward pass; the other layers run in accumulate "
+                                 "mode, msda_bwd_accumulate)"},
+        "kernel_ms": kms,
+        "eager_kernel_ms": kernel_ms, "kernel_calls_per_step": kernel_calls,
+        "measured_in": "kernel leg after the timed region: 20 back-to-back launches of each C-ABI "
+                       "kernel between two CUDA events on the launching stream (kernel_ms); "
+                       "eager_kernel_ms brackets every launch of an eager step and includes host gaps; "
+                       "the timed region itself replays a CUDA graph",
     }
 
     out = {
@@ -528,6 +590,7 @@ def main():
         "config": {"workload": args.workload, "images_per_gpu": wl["B"], "queries": wl["Lq"],
                    "levels": wl["shapes"], "points": wl["npts"], "decoder_layers": wl["layers"],
                    "value_dtype": "bf16", "accumulate": "f32", "cuda_graph": True,
+                   "memory_grad": "one buffer shared by the 4 layers (hub node), layers 2-4 accumulate in the kernel",
                    "l2_policy": "inputs_larger_than_l2 (per layer: memory 137.6 MB + grad 137.6 MB + queries, "
                                 "grads, records; 4 layers per step)",
                    "parallelism": f"dp{world} (batch-sharded, no data-path collective)"},

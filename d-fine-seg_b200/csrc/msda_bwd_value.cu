@@ -19,8 +19,9 @@
 //       row is stored once.
 // grad_value is written exactly once, coalesced per row, directly in its final dtype (fp32,
 // or bf16 under AMP): no zero-fill pass, no float atomics, no cast pass.  In accumulate mode
-// (DFINE_MSDA_GRAD_VALUE_ACCUMULATE) touched rows are read-modify-written and untouched rows
-// are skipped: this replaces autograd's accumulation of the per-layer `memory` gradients.
+// (DFINE_MSDA_GRAD_VALUE_ACCUMULATE) touched rows are added to the running gradient with vector
+// reductions (one owner per row: deterministic) and untouched rows are skipped: this replaces
+// autograd's accumulation of the per-layer `memory` gradients.
 // The summation order inside a pixel follows the exchange order (like the reference's
 // atomics, results are reproducible up to fp32 rounding only).
 #include <cstdlib>
@@ -78,6 +79,17 @@ __device__ __forceinline__ uint4 lds_u4(uint32_t a) {
   uint4 r;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
   return r;
+}
+
+__device__ __forceinline__ void red_bf16x4(char* a, uint32_t x, uint32_t y) {
+  asm volatile("red.global.add.noftz.v2.bf16x2 [%0], {%1, %2};" ::"l"(a), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void red_bf16x8(char* a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("red.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(a), "r"(x), "r"(y), "r"(z), "r"(w)
+               : "memory");
+}
+__device__ __forceinline__ void red_f32x4(char* a, float x, float y, float z, float w) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
 }
 
 // VPL channels of one grad_out row, from shared (staged) or global memory.  `hs` = 1 swaps
@@ -299,33 +311,9 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
     float acc[VPL];
 #pragma unroll
     for (int i = 0; i < VPL; ++i) acc[i] = 0.f;
-    if (kAccum) {
 #ifdef DFINE_BV_NOSORT
-      if (n == 0u) continue;
+    if (kAccum && n == 0u) continue;
 #endif
-      if constexpr (kGvBf16) {
-        uint32_t u[VPL / 2];
-        if constexpr (VPL == 8) {
-          const uint2 t0 = *reinterpret_cast<const uint2*>(o + 8u * hs);
-          const uint2 t1 = *reinterpret_cast<const uint2*>(o + 8u * (hs ^ 1u));
-          u[0] = t0.x; u[1] = t0.y; u[2] = t1.x; u[3] = t1.y;
-        } else {
-          const uint2 t = *reinterpret_cast<const uint2*>(o);
-          u[0] = t.x; u[1] = t.y;
-        }
-#pragma unroll
-        for (int i = 0; i < VPL / 2; ++i) {
-          acc[2 * i] = __uint_as_float(u[i] << 16);
-          acc[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
-        }
-      } else {
-#pragma unroll
-        for (int v = 0; v < VPL / 4; ++v) {
-          const float4 t = *reinterpret_cast<const float4*>(o + (VPL == 8 ? 16u * ((uint32_t)v ^ hs) : 16u * (uint32_t)v));
-          acc[4 * v] = t.x; acc[4 * v + 1] = t.y; acc[4 * v + 2] = t.z; acc[4 * v + 3] = t.w;
-        }
-      }
-    }
     uint2 nd = lds_u2(nodes + 8u * n);
     while (n != 0u) {
       const uint32_t q = nd.x >> kBvNodeBits;
@@ -342,6 +330,11 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
         acc[2 * i + 1] = r.y;
       }
     }
+    // write-all mode: plain stores.  Accumulate mode: one vector reduction per 16 bytes into the
+    // running gradient (native REDG.ADD BF16x4 / BF16x8 / F32x4, fire and forget: no load, no
+    // wait; a row is touched by exactly one worker per launch, so the result is deterministic).
+    // bf16: the layer's sum is rounded to bf16 and added in bf16 -- the arithmetic of autograd's
+    // own accumulation of per-layer bf16 gradients.
     if constexpr (kGvBf16) {
       uint32_t u[VPL / 2];
 #pragma unroll
@@ -350,18 +343,27 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
         u[i] = *reinterpret_cast<const uint32_t*>(&t);
       }
       if constexpr (VPL == 8 && kSwap) {
-        *reinterpret_cast<uint2*>(o + 8u * hs) = make_uint2(u[0], u[1]);
-        *reinterpret_cast<uint2*>(o + 8u * (hs ^ 1u)) = make_uint2(u[2], u[3]);
+        if constexpr (kAccum) {
+          red_bf16x4(o + 8u * hs, u[0], u[1]);
+          red_bf16x4(o + 8u * (hs ^ 1u), u[2], u[3]);
+        } else {
+          *reinterpret_cast<uint2*>(o + 8u * hs) = make_uint2(u[0], u[1]);
+          *reinterpret_cast<uint2*>(o + 8u * (hs ^ 1u)) = make_uint2(u[2], u[3]);
+        }
       } else if constexpr (VPL == 8) {
-        *reinterpret_cast<uint4*>(o) = make_uint4(u[0], u[1], u[2], u[3]);
+        if constexpr (kAccum) red_bf16x8(o, u[0], u[1], u[2], u[3]);
+        else *reinterpret_cast<uint4*>(o) = make_uint4(u[0], u[1], u[2], u[3]);
       } else {
-        *reinterpret_cast<uint2*>(o) = make_uint2(u[0], u[1]);
+        if constexpr (kAccum) red_bf16x4(o, u[0], u[1]);
+        else *reinterpret_cast<uint2*>(o) = make_uint2(u[0], u[1]);
       }
     } else {
 #pragma unroll
-      for (int v = 0; v < VPL / 4; ++v)
-        *reinterpret_cast<float4*>(o + (VPL == 8 ? 16u * ((uint32_t)v ^ hs) : 16u * (uint32_t)v)) =
-            make_float4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]);
+      for (int v = 0; v < VPL / 4; ++v) {
+        char* ov = o + (VPL == 8 ? 16u * ((uint32_t)v ^ hs) : 16u * (uint32_t)v);
+        if constexpr (kAccum) red_f32x4(ov, acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]);
+        else *reinterpret_cast<float4*>(ov) = make_float4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]);
+      }
     }
   }
 #ifndef DFINE_BV_NOSORT
