@@ -22,6 +22,7 @@ int launch_fdr_project(const float*, const float*, float*, int, cudaStream_t);
 int launch_fdr(bool, const void*, int, const float*, const float*, const float*, float*, float*,
                const float*, const float*, float*, long long, int, cudaStream_t);
 int launch_mask_gemm(const void*, const void*, void*, int, int, int, int, int, int, cudaStream_t);
+int launch_colsum(const void*, int, long long, int, long long, float*, cudaStream_t);
 
 static int cuda_rc(int rc, const char* what) {
   if (rc > 0) set_error("%s: CUDA error %d (%s)", what, rc, cudaGetErrorString((cudaError_t)rc));
@@ -331,6 +332,29 @@ int dfine_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream)
   cast_f32_bf16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       src, reinterpret_cast<__nv_bfloat16*>(dst), n);
   return cuda_rc((int)cudaGetLastError(), "dfine_cast_f32_to_bf16");
+}
+
+int dfine_colsum(const void* x, int x_dtype, int64_t M, int N, int64_t row_stride, float* out,
+                 void* stream) {
+  const char* fn = "dfine_colsum";
+  int rc;
+  if (M < 0 || N <= 0 || (N & 1) || N > 1024 || (row_stride != 0 && row_stride < N) || (row_stride & 1)) {
+    set_error("%s: need M >= 0, even 0 < N <= 1024 and an even row_stride >= N (got %lld, %d, %lld)", fn,
+              (long long)M, N, (long long)row_stride);
+    return DFINE_E_SHAPE;
+  }
+  if (x_dtype != DFINE_F32 && x_dtype != DFINE_BF16) {
+    set_error("%s: x_dtype must be DFINE_F32 or DFINE_BF16", fn);
+    return DFINE_E_UNSUPPORTED;
+  }
+  if ((rc = require_device(out, "out", fn))) return rc;
+  if (M > 0 && (rc = require_device(x, "x", fn))) return rc;
+  if (M > 0 && (reinterpret_cast<uintptr_t>(x) & 7u)) {
+    set_error("%s: x must be 8-byte aligned", fn);
+    return DFINE_E_ALIGN;
+  }
+  return cuda_rc(launch_colsum(x, x_dtype == DFINE_BF16, M, N, row_stride ? row_stride : N, out,
+                               (cudaStream_t)stream), fn);
 }
 
 int dfine_fdr_project(const float* up, const float* reg_scale, float* project, int reg_max,

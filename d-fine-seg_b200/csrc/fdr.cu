@@ -69,9 +69,10 @@ fdr_kernel(const void* __restrict__ corners, int c_bf16, const float* __restrict
 #pragma unroll
   for (int o = 4; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   float d = 0.f;
+  const float inv = 1.0f / sum;   // one IEEE division per lane instead of one per bin
 #pragma unroll
   for (int t = 0; t < kBinsPerLane; ++t) {
-    x[t] = x[t] / sum;  // Pr(n)
+    x[t] = x[t] * inv;  // Pr(n)
     d = fmaf(x[t], w[t], d);
   }
 #pragma unroll

@@ -39,6 +39,7 @@ _SIGNATURES = {
                                c_void_p]),
     "dfine_msda_bwd_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int]),
     "dfine_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "dfine_colsum": (c_int, [c_void_p, c_int, c_int64, c_int, c_int64, c_void_p, c_void_p]),
     "dfine_fdr_project": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "dfine_fdr_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_int64, c_int, c_void_p]),

@@ -18,7 +18,7 @@ INCLUDE = os.path.join(REPO_ROOT, "include")
 LIB_DIR = os.path.join(PKG_DIR, "_C")
 LIB_PATH = os.path.join(LIB_DIR, "libdfine_b200.so")
 
-SOURCES = ["api.cu", "msda_fwd.cu", "msda_fwd_tiled.cu", "msda_bwd.cu", "msda_bwd_value.cu", "fdr.cu", "mask_gemm.cu"]
+SOURCES = ["api.cu", "msda_fwd.cu", "msda_fwd_tiled.cu", "msda_bwd.cu", "msda_bwd_value.cu", "fdr.cu", "mask_gemm.cu", "reduce.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--use_fast_math=false",

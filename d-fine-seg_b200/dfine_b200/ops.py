@@ -458,8 +458,31 @@ class _LinearFn(torch.autograd.Function):
             g2 = g2.to(w.dtype)
         gx = _mm(g2, w, ctx.x_dtype).reshape(ctx.x_shape)
         gw = _mm(g2.t(), x2, ctx.w_dtype)
-        gb = _mm(_ones_row(g2.shape[0], g2.dtype, g2.device), g2, ctx.b_dtype).reshape(-1)
+        if colsum_supported(g2):
+            gb = colsum(g2)
+            if gb.dtype != ctx.b_dtype:
+                gb = gb.to(ctx.b_dtype)
+        else:   # odd widths: library GEMM with a row of ones
+            gb = _mm(_ones_row(g2.shape[0], g2.dtype, g2.device), g2, ctx.b_dtype).reshape(-1)
         return gx, gw, gb
+
+
+def colsum_supported(x: torch.Tensor) -> bool:
+    return (x.dim() == 2 and x.stride(1) == 1 and x.dtype in _DT and x.shape[1] % 2 == 0
+            and x.shape[1] <= 1024 and x.stride(0) % 2 == 0 and x.data_ptr() % 8 == 0)
+
+
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    """Column sums of a row-major 2-D float32 / bfloat16 matrix -> float32 [N] (dfine_colsum)."""
+    _require_cuda(x)
+    if not colsum_supported(x):
+        raise ValueError("colsum: need a row-major 2-D float32/bfloat16 matrix with an even width <= 1024")
+    out = torch.empty(x.shape[1], dtype=torch.float32, device=x.device)
+    with torch.cuda.device_of(x), _timed("colsum", x):
+        rc = _lib.lib().dfine_colsum(x.data_ptr(), _dt(x, "x"), x.shape[0], x.shape[1], x.stride(0),
+                                     out.data_ptr(), _stream(x))
+    check(rc, "dfine_colsum")
+    return out
 
 
 def _mm(a, b, out_dtype):

@@ -155,6 +155,14 @@ DFINE_API int64_t dfine_msda_bwd_workspace_bytes(int B, int Lq, int H, int P);
 /* Packs fp32 grad_value [n] to bf16 (AMP: the gradient of a bf16 `memory`). */
 DFINE_API int dfine_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 
+/* Column sums of a row-major matrix: out[n] = sum_m x[m*row_stride + n], float32 accumulation.
+ * The bias gradient of the concatenated sampling_offsets / attention_weights Linear
+ * (autograd of dfine_decoder.py:139-147) over the [B*Lq, 3HP] gradient dfine_msda_bwd writes.
+ * x: x_dtype [M, N] (row_stride elements between rows, 0 = N; N and row_stride even, N <= 1024,
+ * x 8-byte aligned); out: float32 [N], overwritten. */
+DFINE_API int dfine_colsum(const void* x, int x_dtype, int64_t M, int N, int64_t row_stride, float* out,
+                 void* stream);
+
 /* --------------------------------------------------------------------------
  * K3  FDR: weighting function, Integral and distance2bbox.
  *

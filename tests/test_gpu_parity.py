@@ -409,6 +409,25 @@ def test_mask_gemm(dev):
     assert a.grad.shape == a.shape and b.grad.shape == b.shape
 
 
+def test_colsum(dev):
+    """dfine_colsum (bias gradient of the concatenated Linear) against a float64 sum."""
+    import dfine_b200.ops as ops
+    torch.manual_seed(2)
+    for (M, N, dt) in [(16000, 288, torch.bfloat16), (16000, 288, torch.float32), (77, 96, torch.bfloat16),
+                       (1, 2, torch.float32), (4099, 1024, torch.bfloat16)]:
+        x = torch.randn(M, N, device=dev).to(dt)
+        want = x.double().sum(0)
+        got = ops.colsum(x)
+        assert got.dtype == torch.float32 and got.shape == (N,)
+        scale = x.double().abs().sum(0).max().item()
+        assert (got.double() - want).abs().max().item() <= 1e-6 * scale, (M, N, dt)
+    # a strided view (row stride > width)
+    big = torch.randn(500, 300, device=dev)
+    assert torch.allclose(ops.colsum(big[:, :288]), big[:, :288].sum(0), rtol=1e-5, atol=1e-4)
+    with pytest.raises(ValueError):
+        ops.colsum(torch.randn(8, 7, device=dev))
+
+
 def test_error_behaviour(dev):
     import dfine_b200
     import dfine_b200.ops as ops
