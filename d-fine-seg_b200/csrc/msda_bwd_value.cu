@@ -60,6 +60,7 @@ __device__ __forceinline__ unsigned long long bv_now() {
 
 struct BvChunks {
   int n;
+  int n_heavy;            // the first n_heavy chunks (sorted by cost) are interleaved over the grid
   int lvl[kBvMaxChunks];
   int px0[kBvMaxChunks];  // level-local pixel range [px0, px1)
   int px1[kBvMaxChunks];
@@ -149,11 +150,24 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
       (reinterpret_cast<uintptr_t>(s_order + mpx) + 127) & ~static_cast<uintptr_t>(127));
 
   BV_STAMP(0);
-  // grid (H, B, chunks): the chunk index is the SLOWEST grid dimension and the chunks are sorted by
-  // estimated cost, so the heaviest CTAs of every (image, head) are dispatched first
-  const int lvl = ch.lvl[blockIdx.z], px0 = ch.px0[blockIdx.z], px1 = ch.px1[blockIdx.z];
+  // 1-D grid over (chunk, image, head).  The chunks are sorted by estimated cost; the n_heavy
+  // heaviest ones (comparable cost: e.g. the dense 40x40 level -- shared-memory bound -- and the
+  // sparse 80x80 level -- bound by its HBM row stores) alternate over the first CTAs so that
+  // both kinds run side by side on the chip; the light chunks follow and fill the tail.
+  int chunk, bh;
+  {
+    const int HB = p.H * p.B, bid = blockIdx.x, heavy = ch.n_heavy * HB;
+    if (bid < heavy) {
+      chunk = bid % ch.n_heavy;
+      bh = bid / ch.n_heavy;
+    } else {
+      chunk = ch.n_heavy + (bid - heavy) / HB;
+      bh = (bid - heavy) % HB;
+    }
+  }
+  const int lvl = ch.lvl[chunk], px0 = ch.px0[chunk], px1 = ch.px1[chunk];
   const int npx = px1 - px0;
-  const int h = blockIdx.x, b = blockIdx.y;
+  const int b = bh / p.H, h = bh - b * p.H;
   const int p0 = lvl == 0 ? 0 : p.lvl_pend[lvl - 1];
   const int np = p.lvl_pend[lvl] - p0;
   const int lw = p.lvl_w[lvl], lh = p.lvl_h[lvl];
@@ -166,14 +180,11 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
   // counts static + dynamic)
   const uint32_t go_bytes = kStage ? (uint32_t)(go_loads * go_rows * kRowBytes) : 0u;
   const uint32_t mbar = tma::smem_u32(s_go + go_bytes);
-  if (kStage && tid == 0) {
-    // TMA: go_loads boxes of [go_rows queries][c channels] of grad_out[b, :, h, :] -> s_go.
-    // Issued before anything else: the copy runs under the whole list-building phase.
+  if (kStage && tid == kBvThreads - 1) {   // (the last thread owns the fewest sample records)
+    // the descriptor fetch (~1 us, measured) starts now; the copies are issued after the first
+    // barrier so that the barrier does not wait for it
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&go_map) : "memory");
     tma::mbar_init(mbar, 1);
-    tma::mbar_expect_tx(mbar, go_bytes);
-    for (int i = 0; i < go_loads; ++i)
-      tma::load_3d(&go_map, tma::smem_u32(s_go + (size_t)i * go_rows * kRowBytes), mbar, h * kC,
-                   i * go_rows, b);
   }
   // this thread's first RB sample records: the loads are in flight while the arrays are cleared
   constexpr int RB = 4;
@@ -192,6 +203,14 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
   if (tid == 0) s_node[0] = make_uint2(0u, 0u);  // end marker: target of the look-ahead load
   __syncthreads();
   BV_STAMP(6);
+  if (kStage && tid == kBvThreads - 1) {
+    // TMA: go_loads boxes of [go_rows queries][c channels] of grad_out[b, :, h, :] -> s_go; the
+    // copy runs under the list-building and sorting phases
+    tma::mbar_expect_tx(mbar, go_bytes);
+    for (int i = 0; i < go_loads; ++i)
+      tma::load_3d(&go_map, tma::smem_u32(s_go + (size_t)i * go_rows * kRowBytes), mbar, h * kC,
+                   i * go_rows, b);
+  }
   BV_STAMP(7);
   // S1: push every in-chunk corner onto its pixel's list
   {
@@ -366,6 +385,10 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
       }
     }
   }
+#ifdef DFINE_BV_PROF
+  __syncthreads();
+  BV_STAMP(9);
+#endif
 #ifndef DFINE_BV_NOSORT
   if (!kAccum) {
     // pixels no sample touched (the tail of the order): explicit zeros, 16 bytes per thread --
@@ -387,7 +410,7 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
     const unsigned cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
     unsigned smid;
     asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
-    if (cta < 8192) { g_bv_prof[cta][4] = smid; g_bv_prof[cta][5] = blockIdx.z; }
+    if (cta < 8192) { g_bv_prof[cta][4] = smid; g_bv_prof[cta][5] = (unsigned long long)chunk; }
   }
 #endif
 }
@@ -484,8 +507,11 @@ int launch_msda_bwd_value(const MsdaParams& p, void* grad_value, int gv_bf16, in
         std::swap(ch.px0[j], ch.px0[j - 1]);
         std::swap(ch.px1[j], ch.px1[j - 1]);
       }
+    ch.n_heavy = 1;
+    while (ch.n_heavy < ch.n && cost[ch.n_heavy] >= 0.6 * cost[0]) ++ch.n_heavy;
   }
-  const dim3 grid((unsigned)p.H, (unsigned)p.B, (unsigned)ch.n);
+  if ((long long)ch.n * p.H * p.B > 0x7fffffffLL) return DFINE_E_UNSUPPORTED;
+  const dim3 grid((unsigned)(ch.n * p.H * p.B));
   cudaError_t e = cudaSuccess;
   // the opt-in shared-memory ceiling is raised once per instantiation (not per launch, so that
   // nothing but the launch itself happens under CUDA-graph capture)

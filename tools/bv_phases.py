@@ -59,7 +59,8 @@ def main():
     for chunk in sorted(set(buf[:, 5].tolist())):
         m = buf[:, 5] == chunk
         print(f"   chunk {chunk}: start->cleared {(t6[m, 0] - t[m, 0]).mean() / 1e3:.2f}, ->bulk issued {(t6[m, 1] - t[m, 0]).mean() / 1e3:.2f}, "
-              f"->first record done {(t6[m, 2] - t[m, 0]).mean() / 1e3:.2f}, ->lists built {(t[m, 1] - t[m, 0]).mean() / 1e3:.2f}")
+              f"->first record done {(t6[m, 2] - t[m, 0]).mean() / 1e3:.2f}, ->lists built {(t[m, 1] - t[m, 0]).mean() / 1e3:.2f}; "
+              f"walk: touched pixels {(buf[m, 9].astype(np.int64) - t[m, 2]).mean() / 1e3:.2f}, zero fill {(t[m, 3] - buf[m, 9].astype(np.int64)).mean() / 1e3:.2f}")
         print(f"chunk {chunk}: n={m.sum()} build {d[m, 0].mean():.2f} sort {d[m, 1].mean():.2f} walk {d[m, 2].mean():.2f} "
               f"total {(t[m, 3] - t[m, 0]).mean() / 1e3:.2f} us (max {(t[m, 3] - t[m, 0]).max() / 1e3:.2f})")
     # per-SM timeline: gaps between consecutive CTAs on the same SM
