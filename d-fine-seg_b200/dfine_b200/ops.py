@@ -245,7 +245,15 @@ def msda_backward_raw(memory, spec: LevelSpec, H: int, samp, attn, ref, pts_scal
             flags |= _lib.MSDA_GRAD_VALUE_BF16
         if force_atomic:
             flags |= _lib.MSDA_FORCE_ATOMIC
-        check(call(g_mem, flags), "dfine_msda_bwd")
+        rc = call(g_mem, flags)
+        if rc == _lib.E_UNSUPPORTED and g_mem.dtype == torch.bfloat16:
+            # shapes the gather path cannot take (sample lists larger than shared memory): this
+            # layer's gradient through the fp32 vector-reduction path, then one in-place add
+            part = torch.empty((B, spec.L, C), dtype=torch.float32, device=dev)
+            check(call(part, base_flags | _lib.MSDA_FORCE_ATOMIC), "dfine_msda_bwd")
+            g_mem.add_(part)
+            return g_mem, g_samp, g_attn
+        check(rc, "dfine_msda_bwd")
         return g_mem, g_samp, g_attn
     if gv_dtype == torch.bfloat16 and not force_atomic:
         g_mem = torch.empty((B, spec.L, C), dtype=torch.bfloat16, device=dev)

@@ -679,6 +679,48 @@ def test_shared_memory_gradient_hub(amp, dev):
     assert len(ops._HUBS) <= ops._MAX_HUBS
 
 
+def test_many_queries_fall_back_to_reductions(dev):
+    """More sampling points per (image, head, level) than the grad_value kernel can list in
+    shared memory (node ids are 16-bit): the library switches to fp32 vector reductions, the
+    shared bf16 gradient buffer of the hub still accumulates (one add), results unchanged."""
+    import dfine_b200
+    from dfine_b200 import ops
+    from oracle import torch_port as TP
+    torch.manual_seed(4)
+    B, Lq, H, c = 1, 2800, 8, 32
+    shapes, npts = [[12, 10], [6, 5]], [6, 6]          # 4 * 6 * 2800 = 67200 > 65535 nodes
+    spec = ops.level_spec(shapes, npts)
+    P = spec.P
+    ref = torch.cat([torch.rand(B, Lq, 2, device=dev), torch.rand(B, Lq, 2, device=dev) * 0.5 + 0.05], -1)
+    nps = torch.tensor([1.0 / n for n in npts for _ in range(n)], device=dev)
+    raws = [torch.randn(B, Lq, 3 * H * P, device=dev).to(torch.bfloat16) for _ in range(2)]
+    gos = [torch.randn(B, Lq, H * c, device=dev) for _ in range(2)]
+    mem0 = torch.randn(B, spec.L, H * c, device=dev).to(torch.bfloat16)
+
+    def run(share):
+        old = ops.share_memory_grad(share)
+        try:
+            mem = mem0.clone().requires_grad_(True)
+            value = TP.value_views(mem, H, shapes)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                outs = [dfine_b200.ops.msda_fused_packed(value, shapes, r, ref.unsqueeze(2), nps, npts) for r in raws]
+            torch.autograd.backward(outs, gos)
+            return outs[0].detach(), mem.grad.float()
+        finally:
+            ops.share_memory_grad(old)
+
+    (o1, g1), (o0, g0) = run(True), run(False)
+    assert torch.equal(o1, o0)
+    assert_close(g1.cpu().numpy(), g0.cpu().numpy(), BF16_RTOL, "grad_memory through the fallback")
+    m32 = mem0.float().requires_grad_(True)
+    want = sum((TP.msda_from_raw(r.float()[..., :2 * H * P].reshape(B, Lq, H, P, 2),
+                                 r.float()[..., 2 * H * P:].reshape(B, Lq, H, P), ref.unsqueeze(2),
+                                 TP.value_views(m32, H, shapes), shapes, nps, npts) * g).sum()
+               for r, g in zip(raws, gos))
+    want.backward()
+    assert_close(g1.cpu().numpy(), m32.grad.cpu().numpy(), BF16_RTOL, "grad_memory vs eager reference")
+
+
 def test_no_out_of_bounds_writes(dev):
     """compute-sanitizer is closed on this pool, so writes are checked with canaries: every
     output / workspace of the C-ABI calls sits between guard zones that must stay intact."""
