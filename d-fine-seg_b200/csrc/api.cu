@@ -20,7 +20,9 @@ void set_error(const char* fmt, ...) {
 
 int launch_fdr_project(const float*, const float*, float*, int, cudaStream_t);
 int launch_fdr(bool, const void*, int, const float*, const float*, const float*, float*, float*,
-               const float*, const float*, float*, long long, int, cudaStream_t);
+               const float*, const float*, void*, int, long long, int, cudaStream_t);
+int launch_pack_linear(const float*, const float*, int, const float*, const float*, int, int, void*, void*, int,
+                       cudaStream_t);
 int launch_mask_gemm(const void*, const void*, void*, int, int, int, int, int, int, cudaStream_t);
 int launch_colsum(const void*, int, long long, int, long long, float*, cudaStream_t);
 
@@ -357,6 +359,26 @@ int dfine_colsum(const void* x, int x_dtype, int64_t M, int N, int64_t row_strid
                                (cudaStream_t)stream), fn);
 }
 
+int dfine_pack_linear(const float* w0, const float* b0, int n0, const float* w1, const float* b1, int n1,
+                      int K, void* w, void* b, int out_dtype, void* stream) {
+  const char* fn = "dfine_pack_linear";
+  int rc;
+  if (n0 <= 0 || n1 <= 0 || K <= 0) {
+    set_error("%s: n0, n1, K must be positive (got %d, %d, %d)", fn, n0, n1, K);
+    return DFINE_E_SHAPE;
+  }
+  if (out_dtype != DFINE_F32 && out_dtype != DFINE_BF16) {
+    set_error("%s: out_dtype must be DFINE_F32 or DFINE_BF16", fn);
+    return DFINE_E_UNSUPPORTED;
+  }
+  const void* ptrs[6] = {w0, b0, w1, b1, w, b};
+  const char* names[6] = {"w0", "b0", "w1", "b1", "w", "b"};
+  for (int i = 0; i < 6; ++i)
+    if ((rc = require_device(ptrs[i], names[i], fn))) return rc;
+  return cuda_rc(launch_pack_linear(w0, b0, n0, w1, b1, n1, K, w, b, out_dtype == DFINE_BF16,
+                                    (cudaStream_t)stream), fn);
+}
+
 int dfine_fdr_project(const float* up, const float* reg_scale, float* project, int reg_max,
                       void* stream) {
   int rc;
@@ -405,16 +427,20 @@ int dfine_fdr_fwd(const void* corners, int c_dtype, const float* ref_init, const
     return DFINE_E_ALIGN;
   }
   return cuda_rc(launch_fdr(false, corners, c_dtype == DFINE_BF16, ref_init, project, reg_scale,
-                            dist, boxes, nullptr, nullptr, nullptr, N, reg_max,
+                            dist, boxes, nullptr, nullptr, nullptr, 0, N, reg_max,
                             (cudaStream_t)stream), fn);
 }
 
 int dfine_fdr_bwd(const void* corners, int c_dtype, const float* ref_init, const float* project,
                   const float* reg_scale, const float* grad_boxes, const float* grad_dist,
-                  float* grad_corners, int64_t N, int reg_max, void* stream) {
+                  void* grad_corners, int gc_dtype, int64_t N, int reg_max, void* stream) {
   const char* fn = "dfine_fdr_bwd";
   int rc = fdr_common(fn, corners, c_dtype, project, reg_scale, N, reg_max);
   if (rc || N == 0) return rc;
+  if (gc_dtype != DFINE_F32 && gc_dtype != DFINE_BF16) {
+    set_error("%s: gc_dtype must be DFINE_F32 or DFINE_BF16", fn);
+    return DFINE_E_UNSUPPORTED;
+  }
   if ((rc = require_device(grad_corners, "grad_corners", fn))) return rc;
   if (!grad_boxes && !grad_dist) {
     set_error("%s: at least one of grad_boxes / grad_dist must be given", fn);
@@ -427,8 +453,8 @@ int dfine_fdr_bwd(const void* corners, int c_dtype, const float* ref_init, const
     return DFINE_E_ALIGN;
   }
   return cuda_rc(launch_fdr(true, corners, c_dtype == DFINE_BF16, ref_init, project, reg_scale,
-                            nullptr, nullptr, grad_boxes, grad_dist, grad_corners, N, reg_max,
-                            (cudaStream_t)stream), fn);
+                            nullptr, nullptr, grad_boxes, grad_dist, grad_corners,
+                            gc_dtype == DFINE_BF16, N, reg_max, (cudaStream_t)stream), fn);
 }
 
 int dfine_mask_gemm_fwd(const void* coef, const void* proto, void* out, int B, int M, int K,

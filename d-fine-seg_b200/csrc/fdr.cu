@@ -41,7 +41,7 @@ fdr_kernel(const void* __restrict__ corners, int c_bf16, const float* __restrict
            const float* __restrict__ project, const float* __restrict__ reg_scale,
            float* __restrict__ dist, float* __restrict__ boxes,
            const float* __restrict__ grad_boxes, const float* __restrict__ grad_dist,
-           float* __restrict__ grad_corners, long long N, int nb) {
+           void* __restrict__ grad_corners, int gc_bf16, long long N, int nb) {
   const int lane = threadIdx.x & 31;
   const long long i = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= N) return;
@@ -94,7 +94,11 @@ fdr_kernel(const void* __restrict__ corners, int c_bf16, const float* __restrict
 #pragma unroll
     for (int t = 0; t < kBinsPerLane; ++t) {
       const int k = l8 + 8 * t;
-      if (k < nb) grad_corners[row + k] = gd * x[t] * (w[t] - d);
+      if (k < nb) {
+        const float g = gd * x[t] * (w[t] - d);
+        if (gc_bf16) reinterpret_cast<__nv_bfloat16*>(grad_corners)[row + k] = __float2bfloat16_rn(g);
+        else reinterpret_cast<float*>(grad_corners)[row + k] = g;
+      }
     }
   } else {
     const float d0 = __shfl_sync(0xffffffffu, d, 0), d1 = __shfl_sync(0xffffffffu, d, 8);
@@ -123,8 +127,8 @@ int launch_fdr_project(const float* up, const float* reg_scale, float* project, 
 
 int launch_fdr(bool backward, const void* corners, int c_bf16, const float* ref_init,
                const float* project, const float* reg_scale, float* dist, float* boxes,
-               const float* grad_boxes, const float* grad_dist, float* grad_corners, long long N,
-               int reg_max, cudaStream_t s) {
+               const float* grad_boxes, const float* grad_dist, void* grad_corners, int gc_bf16,
+               long long N, int reg_max, cudaStream_t s) {
   const int nb = reg_max + 1;
   const long long ctas = (N + 7) / 8;
   if (ctas == 0) return 0;
@@ -135,7 +139,7 @@ int launch_fdr(bool backward, const void* corners, int c_bf16, const float* ref_
 #define DFINE_FDR_LAUNCH(BPL, BWD)                                                             \
   fdr_kernel<BPL, BWD><<<(unsigned)ctas, 256, 0, s>>>(corners, c_bf16, ref_init, project,      \
                                                       reg_scale, dist, boxes, grad_boxes,      \
-                                                      grad_dist, grad_corners, N, nb)
+                                                      grad_dist, grad_corners, gc_bf16, N, nb)
   if (nb <= 40) {  // reg_max = 32: five bins per lane
     if (backward) DFINE_FDR_LAUNCH(5, true); else DFINE_FDR_LAUNCH(5, false);
   } else if (nb <= 128) {

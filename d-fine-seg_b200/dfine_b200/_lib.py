@@ -44,7 +44,9 @@ _SIGNATURES = {
     "dfine_fdr_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_int64, c_int, c_void_p]),
     "dfine_fdr_bwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                              c_void_p, c_int64, c_int, c_void_p]),
+                              c_void_p, c_int, c_int64, c_int, c_void_p]),
+    "dfine_pack_linear": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p,
+                                  c_void_p, c_int, c_void_p]),
     "dfine_mask_gemm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                     c_int, c_int, c_void_p]),
 }

@@ -38,7 +38,10 @@ def _fused_forward(self, query: torch.Tensor, reference_points: torch.Tensor, va
         # ONE concatenated Linear (N = 3*H*P) instead of two; its output feeds the kernel
         # through row strides, its gradient is written by the backward kernel in one piece
         so, aw = self.sampling_offsets, self.attention_weights
-        raw = ops.fused_linear(query, torch.cat([so.weight, aw.weight], 0), torch.cat([so.bias, aw.bias], 0))
+        if ops.packed_linear_supported(query, so.weight, so.bias, aw.weight, aw.bias):
+            raw = ops.packed_linear(query, so.weight, so.bias, aw.weight, aw.bias)
+        else:   # parameters in another dtype / layout: concatenate with torch
+            raw = ops.fused_linear(query, torch.cat([so.weight, aw.weight], 0), torch.cat([so.bias, aw.bias], 0))
         return ops.msda_fused_packed(value, value_spatial_shapes, raw, reference_points,
                                      self.num_points_scale, self.num_points_list, self.offset_scale)
     if last == 2:

@@ -475,6 +475,54 @@ class _LinearFn(torch.autograd.Function):
         return gx, gw, gb
 
 
+class _PackedLinearFn(torch.autograd.Function):
+    """The two Linears of MSDeformableAttention as ONE GEMM: y = x [W0; W1]^T + [b0; b1].  The
+    parameters stay separate tensors (state-dict compatible); they are concatenated and cast to
+    the compute dtype by one kernel (dfine_pack_linear), the GEMMs are cuBLAS, the bias gradient
+    is dfine_colsum, and the parameter gradients are returned as views of one [N0+N1, K] GEMM
+    result."""
+
+    @staticmethod
+    def forward(ctx, x, w0, b0, w1, b1):
+        cdt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x.dtype
+        if cdt not in _DT:
+            cdt = torch.float32
+        n0, n1, K = w0.shape[0], w1.shape[0], w0.shape[1]
+        w = torch.empty((n0 + n1, K), dtype=cdt, device=x.device)
+        b = torch.empty((n0 + n1,), dtype=cdt, device=x.device)
+        with torch.cuda.device_of(x), _timed("pack_linear", x):
+            rc = _lib.lib().dfine_pack_linear(w0.data_ptr(), b0.data_ptr(), n0, w1.data_ptr(), b1.data_ptr(),
+                                              n1, K, w.data_ptr(), b.data_ptr(), _DT[cdt], _stream(x))
+        check(rc, "dfine_pack_linear")
+        x2 = x.reshape(-1, x.shape[-1]).to(cdt)
+        y = torch.nn.functional.linear(x2, w, b)
+        ctx.save_for_backward(x2, w)
+        ctx.x_shape, ctx.x_dtype, ctx.n0 = x.shape, x.dtype, n0
+        return y.reshape(*x.shape[:-1], n0 + n1)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        x2, w = ctx.saved_tensors
+        g2 = g.reshape(-1, g.shape[-1])
+        if g2.dtype != w.dtype:
+            g2 = g2.to(w.dtype)
+        gx = _mm(g2, w, ctx.x_dtype).reshape(ctx.x_shape)
+        gw = _mm(g2.t(), x2, torch.float32)
+        gb = colsum(g2) if colsum_supported(g2) else g2.float().sum(0)
+        n0 = ctx.n0
+        return gx, gw[:n0], gb[:n0], gw[n0:], gb[n0:]
+
+
+def packed_linear_supported(x, w0, b0, w1, b1) -> bool:
+    return all(t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() for t in (w0, b0, w1, b1)) \
+        and x.is_cuda and w0.shape[1] == w1.shape[1]
+
+
+def packed_linear(x, w0, b0, w1, b1):
+    return _PackedLinearFn.apply(x, w0, b0, w1, b1)
+
+
 def colsum_supported(x: torch.Tensor) -> bool:
     return (x.dim() == 2 and x.stride(1) == 1 and x.dtype in _DT and x.shape[1] % 2 == 0
             and x.shape[1] <= 1024 and x.stride(0) % 2 == 0 and x.data_ptr() % 8 == 0)
@@ -628,16 +676,16 @@ class _FdrFn(torch.autograd.Function):
         N = corners.numel() // (4 * (ctx.reg_max + 1))
         gd = g_dist.float().contiguous() if g_dist is not None else None
         gb = g_boxes.float().contiguous() if g_boxes is not None else None
-        gc = torch.empty(corners.shape, dtype=torch.float32, device=corners.device)
+        gc = torch.empty_like(corners)    # written directly in the corners' dtype
         if gd is None and gb is None:
-            return gc.zero_().to(corners.dtype), None, None, None, None, None, None
+            return gc.zero_(), None, None, None, None, None, None
         with torch.cuda.device_of(corners), _timed("fdr_bwd", corners):
             rc = _lib.lib().dfine_fdr_bwd(corners.data_ptr(), _dt(corners, "corners"),
                                           _ptr(ref_init), project.data_ptr(), reg_scale.data_ptr(),
-                                          _ptr(gb), _ptr(gd), gc.data_ptr(), N, ctx.reg_max,
-                                          _stream(corners))
+                                          _ptr(gb), _ptr(gd), gc.data_ptr(), _dt(gc, "grad_corners"), N,
+                                          ctx.reg_max, _stream(corners))
         check(rc, "dfine_fdr_bwd")
-        return gc.to(corners.dtype), None, None, None, None, None, None
+        return gc, None, None, None, None, None, None
 
 
 def _fdr_prepare(corners, project, reg_scale, reg_max):

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DFINE_B200_VERSION 100 /* major*100 + minor */
+#define DFINE_B200_VERSION 101 /* major*100 + minor */
 
 #if defined(__GNUC__)
 #define DFINE_API __attribute__((visibility("default")))
@@ -163,6 +163,12 @@ DFINE_API int dfine_cast_f32_to_bf16(const float* src, void* dst, int64_t n, voi
 DFINE_API int dfine_colsum(const void* x, int x_dtype, int64_t M, int N, int64_t row_stride, float* out,
                  void* stream);
 
+/* Parameters of the concatenated Linear in one launch: w = [w0; w1] ([n0+n1, K]) and
+ * b = [b0; b1], float32 in, out_dtype out (bf16 under autocast).  w0/b0 = sampling_offsets,
+ * w1/b1 = attention_weights (dfine_decoder.py:80-81); replaces 2 x torch.cat + 2 x cast. */
+DFINE_API int dfine_pack_linear(const float* w0, const float* b0, int n0, const float* w1, const float* b1, int n1,
+                      int K, void* w, void* b, int out_dtype, void* stream);
+
 /* --------------------------------------------------------------------------
  * K3  FDR: weighting function, Integral and distance2bbox.
  *
@@ -182,7 +188,7 @@ DFINE_API int dfine_colsum(const void* x, int x_dtype, int64_t M, int N, int64_t
  * dfine_fdr_bwd       gradient w.r.t. corners only (ref_init is detached,
  *                     up / reg_scale have requires_grad=False, dfine_decoder.py:597-598)
  *   grad_boxes float32 [N,4] or NULL;  grad_dist float32 [N,4] or NULL (added)
- *   grad_corners float32 [N, 4*(reg_max+1)]
+ *   grad_corners gc_dtype [N, 4*(reg_max+1)]  (bf16 under AMP: no separate cast pass)
  * -------------------------------------------------------------------------- */
 DFINE_API int dfine_fdr_project(const float* up, const float* reg_scale, float* project, int reg_max,
                       void* stream);
@@ -191,7 +197,7 @@ DFINE_API int dfine_fdr_fwd(const void* corners, int c_dtype, const float* ref_i
                   void* stream);
 DFINE_API int dfine_fdr_bwd(const void* corners, int c_dtype, const float* ref_init, const float* project,
                   const float* reg_scale, const float* grad_boxes, const float* grad_dist,
-                  float* grad_corners, int64_t N, int reg_max, void* stream);
+                  void* grad_corners, int gc_dtype, int64_t N, int reg_max, void* stream);
 
 /* --------------------------------------------------------------------------
  * K4  mask assembly: prototype x coefficient contraction on tcgen05 tensor cores.

@@ -409,6 +409,36 @@ def test_mask_gemm(dev):
     assert a.grad.shape == a.shape and b.grad.shape == b.shape
 
 
+def test_packed_linear_matches_two_linears(dev):
+    """dfine_pack_linear + one GEMM against the reference's two nn.Linear calls (fp32 and
+    bf16 autocast): outputs and all five gradients."""
+    import dfine_b200.ops as ops
+    torch.manual_seed(9)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    B, Lq, C, n0, n1 = 3, 70, 256, 192, 96
+    x0 = torch.randn(B, Lq, C, device=dev)
+    ws = [torch.randn(n0, C, device=dev) * 0.05, torch.randn(n0, device=dev) * 0.1,
+          torch.randn(n1, C, device=dev) * 0.05, torch.randn(n1, device=dev) * 0.1]
+    g = torch.randn(B, Lq, n0 + n1, device=dev)
+    for amp in (False, True):
+        def run(ours):
+            x = x0.clone().requires_grad_(True)
+            p = [w.clone().requires_grad_(True) for w in ws]
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+                if ours:
+                    y = ops.packed_linear(x, *p)
+                else:
+                    y = torch.cat([torch.nn.functional.linear(x, p[0], p[1]),
+                                   torch.nn.functional.linear(x, p[2], p[3])], -1)
+            y.float().backward(g)
+            return [y.detach().float(), x.grad] + [t.grad for t in p]
+        got, want = run(True), run(False)
+        tol = 2e-2 if amp else 2e-5
+        for a, b, n in zip(got, want, ["y", "gx", "gw0", "gb0", "gw1", "gb1"]):
+            assert a.shape == b.shape
+            assert rel_err(a.cpu().numpy(), b.float().cpu().numpy()) <= tol, (n, amp)
+
+
 def test_colsum(dev):
     """dfine_colsum (bias gradient of the concatenated Linear) against a float64 sum."""
     import dfine_b200.ops as ops
@@ -785,7 +815,7 @@ def test_no_out_of_bounds_writes(dev):
                                  None, boxes.data_ptr(), N, 32, s), "fdr_fwd")
     gb = torch.randn(N, 4, device=dev)
     _lib.check(lib.dfine_fdr_bwd(corners.data_ptr(), _lib.F32, refi.data_ptr(), proj.data_ptr(), rsd.data_ptr(),
-                                 gb.data_ptr(), None, gc.data_ptr(), N, 32, s), "fdr_bwd")
+                                 gb.data_ptr(), None, gc.data_ptr(), _lib.F32, N, 32, s), "fdr_bwd")
     Bm, M, K, Nn = 2, 77, 64, 264
     a = torch.randn(Bm, M, K, device=dev).to(torch.bfloat16)
     bmat = torch.randn(Bm, K, Nn, device=dev).to(torch.bfloat16)

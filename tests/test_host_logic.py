@@ -25,7 +25,8 @@ def test_cabi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/dfine_b200.h but not exported"
     assert sorted(declared) == dfine_b200._lib.exported_symbols()
-    assert dfine_b200._lib.lib().dfine_version() == 100
+    m = re.search(r"#define DFINE_B200_VERSION (\d+)", header)
+    assert dfine_b200._lib.lib().dfine_version() == int(m.group(1)) >= 101
 
 
 def test_argument_validation_without_gpu():
