@@ -308,6 +308,71 @@ def kernel_leg(wl: dict, hp: "HotPath", device, reps: int = 20):
     return out
 
 
+def secondary_kernel_legs(device, peak: float, reps: int = 10):
+    """Kernel-level numbers at the other BASELINE.json configs (they are parity-test cases, not
+    the bench line): config 2 (D-FINE-s inference, B=64, Lq=300: forward only), config 5
+    (1024x1024, B=8, Lq=500, 3 levels x 4 points: forward + backward) and the config-4 mask
+    assembly (16 x 500 x 256 x 160^2, bf16 out).  Same back-to-back timing as kernel_leg."""
+    from dfine_b200 import ops
+    H, c = 8, 32
+    out = {}
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(device)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(reps):
+            fn()
+        e.record()
+        torch.cuda.synchronize(device)
+        return s.elapsed_time(e) / reps
+
+    cfgs = {
+        "config2_dfine_s_infer_b64": dict(B=64, Lq=300, shapes=[[80, 80], [40, 40], [20, 20]], npts=[3, 6, 3], bwd=False),
+        "config5_dfine_x_1024_b8": dict(B=8, Lq=500, shapes=[[128, 128], [64, 64], [32, 32]], npts=[4, 4, 4], bwd=True),
+    }
+    g = torch.Generator(device=device).manual_seed(7)
+    for name, cf in cfgs.items():
+        B, Lq = cf["B"], cf["Lq"]
+        spec = ops.level_spec(cf["shapes"], cf["npts"])
+        P = spec.P
+        mem = torch.randn(B, spec.L, H * c, device=device, generator=g).to(torch.bfloat16)
+        ref = torch.cat([torch.rand(B, Lq, 2, device=device, generator=g) * 0.9 + 0.05,
+                         torch.exp(torch.rand(B, Lq, 2, device=device, generator=g) * 3.4 - 3.9)], -1)
+        raw = torch.randn(B, Lq, 3 * H * P, device=device, generator=g).to(torch.bfloat16)
+        attn_view = raw.reshape(-1)[2 * H * P:]
+        rs = raw.shape[-1]
+        nps = torch.tensor([1.0 / n for n in cf["npts"] for _ in range(n)], device=device)
+        rec = ops.new_records(mem, spec, H, Lq) if cf["bwd"] else None
+        blc, smp, bqc = mem.numel(), B * Lq * H * P, B * Lq * H * c
+        fwd_bytes = blc * 2 + smp * 12 + bqc * 4
+        res = {}
+        ms = timed(lambda: ops.msda_forward_raw(mem, spec, H, raw, attn_view, ref, nps, 0.5, True, torch.float32,
+                                                samp_rs=rs, attn_rs=rs, records=rec))
+        res["msda_fwd"] = {"ms": ms, "algorithmic_bytes": fwd_bytes, "frac": fwd_bytes / (ms / 1e3) / 1e9 / peak}
+        if cf["bwd"]:
+            go = torch.randn(B, Lq, H * c, device=device, generator=g)
+            g_raw = torch.empty_like(raw)
+            bwd_bytes = bqc * 4 + blc * 2 + smp * 12 + blc * 2 + smp * 12
+            ms = timed(lambda: ops.msda_backward_raw(mem, spec, H, raw, attn_view, ref, nps, 0.5, True, go,
+                                                     gv_dtype=mem.dtype, samp_rs=rs, attn_rs=rs, grad_raw=g_raw,
+                                                     records=rec))
+            res["msda_bwd"] = {"ms": ms, "algorithmic_bytes": bwd_bytes, "frac": bwd_bytes / (ms / 1e3) / 1e9 / peak}
+        out[name] = res
+        del mem, raw
+    Bm, M, K, N = 16, 500, 256, 160 * 160
+    coef = torch.randn(Bm, M, K, device=device, generator=g).to(torch.bfloat16)
+    proto = torch.randn(Bm, K, N, device=device, generator=g).to(torch.bfloat16)
+    ms = timed(lambda: ops.mask_gemm_raw(coef, proto, torch.bfloat16, False))
+    mbytes = Bm * (M * K * 2 + K * N * 2 + M * N * 2)
+    out["config4_mask_assembly_bf16"] = {"mask_gemm_fwd": {
+        "ms": ms, "algorithmic_bytes": mbytes, "frac": mbytes / (ms / 1e3) / 1e9 / peak,
+        "tflops": 2.0 * Bm * M * K * N / (ms / 1e3) / 1e12}}
+    return out
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
 
@@ -482,6 +547,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=4, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager", action="store_true", help="skip the eager-PyTorch GPU bar")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="skip the kernel-level legs at the other BASELINE configs")
     ap.add_argument("--launch-list", action="store_true",
                     help="profiling aid: run W+K eager steps of the B200 path and exit (for an ncu launch list)")
     args = ap.parse_args()
@@ -545,6 +612,12 @@ def main():
     # ---- kernel leg: each kernel of a layer launched back to back (device-bound timing) ----
     kms = kernel_leg(wl, hp, device)
     clocks = sampler.stop() if sampler else None
+    other = None
+    if rank == 0 and world == 1 and not args.no_secondary:
+        try:
+            other = secondary_kernel_legs(device, load_peaks()[0])
+        except Exception as exc:  # noqa: BLE001  (informational legs must not take the bench line down)
+            other = {"error": str(exc)[:200]}
 
     value = job_throughput(wl["B"], world, args.steps, ms)
     e2e = job_throughput(wl["B"], world, args.steps, ms_e2e)
@@ -603,6 +676,8 @@ def main():
                 "serial_ms_per_step": ms_e2e_serial / args.steps},
         "gpu_launches": launches, "roofline": roofline, "clocks": clocks,
     }
+    if other is not None:
+        out["other_configs_kernel_level"] = other
 
     if world == 1 and not args.no_eager:
         # informational: the reference's eager PyTorch path on the same GPU (fp32 restatement

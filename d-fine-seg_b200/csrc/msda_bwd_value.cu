@@ -24,7 +24,6 @@
 // autograd's accumulation of the per-layer `memory` gradients.
 // The summation order inside a pixel follows the exchange order (like the reference's
 // atomics, results are reproducible up to fp32 rounding only).
-#include <cstdlib>
 #include <cstring>
 #include <utility>
 
@@ -229,9 +228,7 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
           // [corner][sample] numbering: the lanes of a warp store consecutive 8-byte nodes
           const uint32_t node = (uint32_t)(j * nsamp + t) + 1u;
           const uint32_t prev = atomicExch(&s_head[px], node);
-#ifndef DFINE_BV_NOSORT
           atomicAdd(&s_cnt[px], 1u);
-#endif
           s_node[node] = make_uint2(prev | qbits, __float_as_uint(wt[j] * a));
         }
       }
@@ -256,9 +253,6 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
   __syncthreads();
   BV_STAMP(1);
 
-#ifdef DFINE_BV_NOSORT
-  const int n_touched = npx;
-#else
   // S2: counting sort of the pixels by corner count, descending
   for (int i = tid; i < npx; i += kBvThreads) atomicAdd(&s_bin[min(s_cnt[i], (uint32_t)(kBvBins - 1))], 1u);
   __syncthreads();
@@ -290,7 +284,6 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
     base = __shfl_sync(0xffffffffu, base, leader);
     if (i < npx) s_order[base + __popc(peers & ((1u << (tid & 31)) - 1u))] = (unsigned short)i;
   }
-#endif
   if (kStage) tma::mbar_wait(mbar, 0);  // grad_out rows have landed
   __syncthreads();
   BV_STAMP(2);
@@ -314,25 +307,14 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
   const uint32_t nodes = static_cast<uint32_t>(__cvta_generic_to_shared(s_node));
 
   // accumulate mode: untouched pixels (the tail of the order) keep their running gradient
-#ifdef DFINE_BV_NOSORT
-  const int n_walk = npx;
-#else
   const int n_walk = n_touched;  // the untouched tail of the order is zero-filled below
-#endif
   for (int k = worker; k < n_walk; k += NWORK) {
-#ifdef DFINE_BV_NOSORT
-    const int px = k;
-#else
     const int px = s_order[k];
-#endif
     uint32_t n = s_head[px];
     char* o = gvb + (uint32_t)px * gv_row;
     float acc[VPL];
 #pragma unroll
     for (int i = 0; i < VPL; ++i) acc[i] = 0.f;
-#ifdef DFINE_BV_NOSORT
-    if (kAccum && n == 0u) continue;
-#endif
     uint2 nd = lds_u2(nodes + 8u * n);
     while (n != 0u) {
       const uint32_t q = nd.x >> kBvNodeBits;
@@ -389,7 +371,6 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
   __syncthreads();
   BV_STAMP(9);
 #endif
-#ifndef DFINE_BV_NOSORT
   if (!kAccum) {
     // pixels no sample touched (the tail of the order): explicit zeros, 16 bytes per thread --
     // this replaces the memset pass of the scatter formulation
@@ -402,7 +383,6 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
       *reinterpret_cast<uint4*>(gz + (uint32_t)px * gv_row + (i % kRowChunks) * 16) = make_uint4(0u, 0u, 0u, 0u);
     }
   }
-#endif
 #ifdef DFINE_BV_PROF
   __syncthreads();
   BV_STAMP(3);
@@ -426,14 +406,11 @@ int launch_msda_bwd_value(const MsdaParams& p, void* grad_value, int gv_bf16, in
                           cudaStream_t s) {
   if (p.Lq >= (1 << (32 - kBvNodeBits)) || p.B > 65535 || p.H > 65535 || !p.rec) return DFINE_E_UNSUPPORTED;
   if (p.c != 16 && p.c != 32 && p.c != 64) return DFINE_E_UNSUPPORTED;
-  // pixels per chunk: the largest power-of-two fraction of 8192 (DFINE_BV_CHUNK_PX overrides the
-  // start, for experiments) whose lists fit shared memory TOGETHER with the staged grad_out
-  // rows; if none does, the largest that fits without staging (rows then come through L1)
-  static const int chunk_px0 = [] {
-    const char* e = getenv("DFINE_BV_CHUNK_PX");
-    const int v = e ? atoi(e) : 0;
-    return v >= 64 && v <= 16384 ? v : 8192;  // <= 65535: sorted pixel ids are 16-bit
-  }();
+  // pixels per chunk: the largest power-of-two fraction of 8192 (sorted pixel ids are 16-bit)
+  // whose lists fit shared memory TOGETHER with the staged grad_out rows; if none does, the
+  // largest that fits without staging (rows then come through L1).  Measured at config 3:
+  // 4096 (1024 CTAs) 91.7 us, 2200 (1280) 100 us, 800 (2816) 151 us, 8192 (768) 82 us.
+  constexpr int chunk_px0 = 8192;
   // grad_out[b, :, h, :] arrives as go_loads TMA boxes of go_rows (<= 256) query rows each
   // (a multiple of 4 rows keeps every box's shared-memory destination 128-byte aligned)
   const int go_loads = (p.Lq + 255) / 256, go_rows = (((p.Lq + go_loads - 1) / go_loads) + 3) & ~3;
@@ -541,17 +518,13 @@ int launch_msda_bwd_value(const MsdaParams& p, void* grad_value, int gv_bf16, in
     if (stage) DFINE_BV_LAUNCH3(C, GT, V, true); else DFINE_BV_LAUNCH3(C, GT, V, false);         \
   } while (0)
   // channels per lane: 8 (4 lanes per row at c = 32), 4 for the narrow head
-  static const int vpl_pref = [] {
-    const char* e2 = getenv("DFINE_BV_VPL");
-    return e2 ? atoi(e2) : 8;
-  }();
   if (p.go_bf16) {
     if (p.c == 16) DFINE_BV_LAUNCH(16, __nv_bfloat16, 4);
-    else if (p.c == 32) { if (vpl_pref == 4) DFINE_BV_LAUNCH(32, __nv_bfloat16, 4); else DFINE_BV_LAUNCH(32, __nv_bfloat16, 8); }
+    else if (p.c == 32) DFINE_BV_LAUNCH(32, __nv_bfloat16, 8);
     else DFINE_BV_LAUNCH(64, __nv_bfloat16, 8);
   } else {
     if (p.c == 16) DFINE_BV_LAUNCH(16, float, 4);
-    else if (p.c == 32) { if (vpl_pref == 4) DFINE_BV_LAUNCH(32, float, 4); else DFINE_BV_LAUNCH(32, float, 8); }
+    else if (p.c == 32) DFINE_BV_LAUNCH(32, float, 8);
     else DFINE_BV_LAUNCH(64, float, 8);
   }
 #undef DFINE_BV_LAUNCH
