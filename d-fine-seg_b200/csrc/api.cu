@@ -240,10 +240,16 @@ int dfine_msda_bwd(const void* value, int64_t v_stride_b, int64_t v_stride_l,
                      lvl_npts, n_lvl, samp, attn, ref_boxes, pts_scale, offset_scale, B, Lq, H, c,
                      value_dtype, samp_dtype, flags, samp_row_stride, attn_row_stride);
   if (rc) return rc;
+  const bool dots_only = (flags & DFINE_MSDA_BWD_DOTS_ONLY) != 0;
+  const bool value_only = (flags & DFINE_MSDA_BWD_VALUE_ONLY) != 0;
+  if (dots_only && value_only) {
+    set_error("dfine_msda_bwd: DFINE_MSDA_BWD_DOTS_ONLY and DFINE_MSDA_BWD_VALUE_ONLY exclude each other");
+    return DFINE_E_UNSUPPORTED;
+  }
   if ((rc = require_device(grad_out, "grad_out", "dfine_msda_bwd"))) return rc;
-  if ((rc = require_device(grad_value, "grad_value", "dfine_msda_bwd"))) return rc;
-  if ((rc = require_device(grad_samp, "grad_samp", "dfine_msda_bwd"))) return rc;
-  if ((rc = require_device(grad_attn, "grad_attn", "dfine_msda_bwd"))) return rc;
+  if (!dots_only && (rc = require_device(grad_value, "grad_value", "dfine_msda_bwd"))) return rc;
+  if (!value_only && (rc = require_device(grad_samp, "grad_samp", "dfine_msda_bwd"))) return rc;
+  if (!value_only && (rc = require_device(grad_attn, "grad_attn", "dfine_msda_bwd"))) return rc;
   if (go_dtype != DFINE_F32 && go_dtype != DFINE_BF16) {
     set_error("dfine_msda_bwd: go_dtype must be DFINE_F32 or DFINE_BF16");
     return DFINE_E_UNSUPPORTED;
@@ -285,16 +291,26 @@ int dfine_msda_bwd(const void* value, int64_t v_stride_b, int64_t v_stride_l,
     }
     p.rec = reinterpret_cast<uint4*>(workspace);
     p.rec_valid = (flags & DFINE_MSDA_RECORDS_VALID) ? 1 : 0;
+    if (value_only && !p.rec_valid) {
+      set_error("dfine_msda_bwd: DFINE_MSDA_BWD_VALUE_ONLY needs the forward's records (DFINE_MSDA_RECORDS_VALID)");
+      return DFINE_E_UNSUPPORTED;
+    }
     // shape check first: nothing is launched if the gather path cannot take this shape
-    rc = launch_msda_bwd_value(p, nullptr, gv_bf16, accumulate, s);
+    rc = dots_only ? 0 : launch_msda_bwd_value(p, nullptr, gv_bf16, accumulate, s);
     if (rc == 0) {
-      if ((rc = launch_msda_bwd(p, value_dtype, /*scatter=*/false, s)))
+      if (!value_only && (rc = launch_msda_bwd(p, value_dtype, /*scatter=*/false, s)))
         return cuda_rc(rc, "dfine_msda_bwd");
+      if (dots_only) return 0;
       return cuda_rc(launch_msda_bwd_value(p, grad_value, gv_bf16, accumulate, s), "dfine_msda_bwd(value)");
     }
     if (rc != DFINE_E_UNSUPPORTED) return cuda_rc(rc, "dfine_msda_bwd(value)");
     p.rec = nullptr;
     p.rec_valid = 0;
+  }
+  if (dots_only || value_only) {
+    set_error("dfine_msda_bwd: the split backward needs the gather path (workspace with the forward's "
+              "records, a shape whose sample lists fit shared memory)");
+    return DFINE_E_UNSUPPORTED;
   }
   if (gv_bf16) {
     set_error("dfine_msda_bwd: a bf16 grad_value needs the gather path (workspace of "

@@ -20,6 +20,8 @@ MSDA_GRAD_SAMP_BF16 = 8
 MSDA_RECORDS_VALID = 16
 MSDA_GRAD_VALUE_ACCUMULATE = 32
 MSDA_TILED = 64
+MSDA_BWD_DOTS_ONLY = 128
+MSDA_BWD_VALUE_ONLY = 256
 E_NULL, E_SHAPE, E_UNSUPPORTED, E_ALIGN = -1, -2, -3, -4
 
 _I32P = ctypes.POINTER(c_int32)

@@ -54,6 +54,11 @@ extern "C" {
 #define DFINE_MSDA_FORCE_ATOMIC 4    /* bwd: force the fp32 vector-reduction fallback */
 #define DFINE_MSDA_GRAD_SAMP_BF16 8  /* bwd: grad_samp / grad_attn are bf16 buffers */
 #define DFINE_MSDA_RECORDS_VALID 16  /* bwd: workspace holds the records dfine_msda_fwd wrote */
+#define DFINE_MSDA_BWD_DOTS_ONLY 128  /* bwd: only grad_samp / grad_attn (grad_value may be NULL) */
+#define DFINE_MSDA_BWD_VALUE_ONLY 256 /* bwd: only grad_value, from the records of the forward
+                                         (needs DFINE_MSDA_RECORDS_VALID; grad_samp / grad_attn may
+                                         be NULL).  The two halves of the backward share no output:
+                                         a caller can run them on two streams (ops.py does) */
 #define DFINE_MSDA_TILED 64          /* fwd: persistent CTAs, small pyramid levels staged in shared
                                        memory by TMA (measured slower than the default kernel at
                                        D-FINE shapes; kept selectable) */

@@ -656,8 +656,9 @@ def test_decoder_loop_integration(dev):
     assert rel_err(got[2].cpu().numpy(), want[2].cpu().numpy()) <= 2e-5
 
 
+@pytest.mark.parametrize("overlap", [False, True], ids=["one_stream", "two_streams"])
 @pytest.mark.parametrize("amp", [False, True], ids=["fp32", "amp_bf16"])
-def test_shared_memory_gradient_hub(amp, dev):
+def test_shared_memory_gradient_hub(amp, overlap, dev):
     """All layers sample one `memory`; their grad_value kernels accumulate into ONE buffer that
     a hub node hands to autograd once (ops.share_memory_grad).  Must equal autograd's own
     per-layer accumulation -- also when a layer is left out of the loss and for a second
@@ -683,6 +684,7 @@ def test_shared_memory_gradient_hub(amp, dev):
 
     def run(share, used, twice=False):
         old = ops.share_memory_grad(share)
+        old_ov = ops.overlap_grad_value(overlap and share)
         try:
             leaf = enc.clone().requires_grad_(True)
             with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
@@ -697,6 +699,7 @@ def test_shared_memory_gradient_hub(amp, dev):
             return leaf.grad.clone()
         finally:
             ops.share_memory_grad(old)
+            ops.overlap_grad_value(old_ov)
 
     tol = BF16_RTOL if amp else FP32_RTOL
     for used in ([True] * 4, [True, False, True, True], [False, False, True, False]):
