@@ -64,6 +64,14 @@ inline EncodeTiledFn encode_fn() {
 inline int encode_3d_plain(CUtensorMap* map, bool bf16, const void* base, uint64_t d0, uint64_t d1,
                            uint64_t d2, uint64_t s1, uint64_t s2, uint32_t b0, uint32_t b1,
                            const char* what) {
+  // cuTensorMapEncodeTiled is a DRIVER call: it needs the primary context current on this thread.
+  // PyTorch's autograd threads may never have made a runtime call that binds it (201 =
+  // CUDA_ERROR_INVALID_CONTEXT otherwise); cudaSetDevice on the current device does, is legal
+  // under stream capture and costs nothing once bound.
+  {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaSetDevice(dev);
+  }
   EncodeTiledFn enc = encode_fn();
   if (!enc) {
     set_error("%s: cuTensorMapEncodeTiled is not available from the CUDA driver", what);
