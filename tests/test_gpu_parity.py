@@ -754,6 +754,111 @@ def test_many_queries_fall_back_to_reductions(dev):
     assert_close(g1.cpu().numpy(), m32.grad.cpu().numpy(), BF16_RTOL, "grad_memory vs eager reference")
 
 
+def test_detection_f1_and_mask_iou_unchanged(dev):
+    """North-star criterion: "detection F1 / mask IoU must be unchanged on a fixed synthetic set".
+    A small detector is assembled from the hot path -- `memory` -> value_op views -> 3 chained
+    cross-attention layers -> class head, FDR box decode, mask-prototype contraction -- and run
+    on a fixed synthetic set (8 images x 10 ground-truth rectangles, planted so that the
+    detector finds most of them) once through the reference call sequence (oracle/torch_port.py,
+    eager PyTorch) and once through the CUDA path, both under bf16 autocast.  The reference's
+    metric (restated in oracle/det_metrics.py: top-300 postprocess, greedy IoU matching, F1,
+    mask IoU) must come out identical, and the pre-threshold top-300 lists must agree."""
+    import dfine_b200
+    from oracle import det_metrics as DM
+    from oracle import torch_port as TP
+    torch.manual_seed(123)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    B, Q, C, H, NC, n_gt = 8, 300, 256, 8, 80, 10
+    shapes, npts, n_layers = [[40, 40], [20, 20], [10, 10]], [3, 6, 3], 3
+    Hm = Wm = 80
+    L = sum(h * w for h, w in shapes)
+    # ground truth + planted queries: query i < n_gt looks at object i
+    gt_xy = torch.rand(B, n_gt, 2, device=dev) * 0.6 + 0.2
+    gt_wh = torch.rand(B, n_gt, 2, device=dev) * 0.2 + 0.08
+    gt_boxes = torch.cat([gt_xy, gt_wh], -1)
+    gt_labels = torch.randint(0, NC, (B, n_gt), device=dev)
+    ref = torch.cat([torch.rand(B, Q, 2, device=dev), torch.rand(B, Q, 2, device=dev) * 0.3 + 0.05], -1)
+    ref[:, :n_gt] = gt_boxes * (1 + 0.03 * torch.randn(B, n_gt, 4, device=dev))
+    # class head = planted logits + a small data-dependent term: objects 0-7 are found (+3), objects
+    # 8-9 are missed (-1 -> false negatives), queries 10-14 fire on random boxes (+1 -> false
+    # positives); margins of >= 4 sigma of the data term keep every decision off the threshold
+    planted = torch.full((B, Q, NC), -4.0, device=dev)
+    strength = torch.tensor([3.0] * 8 + [-1.0] * 2, device=dev).view(1, n_gt, 1).expand(B, n_gt, 1)
+    planted[:, :n_gt].scatter_(2, gt_labels.unsqueeze(-1), strength.contiguous())
+    planted[:, n_gt:n_gt + 5, 7] = 1.0
+    memory = torch.randn(B, L, C, device=dev)
+    query = torch.randn(B, Q, C, device=dev)
+    mask_feat = torch.randn(B, C, Hm, Wm, device=dev)
+    mods = []
+    for _ in range(n_layers):
+        m = dfine_b200.MSDeformableAttention(C, H, len(shapes), npts).to(dev)
+        with torch.no_grad():
+            m.sampling_offsets.weight.normal_(0, 0.02)
+            m.attention_weights.weight.normal_(0, 0.05)
+        mods.append(m)
+    w_cls = torch.randn(NC, C, device=dev) * 0.01
+    w_cor = torch.randn(132, C, device=dev) * 0.05
+    w_msk = torch.randn(C, C, device=dev) * 0.06
+    up, rs = torch.tensor([0.5], device=dev), torch.tensor([4.0], device=dev)
+
+    def detector(ours: bool):
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            mem = memory.to(torch.bfloat16)
+            value = TP.value_views(mem, H, shapes)
+            project = dfine_b200.fdr_project(up, rs) if ours else TP.weighting_function(32, up, rs)
+            x = query
+            for m in mods:
+                if ours:
+                    y = m(x, ref.unsqueeze(2), value, shapes)
+                else:
+                    y = TP.msda_module(x, ref.unsqueeze(2), value, shapes, m.sampling_offsets.weight,
+                                       m.sampling_offsets.bias, m.attention_weights.weight,
+                                       m.attention_weights.bias, m.num_points_scale, npts, H)
+                x = x + torch.tanh(y.float())
+            logits = planted + torch.nn.functional.linear(x, w_cls).float()
+            corners = torch.nn.functional.linear(x, w_cor)
+            coef = torch.nn.functional.linear(x, w_msk)
+            if ours:
+                boxes = dfine_b200.fdr_decode(corners, ref, project, rs)
+                masks = dfine_b200.mask_logits(coef, mask_feat.to(torch.bfloat16), apply_sigmoid=True)
+            else:
+                boxes = TP.distance2bbox(ref, TP.integral(corners, project), rs)
+                masks = torch.sigmoid(TP.mask_logits(coef, mask_feat.to(torch.bfloat16)))
+        return logits.float(), boxes.float(), masks.float()
+
+    gts = [{"boxes": DM.box_cxcywh_to_xyxy(gt_boxes[b]).cpu(), "labels": gt_labels[b].cpu()} for b in range(B)]
+    ys, xs = torch.meshgrid(torch.arange(Hm, device=dev), torch.arange(Wm, device=dev), indexing="ij")
+
+    def evaluate(out):
+        logits, boxes, masks = out
+        preds = DM.postprocess(logits, boxes, conf_thresh=0.5, num_top_queries=300)
+        tps, fps, fns, ious, matches = DM.f1_counts(preds, gts, 0.5)
+        miou = []
+        for b, pairs in enumerate(matches):
+            for p_, g_ in pairs:
+                x1, y1, x2, y2 = (DM.box_cxcywh_to_xyxy(gt_boxes[b, g_]) * Wm).tolist()
+                gt_mask = ((xs >= x1) & (xs < x2) & (ys >= y1) & (ys < y2)).cpu().numpy()
+                pm = (masks[b, int(preds[b]["queries"][p_])] >= 0.5).cpu().numpy()
+                miou.append(DM.mask_iou(pm, gt_mask))
+        return preds, (tps, fps, fns), DM.f1_score(tps, fps, fns), ious, miou
+
+    p_ref, cnt_ref, f1_ref, iou_ref, miou_ref = evaluate(detector(False))
+    p_our, cnt_our, f1_our, iou_our, miou_our = evaluate(detector(True))
+    assert cnt_ref[0] >= 0.5 * B * n_gt, f"the synthetic set should be mostly detected, got {cnt_ref}"
+    assert cnt_ref[1] > 0 and cnt_ref[2] > 0, "the set should also contain false positives / negatives"
+    assert cnt_our == cnt_ref, (cnt_our, cnt_ref)
+    assert f1_our == f1_ref
+    # (mask logits within bf16 rounding of zero may land on either side of the 0.5 threshold)
+    assert len(miou_our) == len(miou_ref) and np.allclose(miou_our, miou_ref, atol=1e-2)
+    assert abs(np.mean(miou_our) - np.mean(miou_ref)) <= 3e-3
+    assert np.allclose(iou_our, iou_ref, atol=5e-3)
+    for a, b_ in zip(p_our, p_ref):   # pre-threshold top-300 lists
+        same = (a["all_queries"] == b_["all_queries"]) & (a["all_labels"] == b_["all_labels"])
+        assert same.float().mean() >= 0.97          # ties between near-equal scores may swap places
+        assert (a["all_scores"] - b_["all_scores"]).abs().max() <= 2e-2
+        assert torch.equal(a["labels"], b_["labels"]) and torch.equal(a["queries"], b_["queries"])
+
+
 def test_no_out_of_bounds_writes(dev):
     """compute-sanitizer is closed on this pool, so writes are checked with canaries: every
     output / workspace of the C-ABI calls sits between guard zones that must stay intact."""
