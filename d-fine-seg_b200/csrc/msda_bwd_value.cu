@@ -7,7 +7,7 @@
 //       (written by K1 / the K2 dots kernel with the same bit-exact geometry) and PUSH every
 //       in-bounds corner onto a per-pixel linked list in shared memory: the node id is implied
 //       by (record, corner), one native shared-memory integer exchange on the pixel's head
-//       links it: node = {next | query << 15, weight*attn}.  No count pass, no scan.
+//       links it: node = {next | query << 16, weight*attn}.  No count pass, no scan.
 //       A second integer atomic counts the pixel's corners.
 //   S2  counting sort of the chunk's pixels by corner count, descending (64 bins): the pixels a
 //       warp walks together then have (nearly) equal list lengths -- without it the warp waits
@@ -15,8 +15,9 @@
 //       pixels start first.
 //   S3  "workers" of c/VPL lanes (VPL channels per lane) take pixels from the sorted order
 //       round-robin; a worker walks its pixel's list, gathers grad_out[b, q, h, :] (staged in
-//       shared memory by cp.async while S1 runs) and accumulates in registers; the finished
-//       row is stored once.
+//       shared memory by one 3-D tensor-map TMA load per 256 queries while S1 / S2 run) and
+//       accumulates in registers; the finished row is stored once; pixels without samples are
+//       zero-filled 16 bytes per thread.
 // grad_value is written exactly once, coalesced per row, directly in its final dtype (fp32,
 // or bf16 under AMP): no zero-fill pass, no float atomics, no cast pass.  In accumulate mode
 // (DFINE_MSDA_GRAD_VALUE_ACCUMULATE) touched rows are added to the running gradient with vector
@@ -129,7 +130,7 @@ __device__ __forceinline__ void load_go_vec(uint32_t saddr, const char* gaddr, u
 }
 
 // kStage: the grad_out slice of this (image, head) -- Lq rows of c channels -- is staged in
-// shared memory with cp.async while the lists are being built, so that S2 gathers from smem.
+// shared memory by TMA while the lists are being built, so that S3 gathers from smem.
 template <int kC, typename GT, int VPL, bool kStage, bool kGvBf16, bool kAccum>
 __global__ void __launch_bounds__(kBvThreads, 1)
 msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ grad_value,
