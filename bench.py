@@ -373,6 +373,64 @@ def secondary_kernel_legs(device, peak: float, reps: int = 10):
     return out
 
 
+def inference_leg(device, steps: int = 30):
+    """BASELINE config 2 through the same public API, forward only: D-FINE-s decoder hot path at
+    batch 64, 300 queries, 3 decoder layers (module forward + FDR decode per layer) under
+    no_grad + bf16 autocast, replayed from a CUDA graph.  Informational (not the bench line)."""
+    import dfine_b200
+    B, Lq, C, H, layers = 64, 300, 256, 8, 3
+    shapes, npts = [[80, 80], [40, 40], [20, 20]], [3, 6, 3]
+    L = sum(h * w for h, w in shapes)
+    g = torch.Generator(device=device).manual_seed(11)
+    mods = []
+    for _ in range(layers):
+        m = dfine_b200.MSDeformableAttention(C, H, len(shapes), npts).to(device)
+        with torch.no_grad():
+            m.sampling_offsets.weight.normal_(0, 0.02, generator=g)
+            m.attention_weights.weight.normal_(0, 0.02, generator=g)
+        mods.append(m.eval())
+    mem = torch.randn(B, L, C, device=device, generator=g).to(torch.bfloat16)
+    queries = [torch.randn(B, Lq, C, device=device, generator=g) for _ in range(layers)]
+    ref = torch.cat([torch.rand(B, Lq, 2, device=device, generator=g) * 0.9 + 0.05,
+                     torch.exp(torch.rand(B, Lq, 2, device=device, generator=g) * 3.4 - 3.9)], -1)
+    corners = [(torch.randn(B, Lq, 132, device=device, generator=g) * 2).to(torch.bfloat16) for _ in range(layers)]
+    up, rs = torch.tensor([0.5], device=device), torch.tensor([4.0], device=device)
+
+    def step():
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            project = dfine_b200.fdr_project(up, rs, 32)
+            value = mem.reshape(B, L, H, C // H).permute(0, 2, 3, 1).split([h * w for h, w in shapes], dim=-1)
+            outs = []
+            for i, m in enumerate(mods):
+                y = m(queries[i], ref.unsqueeze(2), value, shapes)
+                outs.append(dfine_b200.fdr_decode(corners[i], ref, project, rs, 32))
+            return y, torch.stack(outs)
+
+    side = torch.cuda.Stream(device)
+    side.wait_stream(torch.cuda.current_stream(device))
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step()
+    torch.cuda.current_stream(device).wait_stream(side)
+    torch.cuda.synchronize(device)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        keep = step()
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize(device)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(steps):
+        graph.replay()
+    e.record()
+    torch.cuda.synchronize(device)
+    ms = s.elapsed_time(e) / steps
+    del keep
+    return {"workload": "dfine_s_infer_640_b64 (decoder hot path, forward only, 3 layers, CUDA graph)",
+            "ms_per_step": ms, "imgs_per_s": B / (ms / 1e3)}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
 
@@ -616,6 +674,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_secondary:
         try:
             other = secondary_kernel_legs(device, load_peaks()[0])
+            other["config2_inference_step"] = inference_leg(device)
         except Exception as exc:  # noqa: BLE001  (informational legs must not take the bench line down)
             other = {"error": str(exc)[:200]}
 
@@ -676,7 +735,7 @@ def main():
                 "serial_ms_per_step": ms_e2e_serial / args.steps},
         "gpu_launches": launches, "roofline": roofline, "clocks": clocks,
     }
-    if other is not None:
+    if other is not None:   # kernel-level legs at configs 2 / 4 / 5 and the config-2 inference step
         out["other_configs_kernel_level"] = other
 
     if world == 1 and not args.no_eager:
