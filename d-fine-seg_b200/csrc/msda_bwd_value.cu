@@ -345,13 +345,13 @@ msda_bwd_value_kernel(const MsdaParams p, const BvChunks ch, void* __restrict__ 
         u[i] = *reinterpret_cast<const uint32_t*>(&t);
       }
       if constexpr (VPL == 8 && kSwap) {
-        if constexpr (kAccum) {
-          red_bf16x4(o + 8u * hs, u[0], u[1]);
-          red_bf16x4(o + 8u * (hs ^ 1u), u[2], u[3]);
-        } else {
-          *reinterpret_cast<uint2*>(o + 8u * hs) = make_uint2(u[0], u[1]);
-          *reinterpret_cast<uint2*>(o + 8u * (hs ^ 1u)) = make_uint2(u[2], u[3]);
-        }
+        // the lane's two 4-channel halves are adjacent in memory: put them back in channel order
+        // and write / reduce the 16 bytes in one instruction (two 8-byte stores doubled the
+        // store wavefronts of the sparse level)
+        const uint32_t a0 = hs ? u[2] : u[0], a1 = hs ? u[3] : u[1];
+        const uint32_t a2 = hs ? u[0] : u[2], a3 = hs ? u[1] : u[3];
+        if constexpr (kAccum) red_bf16x8(o, a0, a1, a2, a3);
+        else *reinterpret_cast<uint4*>(o) = make_uint4(a0, a1, a2, a3);
       } else if constexpr (VPL == 8) {
         if constexpr (kAccum) red_bf16x8(o, u[0], u[1], u[2], u[3]);
         else *reinterpret_cast<uint4*>(o) = make_uint4(u[0], u[1], u[2], u[3]);
