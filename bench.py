@@ -100,10 +100,19 @@ def algorithmic_bytes(wl: dict, B: int, e_g: int = 2):
 class HotPath:
     """The patched decoder hot path over one batch, driven through the package's public API."""
 
-    def __init__(self, wl: dict, inp: dict, device: torch.device):
+    def __init__(self, wl: dict, inp: dict, device: torch.device, world: int = 1,
+                 sync_mode: str = "eager"):
         import dfine_b200
         self.api = dfine_b200
         self.wl, self.dev = wl, device
+        # data parallel (world > 1): the gradients of the path's own parameters (the two Linears
+        # of every layer) are averaged over the ranks each step -- what DDP does for them in the
+        # reference (src/dl/train.py:161-166).  "eager": one NCCL all-reduce enqueued on the compute
+        # stream right after every graph replay; "off": no exchange.  (Capturing the collective
+        # inside the step's CUDA graph measured 1.068 vs 1.079 ms at N = 2 but left the ranks
+        # hanging at process-group teardown, so it is not offered.)
+        self.world, self.sync_mode = world, (sync_mode if world > 1 else "off")
+        self.bucket = None
         self.mods = []
         for lw in inp["lin"]:
             m = dfine_b200.MSDeformableAttention(wl["C"], wl["H"], len(wl["shapes"]), wl["npts"])
@@ -116,6 +125,10 @@ class HotPath:
         self.reg_scale = torch.tensor([wl["reg_scale"]], device=device)
         self.host = None
         self.d = None
+        self.g_grads = None
+        if self.sync_mode != "off":
+            from dfine_b200 import grad_sync
+            self.bucket = grad_sync.GradBucket(grad_sync.path_parameters(self.mods))
 
     def load_device(self, inp: dict):
         dev = self.dev
@@ -169,6 +182,13 @@ class HotPath:
         torch.autograd.backward(outs + boxes, d["grad_outs"] + d["grad_boxes"])
         return boxes, mem.grad
 
+    def step_eager(self, d: dict):
+        """step() plus the gradient all-reduce a graph replay is followed by (N > 1)."""
+        r = self.step(d)
+        if self.sync_mode == "eager":
+            self.bucket.reduce()
+        return r
+
     def capture(self, warmup: int = 3):
         """Capture one step (forward + backward of all layers) over the static device
         buffers self.d into a CUDA graph: the ~120 launches of a step replay without any
@@ -187,20 +207,24 @@ class HotPath:
             boxes, mem_grad = self.step(self.d)
             self.g_boxes = torch.stack(boxes)
             self.g_mem_grad = mem_grad
+        if self.bucket is not None:   # the graph's own (static) parameter-gradient tensors
+            self.g_grads = [p.grad for p in self.bucket.params]
         self.launches_per_step = ops.LAUNCHES["count"] - n0
         return self.graph
 
     def replay(self):
         self.graph.replay()
+        if self.sync_mode == "eager":
+            self.bucket.reduce(self.g_grads)
 
     def setup_pipeline(self, inp: dict):
         """Second set of static buffers + graph, a copy stream and events: the H2D copies of
         step i+1 overlap the compute of step i (copies and kernels on separate streams)."""
-        first = dict(d=self.d, graph=self.graph, boxes=self.g_boxes)
+        first = dict(d=self.d, graph=self.graph, boxes=self.g_boxes, grads=self.g_grads)
         self.load_device(inp)             # fresh static buffers -> self.d
         self.capture(warmup=3)            # second graph over them
-        second = dict(d=self.d, graph=self.graph, boxes=self.g_boxes)
-        self.d, self.graph, self.g_boxes = first["d"], first["graph"], first["boxes"]
+        second = dict(d=self.d, graph=self.graph, boxes=self.g_boxes, grads=self.g_grads)
+        self.d, self.graph, self.g_boxes, self.g_grads = first["d"], first["graph"], first["boxes"], first["grads"]
         self.sets = [first, second]
         self.copy_stream = torch.cuda.Stream(self.dev)
         for st in self.sets:
@@ -229,6 +253,8 @@ class HotPath:
             st["copied"].record(self.copy_stream)
         comp.wait_event(st["copied"])
         st["graph"].replay()
+        if self.sync_mode == "eager":
+            self.bucket.reduce(st["grads"])
         st["host_boxes"].copy_(st["boxes"], non_blocking=True)
         st["done"].record(comp)
         return st["host_boxes"]
@@ -246,7 +272,7 @@ class HotPath:
                     dst.copy_(src, non_blocking=True)
             else:
                 self.d[k].copy_(v, non_blocking=True)
-        self.graph.replay()
+        self.replay()
         self.boxes_host.copy_(self.g_boxes, non_blocking=True)
         torch.cuda.current_stream(self.dev).synchronize()
         return self.boxes_host
@@ -607,6 +633,8 @@ def main():
     ap.add_argument("--no-eager", action="store_true", help="skip the eager-PyTorch GPU bar")
     ap.add_argument("--no-secondary", action="store_true",
                     help="skip the kernel-level legs at the other BASELINE configs")
+    ap.add_argument("--grad-sync", default="eager", choices=["eager", "off"],
+                    help="N > 1: NCCL all-reduce of the path's Linear gradients after every step / no exchange")
     ap.add_argument("--launch-list", action="store_true",
                     help="profiling aid: run W+K eager steps of the B200 path and exit (for an ncu launch list)")
     args = ap.parse_args()
@@ -634,7 +662,7 @@ def main():
     dfine_b200._lib.lib()  # fail loudly if the extension is missing
 
     inp = make_inputs(wl, wl["B"], rank_seed(rank), "cpu")
-    hp = HotPath(wl, inp, device)
+    hp = HotPath(wl, inp, device, world=world, sync_mode=args.grad_sync)
     hp.load_device(inp)
     hp.pin_host(inp)
 
@@ -660,9 +688,9 @@ def main():
     # ---- eager pass (no graph) with CUDA-event brackets around every C-ABI launch: the
     #      per-kernel durations behind the roofline figures ----
     for _ in range(2):
-        hp.step(hp.d)
+        hp.step_eager(hp.d)
     ops.enable_kernel_timers(True)
-    ms_eager = time_steps(lambda: hp.step(hp.d), args.steps, 0, device, dist_on)
+    ms_eager = time_steps(lambda: hp.step_eager(hp.d), args.steps, 0, device, dist_on)
     timers = ops.kernel_timers()
     kernel_ms = {k: sum(s.elapsed_time(e) for s, e in v) / len(v) for k, v in timers.items()}
     kernel_calls = {k: len(v) // args.steps for k, v in timers.items()}
@@ -725,7 +753,11 @@ def main():
                    "memory_grad": "one buffer shared by the 4 layers (hub node), layers 2-4 accumulate in the kernel",
                    "l2_policy": "inputs_larger_than_l2 (per layer: memory 137.6 MB + grad 137.6 MB + queries, "
                                 "grads, records; 4 layers per step)",
-                   "parallelism": f"dp{world} (batch-sharded, no data-path collective)"},
+                   "parallelism": f"dp{world} (batch-sharded; the kernels need no collective)",
+                   "collective": (None if hp.bucket is None else
+                                  f"NCCL all-reduce (avg) of the {wl['layers']} layers' Linear gradients, "
+                                  f"{hp.bucket.nbytes} B per step, one bucket, enqueued on the compute "
+                                  f"stream after every graph replay")},
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": hp.h2d_bytes, "d2h_bytes_per_step": hp.d2h_bytes,
                 "pipeline": "double-buffered: H2D of step i+1 on a copy stream overlaps the graph "

@@ -16,7 +16,8 @@ REPO_ROOT = os.path.dirname(PROJ_DIR)
 CSRC = os.path.join(PROJ_DIR, "csrc")
 INCLUDE = os.path.join(REPO_ROOT, "include")
 LIB_DIR = os.path.join(PKG_DIR, "_C")
-LIB_PATH = os.path.join(LIB_DIR, "libdfine_b200.so")
+# DFINE_B200_LIB: load another build of the same C-ABI (A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("DFINE_B200_LIB") or os.path.join(LIB_DIR, "libdfine_b200.so")
 
 SOURCES = ["api.cu", "msda_fwd.cu", "msda_fwd_tiled.cu", "msda_bwd.cu", "msda_bwd_value.cu", "fdr.cu", "mask_gemm.cu", "reduce.cu"]
 NVCC_FLAGS = [
@@ -37,6 +38,8 @@ def sources() -> List[str]:
 
 
 def is_stale() -> bool:
+    if os.environ.get("DFINE_B200_LIB"):
+        return False          # an explicitly named library is used as it is (and must exist)
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)

@@ -1,0 +1,65 @@
+"""Gradient exchange of the hot path's own parameters under data parallelism.
+
+The path shards by image: the kernels own no parameters and need no
+collective.  The only parameters inside the module boundary are the two ``nn.Linear`` of every
+``MSDeformableAttention`` (reference src/d_fine/arch/dfine_decoder.py:79-80); in the reference
+their gradients are averaged over the ranks by ``DistributedDataParallel``
+(reference src/dl/train.py:161-166).  ``GradBucket`` is that step for this path alone: one flat
+bucket, ONE all-reduce (NCCL on GPUs, NVLink / NVSwitch), the averaged gradients written back
+into ``param.grad``.  Plain ``torch.distributed`` plumbing -- no kernels of ours.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def path_parameters(modules: Iterable[torch.nn.Module]) -> List[torch.nn.Parameter]:
+    """Trainable parameters of the given MSDeformableAttention modules in a fixed order
+    (module order, then ``named_parameters`` order) -- the same on every rank."""
+    out: List[torch.nn.Parameter] = []
+    for m in modules:
+        out.extend(p for _, p in m.named_parameters() if p.requires_grad)
+    return out
+
+
+class GradBucket:
+    """Flat all-reduce bucket over a fixed parameter list."""
+
+    def __init__(self, params: Sequence[torch.nn.Parameter], group=None):
+        self.params = list(params)
+        if not self.params:
+            raise ValueError("GradBucket: empty parameter list")
+        self.group = group
+        self.numels = [p.numel() for p in self.params]
+        self.nbytes = sum(p.numel() * p.element_size() for p in self.params)
+
+    def world(self) -> int:
+        return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+
+    def reduce(self, grads: Optional[Sequence[torch.Tensor]] = None) -> torch.Tensor:
+        """Average the gradients over the ranks of the group, in place.  ``grads`` defaults to
+        the parameters' ``.grad``; every rank must pass gradients for every parameter
+        (the reference wraps with ``find_unused_parameters=False``).  Returns the flat bucket.
+        Enqueued on the current stream; does not synchronise."""
+        if grads is None:
+            grads = [p.grad for p in self.params]
+        if len(grads) != len(self.params) or any(g is None for g in grads):
+            missing = [i for i, g in enumerate(grads) if g is None]
+            raise RuntimeError(f"GradBucket.reduce: parameters {missing} have no gradient on this rank")
+        for g, n in zip(grads, self.numels):
+            if g.numel() != n:
+                raise RuntimeError("GradBucket.reduce: gradient shape does not match its parameter")
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        world = self.world()
+        if world > 1:
+            if flat.is_cuda:
+                dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)   # NCCL averages in the collective
+            else:
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)   # gloo: no AVG
+                flat.mul_(1.0 / world)
+            with torch.no_grad():
+                torch._foreach_copy_(list(grads), [c.view_as(g) for c, g in zip(flat.split(self.numels), grads)])
+        return flat

@@ -160,3 +160,61 @@ def test_bench_multi_rank_logic_gloo():
     assert ms0 == ms1 == 20.0
     assert sum0 != sum1
     assert thr0 == thr1 == 32 * 2 * 4 / 0.020
+
+
+def _bucket_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "d-fine-seg_b200"))
+    from dfine_b200 import grad_sync
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)                       # same parameters on every rank
+    mods = [torch.nn.ModuleDict(dict(sampling_offsets=torch.nn.Linear(8, 12),
+                                     attention_weights=torch.nn.Linear(8, 6))) for _ in range(2)]
+    params = grad_sync.path_parameters(mods)
+    bucket = grad_sync.GradBucket(params)
+    g = torch.Generator().manual_seed(100 + rank)   # different shards -> different gradients
+    local = [torch.randn(p.shape, generator=g) for p in params]
+    for p, t in zip(params, local):
+        p.grad = t.clone()
+    flat = bucket.reduce()
+    # explicit gradient list (what a CUDA-graph replay hands over) gives the same result
+    again = [t.clone() for t in local]
+    bucket.reduce(again)
+    q.put((rank, [t.numpy() for t in local], [p.grad.numpy() for p in params],
+           [t.numpy() for t in again], flat.numel(), bucket.nbytes))
+    # a rank that lacks a gradient must fail loudly, before any collective is entered
+    params[0].grad = None
+    try:
+        bucket.reduce()
+        q.put((rank, "no error"))
+    except RuntimeError as exc:
+        q.put((rank, str(exc)))
+    dist.destroy_process_group()
+
+
+def test_grad_bucket_averages_linear_gradients_gloo():
+    """world_size 2 over gloo: the flat bucket all-reduce leaves the rank average of every
+    Linear gradient in param.grad on both ranks (DDP's step for the path's own parameters)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    got = [q.get(timeout=120) for _ in range(4)]
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    res = sorted((g for g in got if len(g) == 6), key=lambda g: g[0])
+    errs = [g for g in got if len(g) == 2]
+    assert len(res) == 2 and len(errs) == 2
+    assert all("no gradient" in e[1] for e in errs)
+    (_, l0, r0, a0, n0, b0), (_, l1, r1, a1, n1, b1) = res
+    assert n0 == n1 == 2 * (8 * 12 + 12 + 8 * 6 + 6) and b0 == 4 * n0
+    for x0, x1, y0, y1, z0, z1 in zip(l0, l1, r0, r1, a0, a1):
+        want = (x0 + x1) / 2
+        np.testing.assert_allclose(y0, want, rtol=0, atol=1e-7)
+        np.testing.assert_array_equal(y0, y1)
+        np.testing.assert_array_equal(z0, y0)
+        np.testing.assert_array_equal(z1, y1)
