@@ -25,6 +25,7 @@ int launch_pack_linear(const float*, const float*, int, const float*, const floa
                        cudaStream_t);
 int launch_mask_gemm(const void*, const void*, void*, int, int, int, int, int, int, cudaStream_t);
 int launch_colsum(const void*, int, long long, int, long long, float*, cudaStream_t);
+int launch_linear_wgrad(const void*, int64_t, const void*, int64_t, int, int, int, float*, cudaStream_t);
 
 static int cuda_rc(int rc, const char* what) {
   if (rc > 0) set_error("%s: CUDA error %d (%s)", what, rc, cudaGetErrorString((cudaError_t)rc));
@@ -373,6 +374,33 @@ int dfine_colsum(const void* x, int x_dtype, int64_t M, int N, int64_t row_strid
   }
   return cuda_rc(launch_colsum(x, x_dtype == DFINE_BF16, M, N, row_stride ? row_stride : N, out,
                                (cudaStream_t)stream), fn);
+}
+
+int dfine_linear_wgrad(const void* grad_y, int64_t gy_row_stride, const void* x, int64_t x_row_stride,
+                       int64_t M, int N, int K, float* dw_db, void* stream) {
+  const char* fn = "dfine_linear_wgrad";
+  int rc;
+  if (M <= 0 || M > 0x7fffffffLL || N <= 0 || K <= 0 || (N & 7) || (K & 7) || K > 256) {
+    set_error("%s: need 0 < M < 2^31, N and K positive multiples of 8 and K <= 256 (got %lld, %d, %d)", fn,
+              (long long)M, N, K);
+    return (K > 256) ? DFINE_E_UNSUPPORTED : DFINE_E_SHAPE;
+  }
+  if (gy_row_stride == 0) gy_row_stride = N;
+  if (x_row_stride == 0) x_row_stride = K;
+  if (gy_row_stride < N || x_row_stride < K || (gy_row_stride & 7) || (x_row_stride & 7)) {
+    set_error("%s: row strides (%lld, %lld) must be >= (N, K) and multiples of 8 elements", fn,
+              (long long)gy_row_stride, (long long)x_row_stride);
+    return DFINE_E_SHAPE;
+  }
+  if ((rc = require_device(grad_y, "grad_y", fn))) return rc;
+  if ((rc = require_device(x, "x", fn))) return rc;
+  if ((rc = require_device(dw_db, "dw_db", fn))) return rc;
+  if (!aligned16(grad_y) || !aligned16(x) || !aligned16(dw_db)) {
+    set_error("%s: grad_y, x and dw_db must be 16-byte aligned", fn);
+    return DFINE_E_ALIGN;
+  }
+  return cuda_rc(launch_linear_wgrad(grad_y, gy_row_stride, x, x_row_stride, (int)M, N, K, dw_db,
+                                     (cudaStream_t)stream), fn);
 }
 
 int dfine_pack_linear(const float* w0, const float* b0, int n0, const float* w1, const float* b1, int n1,

@@ -3,6 +3,8 @@ pointers, streams).  All compute happens in libdfine_b200.so; CPU tensors are re
 """
 from __future__ import annotations
 
+import os
+
 import functools
 import weakref
 from typing import List, Optional, Sequence, Tuple, Union
@@ -602,8 +604,11 @@ class _PackedLinearFn(torch.autograd.Function):
         if g2.dtype != w.dtype:
             g2 = g2.to(w.dtype)
         gx = _mm(g2, w, ctx.x_dtype).reshape(ctx.x_shape)
-        gw = _mm(g2.t(), x2, torch.float32)
-        gb = colsum(g2) if colsum_supported(g2) else g2.float().sum(0)
+        if linear_wgrad_supported(g2, x2):
+            gw, gb = linear_wgrad(g2, x2)      # dW and db in one tensor-core launch
+        else:
+            gw = _mm(g2.t(), x2, torch.float32)
+            gb = colsum(g2) if colsum_supported(g2) else g2.float().sum(0)
         n0 = ctx.n0
         return gx, gw[:n0], gb[:n0], gw[n0:], gb[n0:]
 
@@ -615,6 +620,33 @@ def packed_linear_supported(x, w0, b0, w1, b1) -> bool:
 
 def packed_linear(x, w0, b0, w1, b1):
     return _PackedLinearFn.apply(x, w0, b0, w1, b1)
+
+
+def linear_wgrad_supported(gy: torch.Tensor, x: torch.Tensor) -> bool:
+    if os.environ.get("DFINE_LINEAR_WGRAD", "1") == "0":     # A/B switch: cuBLAS split-K GEMM + dfine_colsum
+        return False
+    return (gy.is_cuda and x.is_cuda and gy.dim() == 2 and x.dim() == 2 and gy.shape[0] == x.shape[0]
+            and gy.shape[0] > 0 and gy.dtype == torch.bfloat16 and x.dtype == torch.bfloat16
+            and gy.stride(1) == 1 and x.stride(1) == 1 and gy.shape[1] % 8 == 0 and x.shape[1] % 8 == 0
+            and x.shape[1] <= 256 and gy.stride(0) % 8 == 0 and x.stride(0) % 8 == 0
+            and gy.data_ptr() % 16 == 0 and x.data_ptr() % 16 == 0)
+
+
+def linear_wgrad(gy: torch.Tensor, x: torch.Tensor):
+    """(gy.t() @ x, gy.sum(0)) in float32 for bf16 gy [M, N], x [M, K <= 256] (dfine_linear_wgrad:
+    one tcgen05 launch; the two results are views of one buffer)."""
+    _require_cuda(gy, x)
+    if not linear_wgrad_supported(gy, x):
+        raise ValueError("linear_wgrad: need row-major bf16 gy [M, N], x [M, K] with N, K, strides multiples "
+                         "of 8 and K <= 256")
+    M, N = gy.shape
+    K = x.shape[1]
+    buf = torch.empty(N * K + N, dtype=torch.float32, device=gy.device)
+    with torch.cuda.device_of(gy), _timed("linear_wgrad", gy):
+        rc = _lib.lib().dfine_linear_wgrad(gy.data_ptr(), gy.stride(0), x.data_ptr(), x.stride(0), M, N, K,
+                                           buf.data_ptr(), _stream(gy))
+    check(rc, "dfine_linear_wgrad")
+    return buf[:N * K].view(N, K), buf[N * K:]
 
 
 def colsum_supported(x: torch.Tensor) -> bool:

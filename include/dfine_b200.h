@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DFINE_B200_VERSION 101 /* major*100 + minor */
+#define DFINE_B200_VERSION 102 /* major*100 + minor */
 
 #if defined(__GNUC__)
 #define DFINE_API __attribute__((visibility("default")))
@@ -167,6 +167,19 @@ DFINE_API int dfine_cast_f32_to_bf16(const float* src, void* dst, int64_t n, voi
  * x 8-byte aligned); out: float32 [N], overwritten. */
 DFINE_API int dfine_colsum(const void* x, int x_dtype, int64_t M, int N, int64_t row_stride, float* out,
                  void* stream);
+
+/* Weight and bias gradient of the concatenated sampling_offsets / attention_weights Linear in one
+ * tensor-core launch (tcgen05, split over the rows, fp32 accumulation): autograd's
+ * grad_output.t() @ input and grad_output.sum(0) for the nn.Linear of dfine_decoder.py:87-88
+ * (forward :139-147).
+ *   grad_y: bf16 [M, N] (gy_row_stride elements between rows, 0 = N) -- the [B*Lq, 3HP] gradient
+ *           dfine_msda_bwd writes;  x: bf16 [M, K] (x_row_stride, 0 = K) -- the Linear's input;
+ *   dw_db : float32 [N*K + N]: dW [N, K] followed by db [N]; zero-filled, then accumulated with
+ *           fp32 reductions (the order over the row splits is not fixed: fp32 rounding only).
+ * N, K and the strides are multiples of 8, K <= 256 (DFINE_E_UNSUPPORTED otherwise: use a
+ * library GEMM); pointers 16-byte aligned. */
+DFINE_API int dfine_linear_wgrad(const void* grad_y, int64_t gy_row_stride, const void* x, int64_t x_row_stride,
+                       int64_t M, int N, int K, float* dw_db, void* stream);
 
 /* Parameters of the concatenated Linear in one launch: w = [w0; w1] ([n0+n1, K]) and
  * b = [b0; b1], float32 in, out_dtype out (bf16 under autocast).  w0/b0 = sampling_offsets,

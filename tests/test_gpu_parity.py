@@ -4,6 +4,8 @@ reference, (b) the CPU oracle on seeded inputs, and (c) size-independent propert
 BASELINE.json sizes.  Tolerances are the ones north_star states: corner indices bit-exact,
 fp32 1e-5 relative, bf16 1e-2 relative (relative to the tensor's max magnitude).
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -456,6 +458,52 @@ def test_colsum(dev):
     assert torch.allclose(ops.colsum(big[:, :288]), big[:, :288].sum(0), rtol=1e-5, atol=1e-4)
     with pytest.raises(ValueError):
         ops.colsum(torch.randn(8, 7, device=dev))
+
+
+def test_linear_wgrad(dev):
+    """dfine_linear_wgrad (tcgen05: dW = gy^T x and db = column sums of gy in one launch) against a
+    float64 product of the same bf16 inputs; shapes with a ragged row tile / row block / column box,
+    strided operands, and the packed-Linear backward that uses it against the cuBLAS route."""
+    import dfine_b200.ops as ops
+    torch.manual_seed(3)
+    for (M, N, K) in [(16000, 288, 256), (4800, 288, 128), (77, 96, 64), (1, 8, 8), (8009, 136, 200), (64, 128, 256)]:
+        gy = torch.randn(M, N, device=dev).to(torch.bfloat16)
+        x = torch.randn(M, K, device=dev).to(torch.bfloat16)
+        gw, gb = ops.linear_wgrad(gy, x)
+        assert gw.shape == (N, K) and gb.shape == (N,) and gw.dtype == gb.dtype == torch.float32
+        want_w = gy.double().t() @ x.double()
+        want_b = gy.double().sum(0)
+        # fp32 accumulation of exact bf16 products: error ~ sqrt(M) * 2^-24 of the magnitude
+        assert rel_err(gw.double().cpu().numpy(), want_w.cpu().numpy()) <= 1e-5, (M, N, K)
+        assert rel_err(gb.double().cpu().numpy(), want_b.cpu().numpy()) <= 1e-5, (M, N, K)
+    # row-strided views of wider buffers
+    big_g = torch.randn(500, 320, device=dev).to(torch.bfloat16)
+    big_x = torch.randn(500, 264, device=dev).to(torch.bfloat16)
+    gw, gb = ops.linear_wgrad(big_g[:, :288], big_x[:, :256])
+    assert rel_err(gw.double().cpu().numpy(), (big_g[:, :288].double().t() @ big_x[:, :256].double()).cpu().numpy()) <= 1e-5
+    assert rel_err(gb.double().cpu().numpy(), big_g[:, :288].double().sum(0).cpu().numpy()) <= 1e-5
+    with pytest.raises(ValueError):
+        ops.linear_wgrad(torch.zeros(8, 7, device=dev, dtype=torch.bfloat16), torch.zeros(8, 8, device=dev, dtype=torch.bfloat16))
+    with pytest.raises(ValueError):   # K > 256 is left to the library GEMM
+        ops.linear_wgrad(torch.zeros(8, 8, device=dev, dtype=torch.bfloat16), torch.zeros(8, 512, device=dev, dtype=torch.bfloat16))
+    # the packed Linear's backward through it == through cuBLAS + dfine_colsum
+    q = torch.randn(4, 50, 256, device=dev)
+    lin = [torch.nn.Linear(256, 192).to(dev), torch.nn.Linear(256, 96).to(dev)]
+    go = torch.randn(4, 50, 288, device=dev)
+    grads = {}
+    for mode in ("1", "0"):
+        os.environ["DFINE_LINEAR_WGRAD"] = mode
+        try:
+            for l in lin:
+                l.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                y = ops.packed_linear(q, lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias)
+            y.backward(go.to(y.dtype))
+            grads[mode] = [p.grad.clone() for l in lin for p in (l.weight, l.bias)]
+        finally:
+            os.environ.pop("DFINE_LINEAR_WGRAD", None)
+    for a, b in zip(grads["1"], grads["0"]):
+        assert a.shape == b.shape and rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 1e-5
 
 
 def test_error_behaviour(dev):
