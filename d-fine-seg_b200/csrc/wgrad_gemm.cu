@@ -17,7 +17,8 @@
 //                              K = 16 (m) into TMEM columns [0, 256); a second MMA with N = 16
 //                              against a shared-memory tile of ones accumulates the column sums
 //                              of gy (the bias gradient) in TMEM columns [256, 272).
-//   warps 2..5  epilogue     : tcgen05.ld -> red.global.add.v4.f32 into the zero-filled fp32 result
+//   warps 2..5  epilogue     : tcgen05.ld -> transpose through smem (row-contiguous lanes) ->
+//                              red.global.add.v4.f32 into the zero-filled fp32 result
 //                              (the splits of the m range meet in L2; the summation order over
 //                              the splits is not fixed, fp32 rounding only).
 #include <cuda.h>
@@ -42,7 +43,10 @@ constexpr int A_BYTES = BOX_BYTES * (BLOCK_N / 64);     // 16 KiB
 constexpr int B_BYTES = BOX_BYTES * (BLOCK_K / 64);     // 32 KiB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int ONES_BYTES = BOX_BYTES;                   // bf16 1.0 everywhere: layout-free B operand
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + ONES_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int EPI_WARPS = 4;
+constexpr int STG_ROW = 36;                             // floats per staged row: 32 + pad, 16-byte rows
+constexpr int STG_BYTES = EPI_WARPS * 32 * STG_ROW * 4; // per-warp transposition buffers, 18 KiB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + ONES_BYTES + STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int THREADS = 192;
 constexpr int TMEM_COLS = 512;         // 256 (dW) + 16 (db), rounded to a power of two
 
@@ -69,7 +73,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_constant__
   unsigned char* smem = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   unsigned char* smem_ones = smem + STAGES * STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_ones + ONES_BYTES);
+  float* smem_stg = reinterpret_cast<float*>(smem_ones + ONES_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_ones + ONES_BYTES + STG_BYTES);
   uint64_t* full_bar = bars;                    // [STAGES]
   uint64_t* empty_bar = bars + STAGES;          // [STAGES]
   uint64_t* tmem_full = bars + 2 * STAGES;      // [1]
@@ -168,22 +173,34 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_gy, const __grid_constant__
   } else {
     // ===================== epilogue =====================
     const int wq = warp & 3;                 // TMEM lane quarter this warp may access
-    const int n = nt * BLOCK_N + wq * 32 + lane;   // row of dW held by this thread
+    const int n0 = nt * BLOCK_N + wq * 32;   // first row of dW held by this warp
+    const int n = n0 + lane;                 // row held by this thread (TMEM lane)
     mbar_wait(smem_u32(tmem_full), 0);
     tcgen05_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16);
-    float* row = dw + (size_t)n * K;
+    // A thread holds one ROW of the tile: reducing straight from the registers would make every
+    // warp-wide red touch 32 rows (32 half-used sectors, measured: the reds were a third of the
+    // kernel).  Each 32 x 32 chunk is transposed through a padded per-warp buffer instead, so that
+    // 8 lanes cover 128 contiguous bytes of a row: 4 lines per warp-wide red.v4.
+    float* stg = smem_stg + (warp - 2) * 32 * STG_ROW;
+    const int srow = lane >> 3, c4 = (lane & 7) * 4;
     for (int c0 = 0; c0 < 64 * k_boxes; c0 += 32) {
       uint32_t r[32];
       tmem_ld_32x32(taddr + c0, r);
-      if (n < N) {
+      __syncwarp();                          // the previous chunk has been read back
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (c0 + 4 * j < K)   // K is a multiple of 4
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint4*>(stg + lane * STG_ROW + 4 * j) =
+            make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+      __syncwarp();
+      if (c0 + c4 < K) {                     // K is a multiple of 4
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = 4 * i + srow;
+          const float4 v = *reinterpret_cast<const float4*>(stg + rr * STG_ROW + c4);
+          if (n0 + rr < N)
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
-                         ::"l"(row + c0 + 4 * j), "f"(__uint_as_float(r[4 * j])),
-                           "f"(__uint_as_float(r[4 * j + 1])), "f"(__uint_as_float(r[4 * j + 2])),
-                           "f"(__uint_as_float(r[4 * j + 3]))
+                         ::"l"(dw + (size_t)(n0 + rr) * K + c0 + c4), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                          : "memory");
         }
       }
