@@ -299,7 +299,10 @@ def test_msda_vs_oracle_full_resolution(dev):
 @pytest.mark.parametrize("cfg", [
     dict(name="config3 m train", B=32, Lq=500, shapes=[[80, 80], [40, 40], [20, 20]], npts=[3, 6, 3]),
     dict(name="config5 x 1024", B=8, Lq=500, shapes=[[128, 128], [64, 64], [32, 32]], npts=[4, 4, 4]),
-])
+    dict(name="config2 s infer", B=64, Lq=300, shapes=[[80, 80], [40, 40], [20, 20]], npts=[3, 6, 3]),
+    dict(name="config1 n infer", B=1, Lq=300, shapes=[[40, 40], [20, 20]], npts=[6, 6], c=16),
+    dict(name="config4 m seg", B=16, Lq=500, shapes=[[80, 80], [40, 40], [20, 20]], npts=[3, 6, 3]),
+], ids=lambda c: c["name"].replace(" ", "_"))
 def test_full_size_properties(cfg, dev):
     """BASELINE.json sizes, bf16 value: (1) against eager PyTorch (F.grid_sample restatement)
     on the same GPU, (2) the adjoint identity <out(V), G> == <V, grad_value(G)> which holds
@@ -308,7 +311,7 @@ def test_full_size_properties(cfg, dev):
     import dfine_b200.ops as ops
     from oracle import torch_port as TP
     torch.manual_seed(0)
-    B, Lq, H, c = cfg["B"], cfg["Lq"], 8, 32
+    B, Lq, H, c = cfg["B"], cfg["Lq"], 8, cfg.get("c", 32)
     shapes, npts = cfg["shapes"], cfg["npts"]
     spec = ops.level_spec(shapes, npts)
     P = spec.P
