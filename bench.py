@@ -507,12 +507,13 @@ class ClockSampler:
 
 def load_traffic(kernel: str):
     """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (or None)."""
-    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
-    try:
-        with open(p) as f:
-            return json.load(f).get(kernel)
-    except (OSError, ValueError):
-        return None
+    for name in ("r3_traffic.json", "r2_traffic.json"):   # newest capture first
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                return json.load(f).get(kernel)
+        except (OSError, ValueError):
+            continue
+    return None
 
 
 def load_peaks():
@@ -724,7 +725,7 @@ def main():
     roofline = {
         "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": load_traffic(dom), "peak_source": peak_src,
-        "traffic_source": "profiles/r2_traffic.json (ncu --set full, dram read + write per launch)",
+        "traffic_source": "profiles/r3_traffic.json (ncu --set full, dram read + write per launch)",
         "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": kms[dom],
         "msda_fwd_bwd": {"algorithmic_bytes": fwd_b + bwd_b, "ms": fb_ms,
                          "achieved": (fwd_b + bwd_b) / (fb_ms / 1e3) / 1e9,

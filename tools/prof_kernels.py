@@ -53,6 +53,7 @@ def main():
     attn_view = raw.reshape(-1)[2 * H * spec.P:]
     rs = raw.shape[-1]
     g_raw = torch.empty_like(raw)
+    xq = torch.randn(B * Lq, H * c, device=dev).to(torch.bfloat16)   # the Linear's input (bf16 queries)
     for _ in range(a.iters):
         rec = ops.new_records(mem, spec, H, Lq)
         ev[0].record()
@@ -62,6 +63,8 @@ def main():
         ops.msda_backward_raw(mem, spec, H, raw, attn_view, ref, nps, 0.5, True, go, gv_dtype=mem.dtype,
                               samp_rs=rs, attn_rs=rs, grad_raw=g_raw, records=rec)
         ev[2].record()
+        if vdt == torch.bfloat16:   # weight + bias gradient of the concatenated Linear over the kernel's own output
+            ops.linear_wgrad(g_raw.reshape(B * Lq, rs), xq)
         torch.cuda.synchronize()
         tf.append(ev[0].elapsed_time(ev[1]))
         tb.append(ev[1].elapsed_time(ev[2]))
