@@ -48,6 +48,14 @@ def test_argument_validation_without_gpu():
     assert rc == -1 and b"NULL" in lib.dfine_last_error()
     assert lib.dfine_mask_gemm_fwd(None, None, None, 1, 8, 100, 64, 1, 0, None) == -3
     assert lib.dfine_fdr_project(None, None, None, 31, None) == -2
+    # dfine_linear_wgrad: shapes first (K > 256 is "use a library GEMM", the rest bad shapes), then pointers
+    assert lib.dfine_linear_wgrad(None, 0, None, 0, 16, 288, 512, None, None) == -3
+    assert b"K <= 256" in lib.dfine_last_error()
+    assert lib.dfine_linear_wgrad(None, 0, None, 0, 16, 287, 256, None, None) == -2
+    assert lib.dfine_linear_wgrad(None, 0, None, 0, 0, 288, 256, None, None) == -2
+    assert lib.dfine_linear_wgrad(None, 100, None, 0, 16, 288, 256, None, None) == -2
+    assert b"row strides" in lib.dfine_last_error()
+    assert lib.dfine_linear_wgrad(None, 0, None, 0, 16, 288, 256, None, None) == -1
     with pytest.raises(_lib.DfineB200Error):
         _lib.check(rc, "probe")
 
