@@ -191,3 +191,12 @@ def mask_gemm(coef, proto, apply_sigmoid: bool = False) -> np.ndarray:
                                 int(apply_sigmoid))
     assert rc == 0, rc
     return out.reshape(B, M, *tail)
+
+
+def linear_wgrad(grad_y: np.ndarray, x: np.ndarray):
+    """Weight and bias gradient of y = x W^T + b (autograd of the two nn.Linear of MSDeformableAttention,
+    reference src/d_fine/arch/dfine_decoder.py:87-88, :139-147): dW = grad_y^T x, db = sum over the rows of
+    grad_y.  Plain float64 numpy (test infrastructure: the checker of dfine_linear_wgrad)."""
+    g = np.asarray(grad_y, dtype=np.float64).reshape(-1, grad_y.shape[-1])
+    xx = np.asarray(x, dtype=np.float64).reshape(-1, x.shape[-1])
+    return g.T @ xx, g.sum(0)

@@ -118,3 +118,18 @@ def test_mask_assembly():
     g = golden("mask")
     assert_close(O.mask_gemm(g["coef"], g["proto"]), g["logits"], FP32_RTOL, "logits")
     assert_close(O.mask_gemm(g["coef"], g["proto"], True), g["probs"], FP32_RTOL, "probs")
+
+
+def test_linear_wgrad_restatement_matches_torch_autograd():
+    """oracle.linear_wgrad (checker of dfine_linear_wgrad) == autograd of torch.nn.functional.linear."""
+    import torch
+    from oracle import cpu_oracle as O
+    torch.manual_seed(0)
+    x = torch.randn(37, 24, dtype=torch.float64)
+    w = torch.randn(16, 24, dtype=torch.float64, requires_grad=True)
+    b = torch.randn(16, dtype=torch.float64, requires_grad=True)
+    gy = torch.randn(37, 16, dtype=torch.float64)
+    torch.nn.functional.linear(x, w, b).backward(gy)
+    dw, db = O.linear_wgrad(gy.numpy(), x.numpy())
+    np.testing.assert_allclose(dw, w.grad.numpy(), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(db, b.grad.numpy(), rtol=1e-12, atol=1e-12)
