@@ -457,6 +457,113 @@ def inference_leg(device, steps: int = 30):
             "ms_per_step": ms, "imgs_per_s": B / (ms / 1e3)}
 
 
+# ------------------------------------------------------------------------------------------
+# full model: the UNMODIFIED reference model (baseline/_ref) with and without the patched hot path
+# ------------------------------------------------------------------------------------------
+def full_model_leg(device, rank: int, world: int, dist_on: bool, steps: int, warmup: int):
+    """BASELINE configs 3 and 2 through the real model on this GPU: `build_model` of the reference
+    (baseline/_ref/src/d_fine/dfine.py:51-73), the reference criterion + Hungarian matcher, AdamW from the
+    reference's `build_optimizer`, the train step restated from src/dl/train.py:545-557 / :488-511 (bf16
+    autocast, clip 0.1) -- once unpatched (the reference's own eager CUDA path: the bar), once with
+    `dfine_b200.patch_model`.  Every step copies its images from pinned host memory (end to end: only
+    images and targets cross PCIe).  N > 1: both arms are wrapped in DistributedDataParallel exactly as
+    src/dl/train.py:161-166 does, so the curve includes the real gradient exchange (78 MB for D-FINE-m)."""
+    import copy
+
+    import dfine_b200
+    from baseline import model_harness as MH
+    from baseline import ref_install
+    from dfine_b200 import ops
+
+    if not ref_install.installed():
+        return {"unavailable": "baseline/_ref (reference model package) is not installed: run __graft_entry__.build()"}
+    try:
+        from loguru import logger
+        logger.remove()
+    except Exception:  # noqa: BLE001
+        pass
+    out = {}
+
+    def timed(fn, n, w):
+        return time_steps(fn, n, w, device, dist_on) / n
+
+    # ---- config 3: D-FINE-m training, 640x640, batch 32 per GPU ----
+    B = 32
+    model, loss_fn = MH.build("m", device, 640, False, seed=0)
+    model.train(), loss_fn.train()
+    patched = copy.deepcopy(model)
+    counts = dfine_b200.patch_model(patched)
+    arms = {"reference": model, "patched": patched}
+    images, targets = MH.synthetic_batch(B, 640, "cpu", seed=rank_seed(rank))
+    host_images = images.pin_memory()
+    host_targets = [{k: v.pin_memory() for k, v in t.items()} for t in targets]
+    h2d = host_images.numel() * 4 + sum(v.numel() * v.element_size() for t in host_targets for v in t.values())
+    res = {"workload": "dfine_m_train_640_b32 (full model: HGNetv2-B2 + HybridEncoder + DFINETransformer, "
+                       "criterion + Hungarian matcher, AdamW, clip 0.1, bf16 autocast)",
+           "images_per_gpu": B, "patched_modules": counts, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
+    for name, m in arms.items():
+        opt = MH.build_optimizer(m, "m")
+        run = m
+        if dist_on:
+            from torch.nn.parallel import DistributedDataParallel as DDP
+            run = DDP(m, device_ids=[device.index], output_device=device.index, find_unused_parameters=False)
+        loss_host = torch.zeros(1).pin_memory()
+
+        def step(run=run, opt=opt):
+            img = host_images.to(device, non_blocking=True)
+            tg = [{k: v.to(device, non_blocking=True) for k, v in t.items()} for t in host_targets]
+            _, _, loss = MH.train_step(run, loss_fn, img, tg, torch.bfloat16, optimizer=opt)
+            loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+
+        n0 = ops.LAUNCHES["count"]
+        ms = timed(step, steps, warmup)
+        res[name] = {"ms_per_step": ms, "imgs_per_s": B * world / (ms / 1e3),
+                     "dfine_b200_launches_per_step": (ops.LAUNCHES["count"] - n0) // (steps + warmup),
+                     "loss_after": float(loss_host)}
+        if name == "patched":
+            ops.enable_kernel_timers(True)
+            step()
+            torch.cuda.synchronize(device)
+            tm = ops.kernel_timers()
+            hot = {k: sum(s.elapsed_time(e) for s, e in v) for k, v in tm.items()}
+            ops.enable_kernel_timers(False)
+            res[name]["hot_path_kernel_ms_per_step"] = sum(hot.values())
+            res[name]["hot_path_kernels_ms"] = hot
+        del opt, run
+    res["speedup"] = res["patched"]["imgs_per_s"] / res["reference"]["imgs_per_s"]
+    out["train_config3"] = res
+    del model, patched, arms
+    torch.cuda.empty_cache()
+
+    # ---- config 2: D-FINE-s inference, 640x640, batch 64, bf16 autocast (rank 0 only does not matter:
+    #      inference needs no collective, every rank runs its own batch) ----
+    B = 64
+    model, _ = MH.build("s", device, 640, False, seed=0)
+    model.eval()
+    patched = copy.deepcopy(model)
+    dfine_b200.patch_model(patched)
+    images, _ = MH.synthetic_batch(B, 640, "cpu", seed=rank_seed(rank))
+    host_images = images.pin_memory()
+    res = {"workload": "dfine_s_infer_640_b64 (full model, eval, no_grad, bf16 autocast)", "images_per_gpu": B,
+           "h2d_bytes_per_step": host_images.numel() * 4}
+    for name, m in {"reference": model, "patched": patched}.items():
+        box_host = torch.empty(B, 300, 4).pin_memory()
+        logit_host = torch.empty(B, 300, 80).pin_memory()
+
+        def step(m=m):
+            o = MH.infer_step(m, host_images.to(device, non_blocking=True), torch.bfloat16)
+            box_host.copy_(o["pred_boxes"], non_blocking=True)
+            logit_host.copy_(o["pred_logits"], non_blocking=True)
+
+        ms = timed(step, steps, warmup)
+        res[name] = {"ms_per_step": ms, "imgs_per_s": B * world / (ms / 1e3)}
+    res["d2h_bytes_per_step"] = (box_host.numel() + logit_host.numel()) * 4
+    res["speedup"] = res["patched"]["imgs_per_s"] / res["reference"]["imgs_per_s"]
+    out["infer_config2"] = res
+    return out
+
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
 
@@ -632,6 +739,9 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=4, help="images per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager", action="store_true", help="skip the eager-PyTorch GPU bar")
+    ap.add_argument("--no-full-model", action="store_true",
+                    help="skip the full-model legs (reference model patched / unpatched on this GPU)")
+    ap.add_argument("--full-model-steps", type=int, default=8)
     ap.add_argument("--no-secondary", action="store_true",
                     help="skip the kernel-level legs at the other BASELINE configs")
     ap.add_argument("--grad-sync", default="eager", choices=["eager", "off"],
@@ -698,6 +808,15 @@ def main():
     ops.enable_kernel_timers(False)
     # ---- kernel leg: each kernel of a layer launched back to back (device-bound timing) ----
     kms = kernel_leg(wl, hp, device)
+    full_model = None
+    if not args.no_full_model:
+        try:
+            full_model = full_model_leg(device, rank, world, dist_on, args.full_model_steps, 3)
+        except Exception as exc:  # noqa: BLE001  (must not take the bench line down)
+            import traceback
+            full_model = {"error": f"{type(exc).__name__}: {exc}"[:300], "where": traceback.format_exc()[-400:]}
+            if dist_on:   # keep the ranks in step for the teardown
+                torch.cuda.synchronize(device)
     clocks = sampler.stop() if sampler else None
     other = None
     if rank == 0 and world == 1 and not args.no_secondary:
@@ -768,6 +887,8 @@ def main():
                 "serial_ms_per_step": ms_e2e_serial / args.steps},
         "gpu_launches": launches, "roofline": roofline, "clocks": clocks,
     }
+    if full_model is not None:   # the real model, patched vs unpatched, on this GPU
+        out["full_model"] = full_model
     if other is not None:   # kernel-level legs at configs 2 / 4 / 5 and the config-2 inference step
         out["other_configs_kernel_level"] = other
 

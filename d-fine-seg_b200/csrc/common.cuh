@@ -4,9 +4,28 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "dfine_b200.h"
 
 namespace dfine {
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device (per-context) setting: a process that
+// drives several GPUs must opt in on each of them.  One bit per device ordinal, written atomically (the
+// forward thread and autograd's backward threads may race here).
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> mask{0ull};
+  bool done() const {
+    int d = 0;
+    cudaGetDevice(&d);
+    return d < 64 && ((mask.load(std::memory_order_acquire) >> d) & 1ull);
+  }
+  void mark() {
+    int d = 0;
+    cudaGetDevice(&d);
+    if (d < 64) mask.fetch_or(1ull << d, std::memory_order_release);
+  }
+};
 
 constexpr int kWarpsPerCta = 8;
 constexpr int kMaxPoints = DFINE_MAX_POINTS;
@@ -52,15 +71,17 @@ struct Geometry {
 };
 
 // Bit-exact restatement of  g = 2*loc - 1  (arch/utils.py:215) followed by ATen's
-// grid_sampler_unnormalize ((g+1)*size-1)/2 (ATen/native/GridSampler.h:27-36), floor and
-// the CPU kernel's fractional weights.  __f*_rn intrinsics are never contracted into
-// FMAs, so the corner indices equal the oracle's (oracle/dfine_oracle.c) bit for bit.
+// grid_sampler_unnormalize ((g+1)*size-1)/2 (ATen/native/cuda/GridSampler.cuh:23-31), floor and the
+// fractional weights.  The shipped ATen kernels (CUDA: FADD, FFMA size*(g+1)-1, FMUL 0.5; CPU: vfmsub
+// with size/2 and 0.5) round the multiply-subtract ONCE; the explicit __fmaf_rn reproduces that, every
+// other step uses __f*_rn intrinsics that are never contracted, so the corner indices equal ATen's
+// and the oracle's (oracle/dfine_oracle.c) bit for bit -- also within an ulp of a pixel centre.
 __device__ __forceinline__ Geometry sample_geometry(float lx, float ly, int h, int w) {
   Geometry g;
   const float gx = __fsub_rn(__fmul_rn(2.0f, lx), 1.0f);
   const float gy = __fsub_rn(__fmul_rn(2.0f, ly), 1.0f);
-  const float ix = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.0f), (float)w), 1.0f), 0.5f);
-  const float iy = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.0f), (float)h), 1.0f), 0.5f);
+  const float ix = __fmul_rn(__fmaf_rn(__fadd_rn(gx, 1.0f), (float)w, -1.0f), 0.5f);
+  const float iy = __fmul_rn(__fmaf_rn(__fadd_rn(gy, 1.0f), (float)h, -1.0f), 0.5f);
   const float xw = floorf(ix), yn = floorf(iy);
   g.fw = __fsub_rn(ix, xw);
   g.fe = __fsub_rn(1.0f, g.fw);

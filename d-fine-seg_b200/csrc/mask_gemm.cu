@@ -318,15 +318,15 @@ int launch_mask_gemm(const void* coef, const void* proto, void* out, int B, int 
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long tiles = (long long)B * ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BLOCK_N - 1) / BLOCK_N);
   const int grid = (int)(tiles < sms ? tiles : sms);
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (!configured.done()) {
     cudaError_t e = cudaFuncSetAttribute(mask_gemm_kernel<true>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(mask_gemm_kernel<false>,
                                cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
-    configured = true;
+    configured.mark();
   }
   if (obf) {
     mask_gemm_kernel<true><<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, map_o, B, M, K, N,

@@ -495,11 +495,11 @@ int launch_msda_bwd_value(const MsdaParams& p, void* grad_value, int gv_bf16, in
   // nothing but the launch itself happens under CUDA-graph capture)
 #define DFINE_BV_LAUNCH5(C, GT, V, ST, OB, AC)                                                   \
   do {                                                                                           \
-    static bool configured = false;                                                              \
-    if (!configured) {                                                                           \
+    static PerDeviceOnce configured;                                                                     \
+    if (!configured.done()) {                                                                           \
       e = cudaFuncSetAttribute(msda_bwd_value_kernel<C, GT, V, ST, OB, AC>,                      \
                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit);    \
-      configured = e == cudaSuccess;                                                             \
+      if (e == cudaSuccess) configured.mark();                                                             \
     }                                                                                            \
     if (e == cudaSuccess)                                                                        \
       msda_bwd_value_kernel<C, GT, V, ST, OB, AC><<<grid, kBvThreads, smem, s>>>(                \

@@ -215,11 +215,11 @@ static int launch_fwd_tiled_t(MsdaParams& p, int value_dtype, cudaStream_t s) {
   cudaError_t e = cudaSuccess;
 #define DFINE_FT_LAUNCH(KP)                                                                      \
   do {                                                                                           \
-    static bool configured = false;                                                              \
-    if (!configured) {                                                                           \
+    static PerDeviceOnce configured;                                                                     \
+    if (!configured.done()) {                                                                           \
       e = cudaFuncSetAttribute(msda_fwd_tiled_kernel<VT, LPC, KP>,                               \
                                cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);         \
-      configured = e == cudaSuccess;                                                             \
+      if (e == cudaSuccess) configured.mark();                                                             \
     }                                                                                            \
     if (e == cudaSuccess)                                                                        \
       msda_fwd_tiled_kernel<VT, LPC, KP><<<grid, kTiledWarps * 32, smem, s>>>(p, maps, region,   \

@@ -266,12 +266,12 @@ int launch_linear_wgrad(const void* gy, int64_t gy_rs, const void* x, int64_t x_
   int splits = sms / n_tiles;
   if (splits > m_blocks) splits = m_blocks;
   if (splits < 1) splits = 1;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (!configured.done()) {
     const cudaError_t e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
-    configured = true;
+    configured.mark();
   }
   cudaError_t e = cudaMemsetAsync(dw_db, 0, ((size_t)N * K + N) * sizeof(float), s);
   if (e != cudaSuccess) return (int)e;

@@ -120,11 +120,16 @@ def _integral_forward(self, x, project):
 def _mask_logits_from_h(self, h, mask_feat):
     """DFINETransformer._mask_logits_from_h (reference dfine_decoder.py:937-940)."""
     mask_embed = self.mask_head(h)
-    use_tc = (mask_embed.is_cuda and mask_embed.shape[-1] % 64 == 0
-              and mask_embed.shape[-1] <= 512 and (mask_feat.shape[-1] * mask_feat.shape[-2]) % 8 == 0
-              and (torch.is_autocast_enabled() or mask_embed.dtype == torch.bfloat16))
+    # the tensor-core kernel computes in bfloat16: taken under bf16 autocast (or for bf16 tensors with
+    # autocast off); float16 autocast and fp32 keep the reference's own contraction and dtype
+    if torch.is_autocast_enabled():
+        bf16 = torch.get_autocast_dtype("cuda") == torch.bfloat16
+    else:
+        bf16 = mask_embed.dtype == torch.bfloat16 and mask_feat.dtype == torch.bfloat16
+    use_tc = (bf16 and mask_embed.is_cuda and mask_embed.shape[-1] % 64 == 0
+              and mask_embed.shape[-1] <= 512 and (mask_feat.shape[-1] * mask_feat.shape[-2]) % 8 == 0)
     if not use_tc:
-        # fp32 (non-AMP) contraction stays a plain library GEMM, exactly as in the reference
+        # fp32 (non-AMP) / fp16 contraction stays a plain library GEMM, exactly as in the reference
         return torch.einsum("bqc,bchw->bqhw", mask_embed, mask_feat)
     return ops.mask_logits(mask_embed, mask_feat)
 

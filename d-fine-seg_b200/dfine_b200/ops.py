@@ -124,6 +124,8 @@ def memory_from_value(value: Union[torch.Tensor, Sequence[torch.Tensor]], spec: 
         B, L, H, c = value.shape
         if L != spec.L:
             raise ValueError(f"value length {L} != sum(h*w) = {spec.L}")
+        if value.dtype not in _DT:
+            value = _supported_memory(value)
         return value.reshape(B, L, H * c), H, c, True
     views = list(value)
     if len(views) != spec.n_lvl:
@@ -148,10 +150,32 @@ def memory_from_value(value: Union[torch.Tensor, Sequence[torch.Tensor]], spec: 
                 ok = False
                 break
     if ok:
-        return base, H, c, True
+        return _supported_memory(base), H, c, True
     # generic (slow) path: one packing copy, autograd flows through the views
     mem = torch.cat([v.permute(0, 3, 1, 2) for v in views], dim=1)  # [B, L, H, c]
-    return mem.reshape(B, spec.L, C), H, c, False
+    mem = mem.reshape(B, spec.L, C)
+    return (mem if mem.dtype in _DT else mem.float()), H, c, False
+
+
+# float16 route (the reference trainer's default AMP dtype: `autocast(device)` without a dtype is
+# float16 on CUDA, src/dl/train.py:545-551).  The kernels read float32 / bfloat16 values; a float16
+# `memory` is widened to float32 ONCE per forward -- exactly the cast grid_sample's autocast-to-fp32
+# rule makes the reference do per layer and level -- and every decoder layer of that forward shares
+# the widened tensor (and therefore one gradient hub).  Single entry: it is replaced by the next
+# forward and dropped when the hub has delivered the gradient.
+_WIDENED = {}
+
+
+def _supported_memory(base: torch.Tensor) -> torch.Tensor:
+    if base.dtype in _DT:
+        return base
+    key = (id(base), base._version, torch.is_grad_enabled(), base.data_ptr())
+    ent = _WIDENED.get("entry")
+    if ent is not None and ent[0] == key and ent[1]() is base:
+        return ent[2]
+    wide = base.float()
+    _WIDENED["entry"] = (key, weakref.ref(base), wide)
+    return wide
 
 
 # --------------------------------------------------------------------------------------
@@ -414,6 +438,7 @@ class _MemoryHubFn(torch.autograd.Function):
         if ev is not None and buf is not None:   # grad_value kernels ran on the side stream
             torch.cuda.current_stream(buf.device).wait_event(ev)
         ctx.sess.pop("keep", None)
+        _WIDENED.pop("entry", None)
         return buf, None, None
 
 
@@ -582,7 +607,7 @@ class _PackedLinearFn(torch.autograd.Function):
     def forward(ctx, x, w0, b0, w1, b1):
         cdt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x.dtype
         if cdt not in _DT:
-            cdt = torch.float32
+            raise TypeError(f"packed_linear: compute dtype {cdt} not supported (see packed_linear_supported)")
         n0, n1, K = w0.shape[0], w1.shape[0], w0.shape[1]
         w = torch.empty((n0 + n1, K), dtype=cdt, device=x.device)
         b = torch.empty((n0 + n1,), dtype=cdt, device=x.device)
@@ -614,6 +639,9 @@ class _PackedLinearFn(torch.autograd.Function):
 
 
 def packed_linear_supported(x, w0, b0, w1, b1) -> bool:
+    cdt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x.dtype
+    if cdt not in _DT:      # float16 autocast: the Linear runs in float16 like the reference's (fused_linear)
+        return False
     return all(t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() for t in (w0, b0, w1, b1)) \
         and x.is_cuda and w0.shape[1] == w1.shape[1]
 

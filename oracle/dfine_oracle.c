@@ -43,13 +43,25 @@ typedef struct {
   int32_t w, h;
 } oracle_corner_t;
 
-/* arch/utils.py:215 (2*loc-1) followed by ATen's unnormalise + floor + bounds. */
+/* arch/utils.py:215 (2*loc-1) followed by ATen's unnormalise + floor + bounds.
+ *
+ * The unnormalise ((g+1)*size-1)/2 (ATen/native/GridSampler.h:27-36, cuda/GridSampler.cuh:23-31) is
+ * executed by BOTH shipped ATen kernels with the multiply-subtract fused into one rounding:
+ *   - CUDA grid_sampler_2d_kernel<float,int> (sm_100 SASS of torch 2.11.0+cu128, libtorch_cuda
+ *     cubin 1503):  FADD t = g + 1 ;  FFMA t = size * t - 1 ;  FMUL ix = t * 0.5
+ *   - CPU vectorised kernel (GridSamplerKernel.cpp ComputeLocation::unnormalize,
+ *     (in + 1) * (size/2) - 0.5 compiled to vfmsub): the same real number rounded once.
+ * Scaling by 0.5 commutes with rounding, so the two are the same float; a separately rounded
+ * product differs from them by one ulp for positions within an ulp of a pixel centre, which
+ * flips floor() -- exactly the positions a freshly initialised D-FINE decoder samples (its offset
+ * bias puts whole point rings on pixel centres).  fmaf() keeps the single rounding under
+ * -ffp-contract=off.  Pinned by tests/golden/core_near_centre.npz. */
 static void oracle_geometry(float locx, float locy, int32_t h, int32_t w, int32_t start,
                             oracle_corner_t* g) {
   float gx = 2.0f * locx - 1.0f;
   float gy = 2.0f * locy - 1.0f;
-  float ix = ((gx + 1.0f) * (float)w - 1.0f) / 2.0f;
-  float iy = ((gy + 1.0f) * (float)h - 1.0f) / 2.0f;
+  float ix = fmaf(gx + 1.0f, (float)w, -1.0f) * 0.5f;
+  float iy = fmaf(gy + 1.0f, (float)h, -1.0f) * 0.5f;
   float xw = floorf(ix), yn = floorf(iy);
   float fw = ix - xw, fe = 1.0f - fw, fn = iy - yn, fs = 1.0f - fn;
   g->wt[0] = fs * fe;

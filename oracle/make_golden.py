@@ -121,6 +121,41 @@ def case_edge(ref):
                      attn_override=attn)
 
 
+def case_near_centre(ref):
+    """Positions within a few ulps of pixel centres at the real 640^2 level sizes (80, 40, 20): there the
+    unnormalise ((g+1)*size-1)/2 gives floor() one value when the multiply-subtract is rounded once (what
+    the shipped ATen kernels execute: FFMA on CUDA, vfmsub on CPU) and another when it is rounded twice.
+    The gradient wrt the location and the touched pixels of grad_memory expose the chosen cell.  A freshly
+    initialised decoder samples exactly such positions (offset bias rings on pixel centres)."""
+    shapes, npts, H, c = [[80, 80], [40, 40], [20, 20]], [4, 4, 4], 2, 16
+    per_level = []
+    for (h, w) in shapes:
+        xs = []
+        for k in range(w):
+            base = np.float32((k + 0.5) / w)
+            for d in range(-3, 4):
+                v = base
+                for _ in range(abs(d)):
+                    v = np.nextafter(v, np.float32(2.0 if d > 0 else -2.0), dtype=np.float32)
+                xs.append(float(v))
+        per_level.append(xs)
+    n = max(len(x) for x in per_level)
+    Lq = (n + 3) // 4
+    loc = torch.full((1, Lq, H, 12, 2), 0.5)
+    for lvl, xs in enumerate(per_level):
+        for i, x in enumerate(xs):
+            q, p = divmod(i, 4)
+            # head 0: x sweeps the near-centre values, y sits mid-cell; head 1: the transpose
+            loc[0, q, 0, lvl * 4 + p, 0] = x
+            loc[0, q, 0, lvl * 4 + p, 1] = xs[(i * 7 + 3) % len(xs)] * 0.5 + 0.2
+            loc[0, q, 1, lvl * 4 + p, 1] = x
+            loc[0, q, 1, lvl * 4 + p, 0] = xs[(i * 5 + 1) % len(xs)] * 0.5 + 0.3
+    g = torch.Generator().manual_seed(78)
+    attn = torch.softmax(torch.randn(1, Lq, H, 12, generator=g), -1)
+    return case_core(ref, "core_near_centre", 6, 1, Lq, H, c, shapes, npts, loc_override=loc,
+                     attn_override=attn)
+
+
 def case_probe(ref):
     """Which pixels does aten::grid_sampler_2d touch?  One sample per (image, head):
     the non-zeros of grad_input are the in-bounds corners, their values the weights."""
@@ -243,6 +278,7 @@ def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
     ap.add_argument("--out", default=os.path.join(os.path.dirname(__file__), "..", "tests", "golden"))
+    ap.add_argument("--only", default=None, help="comma-separated fixture names to (re)write; default all")
     a = ap.parse_args()
     torch.set_num_threads(1)
     torch.use_deterministic_algorithms(True)
@@ -253,6 +289,7 @@ def main() -> None:
         case_core(ref, "core_n_small", 2, 1, 30, 8, 16, [[10, 10], [5, 5]], [6, 6]),
         case_core(ref, "core_x444", 3, 1, 20, 8, 32, [[16, 16], [8, 8], [4, 4]], [4, 4, 4]),
         case_edge(ref),
+        case_near_centre(ref),
         case_probe(ref),
         case_module(ref, "module_m_small", 11, 2, 33, 256, 8, [[12, 16], [6, 8], [3, 4]], [3, 6, 3]),
         case_module(ref, "module_n_small", 12, 1, 21, 128, 8, [[10, 12], [5, 6]], [6, 6]),
@@ -260,6 +297,8 @@ def main() -> None:
         case_mask(ref),
     ]
     for name, arrs in cases:
+        if a.only and name not in a.only.split(","):
+            continue
         p = os.path.join(a.out, name + ".npz")
         np.savez_compressed(p, **arrs)
         print(f"{name}: {os.path.getsize(p) / 1024:.0f} KiB")

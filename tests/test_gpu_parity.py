@@ -14,7 +14,7 @@ from util import BF16_RTOL, FP32_RTOL, assert_close, bf16_bits_to_f32, golden, r
 
 pytestmark = pytest.mark.gpu
 
-CORE_CASES = ["core_m_small", "core_n_small", "core_x444", "core_edge"]
+CORE_CASES = ["core_m_small", "core_n_small", "core_x444", "core_edge", "core_near_centre"]
 
 
 @pytest.fixture(scope="module")
@@ -237,6 +237,40 @@ def test_aten_cuda_probe_indices(dev):
     assert not (aten_nz & ~touched).any(), "ATen touched a pixel outside our corner set"
     assert np.array_equal(aten_nz, g["grad_input"] != 0), "ATen CUDA and ATen CPU disagree"
     assert_close(o[0, :, 0].cpu().numpy(), g["out"], FP32_RTOL, "probe out")
+
+
+def test_aten_cuda_near_centre_cells(dev):
+    """Within a few ulps of a pixel centre the cell floor() picks depends on how the unnormalise
+    ((g+1)*size-1)/2 is rounded.  ATen's CUDA kernel fuses the multiply-subtract (FFMA); the kernel must
+    pick the SAME cell as aten::grid_sampler_2d running on this GPU, at the real level sizes."""
+    import dfine_b200.ops as ops
+    for S in (80, 40, 20, 128, 64, 32):
+        xs = []
+        for k in range(S):
+            base = np.float32((k + 0.5) / S)
+            for d in range(-4, 5):
+                v = base
+                for _ in range(abs(d)):
+                    v = np.nextafter(v, np.float32(2.0 if d > 0 else -2.0), dtype=np.float32)
+                xs.append(v)
+        lx = torch.tensor(np.asarray(xs, np.float32), device=dev)
+        n = lx.numel()
+        loc = torch.stack([lx, torch.full_like(lx, 0.5)], -1)
+        # ATen on this GPU: d out / d ix over v[x] = (x+1)^2 identifies the cell
+        img = ((torch.arange(S, device=dev, dtype=torch.float32) + 1) ** 2).reshape(1, 1, 1, S)
+        grid = (2 * loc - 1).reshape(1, 1, n, 2).clone().requires_grad_(True)
+        torch.nn.functional.grid_sample(img, grid, mode="bilinear", padding_mode="zeros",
+                                        align_corners=False).sum().backward()
+        gix = (grid.grad.reshape(n, 2)[:, 0] / (S / 2)).cpu().numpy()
+        x0_aten = np.where(gix < 0, S - 1, np.round((gix - 3) / 2)).astype(np.int64)
+        spec = ops.level_spec([[1, S]], [1])
+        value = torch.ones(1, S, 16, device=dev)
+        _, idx = ops.msda_forward_raw(value, spec, 1, loc.reshape(1, n, 1, 1, 2).contiguous(),
+                                      torch.ones(1, n, 1, 1, device=dev), None, None, 0.5, False,
+                                      torch.float32, want_idx=True)
+        idx = idx.reshape(n, 4).cpu().numpy()
+        x0 = np.where(idx[:, 0] >= 0, idx[:, 0], idx[:, 1] - 1)
+        assert np.array_equal(x0, x0_aten), (S, np.nonzero(x0 != x0_aten)[0][:10])
 
 
 def test_fdr_golden(dev):

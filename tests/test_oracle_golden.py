@@ -9,7 +9,7 @@ import pytest
 from oracle import cpu_oracle as O
 from util import FP32_RTOL, assert_close, bf16_bits_to_f32, golden
 
-CORE_CASES = ["core_m_small", "core_n_small", "core_x444", "core_edge"]
+CORE_CASES = ["core_m_small", "core_n_small", "core_x444", "core_edge", "core_near_centre"]
 
 
 def _core_inputs(g):
