@@ -393,9 +393,23 @@ def secondary_kernel_legs(device, peak: float, reps: int = 10):
     proto = torch.randn(Bm, K, N, device=device, generator=g).to(torch.bfloat16)
     ms = timed(lambda: ops.mask_gemm_raw(coef, proto, torch.bfloat16, False))
     mbytes = Bm * (M * K * 2 + K * N * 2 + M * N * 2)
-    out["config4_mask_assembly_bf16"] = {"mask_gemm_fwd": {
-        "ms": ms, "algorithmic_bytes": mbytes, "frac": mbytes / (ms / 1e3) / 1e9 / peak,
-        "tflops": 2.0 * Bm * M * K * N / (ms / 1e3) / 1e12}}
+    flops = 2.0 * Bm * M * K * N
+    m4 = {"mask_gemm_fwd": {"ms": ms, "algorithmic_bytes": mbytes, "frac": mbytes / (ms / 1e3) / 1e9 / peak,
+                            "tflops": flops / (ms / 1e3) / 1e12}}
+    # the library bar for the same contraction, same run (cuBLAS batched GEMM through torch.bmm)
+    ms_lib = timed(lambda: torch.bmm(coef, proto))
+    m4["mask_gemm_fwd"]["cublas_bmm_ms"] = ms_lib
+    m4["mask_gemm_fwd"]["vs_cublas"] = ms_lib / ms
+    # backward: grad_proto = coef^T x go (reads go, writes [B, K, N]); grad_coef = go x proto^T (reads go + proto)
+    go = torch.randn(Bm, M, N, device=device, generator=g).to(torch.bfloat16)
+    for key, wc, wp, nbytes in (("mask_gemm_bwd_proto", False, True, Bm * (M * K * 2 + M * N * 2 + K * N * 2)),
+                                ("mask_gemm_bwd_coef", True, False, Bm * (M * N * 2 + K * N * 2 + M * K * 4))):
+        ms = timed(lambda: ops.mask_gemm_bwd_raw(coef, proto, go, want_coef=wc, want_proto=wp))
+        ms_lib = timed((lambda: torch.bmm(coef.transpose(1, 2), go)) if wp else
+                       (lambda: torch.bmm(go, proto.transpose(1, 2))))
+        m4[key] = {"ms": ms, "algorithmic_bytes": nbytes, "frac": nbytes / (ms / 1e3) / 1e9 / peak,
+                   "tflops": flops / (ms / 1e3) / 1e12, "cublas_bmm_ms": ms_lib, "vs_cublas": ms_lib / ms}
+    out["config4_mask_assembly_bf16"] = m4
     return out
 
 

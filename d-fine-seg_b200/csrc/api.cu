@@ -24,6 +24,8 @@ int launch_fdr(bool, const void*, int, const float*, const float*, const float*,
 int launch_pack_linear(const float*, const float*, int, const float*, const float*, int, int, void*, void*, int,
                        cudaStream_t);
 int launch_mask_gemm(const void*, const void*, void*, int, int, int, int, int, int, cudaStream_t);
+int launch_mask_gemm_bwd(const void*, const void*, const void*, float*, void*, int, int, int, int, int,
+                         cudaStream_t);
 int launch_colsum(const void*, int, long long, int, long long, float*, cudaStream_t);
 int launch_linear_wgrad(const void*, int64_t, const void*, int64_t, int, int, int, float*, cudaStream_t);
 
@@ -527,6 +529,40 @@ int dfine_mask_gemm_fwd(const void* coef, const void* proto, void* out, int B, i
   }
   return cuda_rc(launch_mask_gemm(coef, proto, out, B, M, K, N, out_dtype, apply_sigmoid,
                                   (cudaStream_t)stream), fn);
+}
+
+int dfine_mask_gemm_bwd(const void* coef, const void* proto, const void* grad_out, float* grad_coef,
+                        void* grad_proto, int B, int M, int K, int N, int gp_dtype, void* stream) {
+  const char* fn = "dfine_mask_gemm_bwd";
+  int rc;
+  if (B <= 0 || M <= 0 || K <= 0 || N <= 0) {
+    set_error("%s: B, M, K, N must be positive (got %d, %d, %d, %d)", fn, B, M, K, N);
+    return DFINE_E_SHAPE;
+  }
+  if (K % 128 || K > 256 || N % 8) {
+    set_error("%s: K must be a multiple of 128 and <= 256, N a multiple of 8 (got K=%d, N=%d)", fn, K, N);
+    return DFINE_E_UNSUPPORTED;
+  }
+  if (gp_dtype != DFINE_F32 && gp_dtype != DFINE_BF16) {
+    set_error("%s: gp_dtype must be DFINE_F32 or DFINE_BF16", fn);
+    return DFINE_E_UNSUPPORTED;
+  }
+  if (!grad_coef && !grad_proto) {
+    set_error("%s: grad_coef and grad_proto are both NULL", fn);
+    return DFINE_E_NULL;
+  }
+  if ((rc = require_device(grad_out, "grad_out", fn))) return rc;
+  if (grad_coef && (rc = require_device(proto, "proto", fn))) return rc;
+  if (grad_coef && (rc = require_device(grad_coef, "grad_coef", fn))) return rc;
+  if (grad_proto && (rc = require_device(coef, "coef", fn))) return rc;
+  if (grad_proto && (rc = require_device(grad_proto, "grad_proto", fn))) return rc;
+  if (!aligned16(grad_out) || (grad_coef && (!aligned16(proto) || !aligned16(grad_coef))) ||
+      (grad_proto && (!aligned16(coef) || !aligned16(grad_proto)))) {
+    set_error("%s: coef / proto / grad_out / grad_coef / grad_proto must be 16-byte aligned", fn);
+    return DFINE_E_ALIGN;
+  }
+  return cuda_rc(launch_mask_gemm_bwd(coef, proto, grad_out, grad_coef, grad_proto, B, M, K, N, gp_dtype,
+                                      (cudaStream_t)stream), fn);
 }
 
 }  // extern "C"

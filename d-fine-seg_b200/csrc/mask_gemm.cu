@@ -19,6 +19,15 @@
 //                               at the M / N edges by the tensor map).
 // The GEMM is HBM-write bound at D-FINE shapes: the double-buffered
 // accumulator lets the store of tile i overlap the MMAs of tile i+1.
+//
+// Backward (autograd of the einsum, dfine_decoder.py:940), same file, same pipeline:
+//   grad_proto[b, k, n] = sum_m coef[b, m, k] * go[b, m, n]   the forward kernel with operand A taken
+//       MN-major (kAMn): coef [M, K] is read as the [K x M] operand without a transpose pass, the
+//       reduction runs over the queries (rows past M are zero-filled by the tensor maps);
+//   grad_coef[b, m, k]  = sum_n go[b, m, n] * proto[b, k, n]  mask_dcoef_kernel: both operands K-major
+//       (the reduction index n is the contiguous one of go and of proto), a long reduction
+//       (N = h*w = 25600) into a small [M, K] result: split over n across the SMs, fp32 partial
+//       sums meet in L2 (red.global.add, like wgrad_gemm.cu).
 #include <cuda.h>
 
 #include "common.cuh"
@@ -46,10 +55,18 @@ constexpr int TMEM_COLS = 512;
 
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, A K-major,
 // B MN-major, N = 256, M = 128.
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (1u << 16) |
-                            ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+// a_mn / b_mn: the operand's contiguous dimension is its M / N dimension (not the reduction)
+__host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+constexpr int A_BOX_BYTES = 64 * BLOCK_K * 2;           // kAMn: one [64 reduction rows][64 m] box
 
-template <bool kOutBf16>
+// kAMn = false: A [M, K] K-major (forward: coef).  kAMn = true: A is stored [K, M] with M contiguous
+// (grad_proto: coef [queries, channels] read as the [channels x queries] operand); `M` is then the
+// number of channels (rows of the result) and `K` the number of queries (reduction, any value:
+// the last block is zero-filled by TMA).
+template <bool kOutBf16, bool kAMn>
 __global__ void __launch_bounds__(THREADS, 1)
 mask_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_o, int B, int M, int K, int N,
@@ -71,7 +88,7 @@ mask_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
   const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
   const int n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
-  const int k_blocks = K / BLOCK_K;
+  const int k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
   const long long tiles = (long long)B * m_tiles * n_tiles;
 
   if (threadIdx.x == 0) {
@@ -112,7 +129,13 @@ mask_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           mbar_expect_tx(fb, STAGE_BYTES);
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sb = sa + A_BYTES;
-          tma_load_3d(&map_a, sa, fb, kb * BLOCK_K, mt * BLOCK_M, b);
+          if (kAMn) {
+#pragma unroll
+            for (int j = 0; j < BLOCK_M / 64; ++j)
+              tma_load_3d(&map_a, sa + j * A_BOX_BYTES, fb, mt * BLOCK_M + j * 64, kb * BLOCK_K, b);
+          } else {
+            tma_load_3d(&map_a, sa, fb, kb * BLOCK_K, mt * BLOCK_M, b);
+          }
 #pragma unroll
           for (int j = 0; j < BLOCK_N / 64; ++j)
             tma_load_3d(&map_b, sb + j * B_BOX_BYTES, fb, nt * BLOCK_N + j * 64, kb * BLOCK_K, b);
@@ -142,11 +165,13 @@ mask_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // A: K-major SW128, 8-row groups 1024 B apart; +32 B per 16 k inside the row.
-            const uint64_t da = make_desc(sa + k * UMMA_K * 2, 16, 1024);
+            // (kAMn: MN-major like B, 64-m blocks A_BOX_BYTES apart)
+            const uint64_t da = kAMn ? make_desc(sa + k * UMMA_K * 128, A_BOX_BYTES, 1024)
+                                     : make_desc(sa + k * UMMA_K * 2, 16, 1024);
             // B: MN-major SW128, 64-n blocks B_BOX_BYTES apart (LBO), 8-k groups 1024 B
             // apart (SBO); +16 k rows = +2048 B.
             const uint64_t db = make_desc(sb + k * UMMA_K * 128, B_BOX_BYTES, 1024);
-            umma_bf16(tmem_d, da, db, kIdesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16(tmem_d, da, db, make_idesc(kAMn, true, BLOCK_N), (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(smem_u32(&empty_bar[stage]));  // smem stage free once these MMAs retire
           if (++stage == STAGES) {
@@ -254,6 +279,144 @@ mask_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// grad_coef[b, m, k] = sum_n go[b, m, n] * proto[b, k, n]
+// One CTA per (image, 128-row tile of queries, split of the n range); 192 threads, same roles
+// as above.  A = go box [128 m][64 n] (K-major), B = proto box [K channels][64 n] (K-major):
+// one tcgen05.mma M128 x N(K channels) x K16 per 16 n.  The fp32 tile is added to the
+// zero-filled result with row-contiguous vector reductions.
+// ---------------------------------------------------------------------------------------
+constexpr int DC_STG_ROW = 36;                             // floats per staged row: 32 + pad
+constexpr int DC_STG_BYTES = EPI_WARPS * 32 * DC_STG_ROW * 4;
+constexpr int DC_SMEM_BYTES = STAGES * STAGE_BYTES + DC_STG_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+__global__ void __launch_bounds__(THREADS, 1)
+mask_dcoef_kernel(const __grid_constant__ CUtensorMap map_go, const __grid_constant__ CUtensorMap map_p,
+                  float* __restrict__ out, int M, int Kc, int N, int m_tiles) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  float* smem_stg = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + DC_STG_BYTES);
+  uint64_t* full_bar = bars;                    // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;          // [STAGES]
+  uint64_t* tmem_full = bars + 2 * STAGES;      // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int mt = blockIdx.x % m_tiles, b = blockIdx.x / m_tiles;
+  // this CTA's share of the 64-wide blocks of the reduction range (never empty: the launcher
+  // keeps gridDim.y <= n_blocks)
+  const int n_blocks = (N + BLOCK_K - 1) / BLOCK_K;
+  const int nb0 = (int)((long long)blockIdx.y * n_blocks / gridDim.y);
+  const int nb1 = (int)((long long)(blockIdx.y + 1) * n_blocks / gridDim.y);
+  const uint32_t b_bytes = (uint32_t)Kc * BLOCK_K * 2;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(smem_u32(&full_bar[i]), 1);
+      mbar_init(smem_u32(&empty_bar[i]), 1);
+    }
+    mbar_init(smem_u32(tmem_full), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(tmem_slot)), "r"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_go) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_p) : "memory");
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int nb = nb0; nb < nb1; ++nb) {
+        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+        const uint32_t fb = smem_u32(&full_bar[stage]);
+        mbar_expect_tx(fb, A_BYTES + b_bytes);
+        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+        tma_load_3d(&map_go, sa, fb, nb * BLOCK_K, mt * BLOCK_M, b);
+        tma_load_3d(&map_p, sa + A_BYTES, fb, nb * BLOCK_K, 0, b);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t idesc = make_idesc(false, false, Kc);
+      for (int nb = nb0; nb < nb1; ++nb) {
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        tcgen05_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+        const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          // both operands K-major SW128: 8-row groups 1024 B apart; +32 B per 16 n inside the row
+          const uint64_t da = make_desc(sa + k * UMMA_K * 2, 16, 1024);
+          const uint64_t db = make_desc(sb + k * UMMA_K * 2, 16, 1024);
+          umma_bf16(tmem_base, da, db, idesc, (nb != nb0 || k != 0) ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&empty_bar[stage]));
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(smem_u32(tmem_full));
+    }
+  } else {
+    const int wq = warp & 3;
+    const int m0 = mt * BLOCK_M + wq * 32;   // first query row held by this warp
+    mbar_wait(smem_u32(tmem_full), 0);
+    tcgen05_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16);
+    float* stg = smem_stg + (warp - 2) * 32 * DC_STG_ROW;
+    float* dst = out + (size_t)b * M * Kc;
+    const int srow = lane >> 3, c4 = (lane & 7) * 4;
+    if (m0 < M) {
+      for (int c0 = 0; c0 < Kc; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c0, r);
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(stg + lane * DC_STG_ROW + 4 * j) =
+              make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        __syncwarp();
+        if (c0 + c4 < Kc) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + srow;
+            const float4 v = *reinterpret_cast<const float4*>(stg + rr * DC_STG_ROW + c4);
+            if (m0 + rr < M)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                           ::"l"(dst + (size_t)(m0 + rr) * Kc + c0 + c4), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                           : "memory");
+          }
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -268,6 +431,11 @@ static EncodeTiledFn get_encode_fn() {
             cudaSuccess &&
         q == cudaDriverEntryPointSuccess)
       fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  // cuTensorMapEncodeTiled is a DRIVER call: bind the primary context on this (autograd) thread
+  {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaSetDevice(dev);
   }
   return fn;
 }
@@ -285,6 +453,28 @@ static int encode_3d(EncodeTiledFn enc, CUtensorMap* map, CUtensorMapDataType dt
   if (r != CUDA_SUCCESS) {
     set_error("mask_gemm: cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
     return DFINE_E_SHAPE;
+  }
+  return 0;
+}
+
+static int sm_count() {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+
+template <bool kAMn>
+static int configure_gemm() {
+  static PerDeviceOnce configured;
+  if (!configured.done()) {
+    cudaError_t e = cudaFuncSetAttribute(mask_gemm_kernel<true, kAMn>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(mask_gemm_kernel<false, kAMn>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    configured.mark();
   }
   return 0;
 }
@@ -313,29 +503,84 @@ int launch_mask_gemm(const void* coef, const void* proto, void* out, int B, int 
                       obf ? 2 : 4, out, N, M, B, obf ? 64 : 32, 32, "out")))
     return rc;
 
-  int dev = 0, sms = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = sm_count();
   const long long tiles = (long long)B * ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BLOCK_N - 1) / BLOCK_N);
   const int grid = (int)(tiles < sms ? tiles : sms);
-  static PerDeviceOnce configured;
-  if (!configured.done()) {
-    cudaError_t e = cudaFuncSetAttribute(mask_gemm_kernel<true>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(mask_gemm_kernel<false>,
-                               cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e != cudaSuccess) return (int)e;
-    configured.mark();
-  }
+  if ((rc = configure_gemm<false>())) return rc;
   if (obf) {
-    mask_gemm_kernel<true><<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, map_o, B, M, K, N,
-                                                             apply_sigmoid);
+    mask_gemm_kernel<true, false><<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, map_o, B, M, K, N,
+                                                                    apply_sigmoid);
   } else {
-    mask_gemm_kernel<false><<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, map_o, B, M, K, N,
-                                                              apply_sigmoid);
+    mask_gemm_kernel<false, false><<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, map_o, B, M, K, N,
+                                                                     apply_sigmoid);
   }
   return (int)cudaGetLastError();
+}
+
+// Backward of the contraction.  coef bf16 [B, M, K], proto bf16 [B, K, N], go bf16 [B, M, N].
+//   grad_coef  float32 [B, M, K]  (zero-filled here, then accumulated) or NULL
+//   grad_proto gp_dtype [B, K, N] or NULL
+int launch_mask_gemm_bwd(const void* coef, const void* proto, const void* go, float* grad_coef,
+                         void* grad_proto, int B, int M, int K, int N, int gp_dtype, cudaStream_t s) {
+  using namespace mg;
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_error("mask_gemm_bwd: cuTensorMapEncodeTiled is not available from the CUDA driver");
+    return DFINE_E_UNSUPPORTED;
+  }
+  int rc;
+  const int sms = sm_count();
+  if (grad_proto) {
+    // result rows = channels (K), reduction = queries (M), columns = pixels (N)
+    alignas(64) CUtensorMap map_a, map_b, map_o;
+    if ((rc = encode_3d(enc, &map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, coef, K, M, B, 64, BLOCK_K,
+                        "coef (MN-major)")))
+      return rc;
+    if ((rc = encode_3d(enc, &map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, go, N, M, B, 64, BLOCK_K,
+                        "grad_out")))
+      return rc;
+    const bool obf = gp_dtype == DFINE_BF16;
+    if ((rc = encode_3d(enc, &map_o, obf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                        obf ? 2 : 4, grad_proto, N, K, B, obf ? 64 : 32, 32, "grad_proto")))
+      return rc;
+    const long long tiles = (long long)B * (K / BLOCK_M) * ((N + BLOCK_N - 1) / BLOCK_N);
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    if ((rc = configure_gemm<true>())) return rc;
+    if (obf)
+      mask_gemm_kernel<true, true><<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, map_o, B, K, M, N, 0);
+    else
+      mask_gemm_kernel<false, true><<<grid, THREADS, SMEM_BYTES, s>>>(map_a, map_b, map_o, B, K, M, N, 0);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+  }
+  if (grad_coef) {
+    alignas(64) CUtensorMap map_go, map_p;
+    if ((rc = encode_3d(enc, &map_go, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, go, N, M, B, BLOCK_K, BLOCK_M,
+                        "grad_out (K-major)")))
+      return rc;
+    if ((rc = encode_3d(enc, &map_p, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, proto, N, K, B, BLOCK_K,
+                        (uint32_t)K, "proto (K-major)")))
+      return rc;
+    static PerDeviceOnce configured;
+    if (!configured.done()) {
+      const cudaError_t e = cudaFuncSetAttribute(mask_dcoef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 DC_SMEM_BYTES);
+      if (e != cudaSuccess) return (int)e;
+      configured.mark();
+    }
+    cudaError_t e = cudaMemsetAsync(grad_coef, 0, (size_t)B * M * K * sizeof(float), s);
+    if (e != cudaSuccess) return (int)e;
+    const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+    const int n_blocks = (N + BLOCK_K - 1) / BLOCK_K;
+    int splits = sms / (B * m_tiles);
+    if (splits > n_blocks) splits = n_blocks;
+    if (splits < 1) splits = 1;
+    mask_dcoef_kernel<<<dim3(B * m_tiles, splits), THREADS, DC_SMEM_BYTES, s>>>(map_go, map_p, grad_coef, M, K, N,
+                                                                                m_tiles);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+  }
+  return 0;
 }
 
 }  // namespace dfine

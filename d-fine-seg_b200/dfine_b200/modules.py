@@ -128,6 +128,9 @@ def _mask_logits_from_h(self, h, mask_feat):
         bf16 = mask_embed.dtype == torch.bfloat16 and mask_feat.dtype == torch.bfloat16
     use_tc = (bf16 and mask_embed.is_cuda and mask_embed.shape[-1] % 64 == 0
               and mask_embed.shape[-1] <= 512 and (mask_feat.shape[-1] * mask_feat.shape[-2]) % 8 == 0)
+    if use_tc and torch.is_grad_enabled() and (mask_embed.requires_grad or mask_feat.requires_grad):
+        # training: the backward kernels take 128 | K <= 256 (every shipped mask head: 128 / 256)
+        use_tc = ops.mask_gemm_bwd_supported(mask_embed.shape[-1], mask_feat.shape[-1] * mask_feat.shape[-2])
     if not use_tc:
         # fp32 (non-AMP) / fp16 contraction stays a plain library GEMM, exactly as in the reference
         return torch.einsum("bqc,bchw->bqhw", mask_embed, mask_feat)

@@ -889,6 +889,31 @@ def mask_gemm_raw(coef: torch.Tensor, proto: torch.Tensor, out_dtype: torch.dtyp
     return out
 
 
+def mask_gemm_bwd_supported(K: int, N: int) -> bool:
+    return K % 128 == 0 and K <= 256 and N % 8 == 0
+
+
+def mask_gemm_bwd_raw(coef: torch.Tensor, proto: torch.Tensor, go: torch.Tensor, want_coef: bool = True,
+                      want_proto: bool = True, proto_dtype: Optional[torch.dtype] = None):
+    """Backward of the mask contraction on tcgen05 tensor cores (autograd of reference
+    dfine_decoder.py:940): grad_coef [B, M, K] (float32) = go x proto^T, grad_proto [B, K, N] = coef^T x go.
+    coef bf16 [B, M, K], proto bf16 [B, K, N], go bf16 [B, M, N]; returns (grad_coef | None, grad_proto | None)."""
+    _require_cuda(coef, proto, go)
+    B, M, K = coef.shape
+    N = proto.shape[2]
+    if go.dtype != torch.bfloat16 or coef.dtype != torch.bfloat16 or proto.dtype != torch.bfloat16:
+        raise TypeError("mask_gemm_bwd: coef, proto and grad_out must be bfloat16")
+    go = go.contiguous()
+    g_coef = torch.empty((B, M, K), dtype=torch.float32, device=coef.device) if want_coef else None
+    g_proto = torch.empty((B, K, N), dtype=proto_dtype or torch.bfloat16, device=coef.device) if want_proto else None
+    with torch.cuda.device_of(coef), _timed("mask_gemm_bwd", coef, kernels=int(want_coef) + int(want_proto)):
+        rc = _lib.lib().dfine_mask_gemm_bwd(coef.data_ptr(), proto.data_ptr(), go.data_ptr(), _ptr(g_coef),
+                                            _ptr(g_proto), B, M, K, N,
+                                            _dt(g_proto, "grad_proto") if want_proto else _lib.BF16, _stream(coef))
+    check(rc, "dfine_mask_gemm_bwd")
+    return g_coef, g_proto
+
+
 class _MaskFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, coef, proto, out_dtype, apply_sigmoid):
@@ -903,10 +928,11 @@ class _MaskFn(torch.autograd.Function):
         coef, proto, out = ctx.saved_tensors
         if ctx.apply_sigmoid:
             go = go * out * (1 - out)
-        go = go.to(torch.bfloat16)
-        # plain library GEMMs (cuBLAS) for the two gradient contractions
-        g_coef = torch.bmm(go, proto.transpose(1, 2))
-        g_proto = torch.bmm(coef.transpose(1, 2), go)
+        go = go.to(torch.bfloat16)          # the dtype autocast's bmm backward would compute in
+        want_coef, want_proto = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        g_coef, g_proto = mask_gemm_bwd_raw(coef, proto, go, want_coef, want_proto, proto.dtype)
+        if g_coef is not None:
+            g_coef = g_coef.to(coef.dtype)
         return g_coef, g_proto, None, None
 
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DFINE_B200_VERSION 102 /* major*100 + minor */
+#define DFINE_B200_VERSION 103 /* major*100 + minor */
 
 #if defined(__GNUC__)
 #define DFINE_API __attribute__((visibility("default")))
@@ -232,6 +232,19 @@ DFINE_API int dfine_fdr_bwd(const void* corners, int c_dtype, const float* ref_i
  * -------------------------------------------------------------------------- */
 DFINE_API int dfine_mask_gemm_fwd(const void* coef, const void* proto, void* out, int B, int M, int K,
                         int N, int out_dtype, int apply_sigmoid, void* stream);
+
+/* Backward of K4 (autograd of the einsum at dfine_decoder.py:940; replaces the two aten::bmm of
+ * its backward), both contractions on tcgen05 tensor cores:
+ *   grad_coef [b, m, k] = sum_n grad_out[b, m, n] * proto[b, k, n]
+ *   grad_proto[b, k, n] = sum_m coef[b, m, k] * grad_out[b, m, n]
+ * coef bf16 [B, M, K], proto bf16 [B, K, N], grad_out bf16 [B, M, N] (contiguous, 16-byte aligned).
+ * grad_coef   float32 [B, M, K]: zero-filled by the call, then accumulated with fp32 reductions over
+ *             the splits of n (summation order not fixed: fp32 rounding only); NULL to skip.
+ * grad_proto  gp_dtype [B, K, N] (bf16 under autocast); NULL to skip.
+ * K a multiple of 128 and <= 256, N a multiple of 8, M arbitrary (DFINE_E_UNSUPPORTED otherwise). */
+DFINE_API int dfine_mask_gemm_bwd(const void* coef, const void* proto, const void* grad_out,
+                        float* grad_coef, void* grad_proto, int B, int M, int K, int N, int gp_dtype,
+                        void* stream);
 
 #ifdef __cplusplus
 }

@@ -193,6 +193,18 @@ def mask_gemm(coef, proto, apply_sigmoid: bool = False) -> np.ndarray:
     return out.reshape(B, M, *tail)
 
 
+def mask_gemm_bwd(coef, proto, grad_out):
+    """Gradients of out[b,m,n] = sum_k coef[b,m,k] proto[b,k,n] (autograd of the einsum at reference
+    src/d_fine/arch/dfine_decoder.py:940): grad_coef = grad_out x proto^T, grad_proto = coef^T x grad_out.
+    Plain float64 numpy (test infrastructure: the checker of dfine_mask_gemm_bwd)."""
+    coef, proto, go = (np.asarray(a, dtype=np.float64) for a in (coef, proto, grad_out))
+    B, M, K = coef.shape
+    tail = proto.shape[2:]
+    p = proto.reshape(B, K, -1)
+    g = go.reshape(B, M, -1)
+    return np.einsum("bmn,bkn->bmk", g, p), np.einsum("bmk,bmn->bkn", coef, g).reshape(B, K, *tail)
+
+
 def linear_wgrad(grad_y: np.ndarray, x: np.ndarray):
     """Weight and bias gradient of y = x W^T + b (autograd of the two nn.Linear of MSDeformableAttention,
     reference src/d_fine/arch/dfine_decoder.py:87-88, :139-147): dW = grad_y^T x, db = sum over the rows of

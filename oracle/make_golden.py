@@ -263,6 +263,21 @@ def case_mask(ref):
                         probs=torch.sigmoid(logits).numpy())
 
 
+def case_mask_bwd(ref):
+    """Gradients of the reference's mask contraction (autograd of dfine_decoder.py:940) for a
+    bf16-representable upstream gradient: what the two backward tensor-core contractions must return."""
+    g = torch.Generator().manual_seed(32)
+    B, Q, C, Hm, Wm = 2, 37, 128, 12, 20
+    h = bf16r(torch.randn(B, Q, C, generator=g)).requires_grad_(True)
+    feat = bf16r(torch.randn(B, C, Hm, Wm, generator=g)).requires_grad_(True)
+    go = bf16r(torch.randn(B, Q, Hm, Wm, generator=g))
+    stub = types.SimpleNamespace(mask_head=torch.nn.Identity())
+    logits = ref.DFINETransformer._mask_logits_from_h(stub, h, feat)
+    logits.backward(go)
+    return "mask_bwd", dict(coef=h.detach().numpy(), proto=feat.detach().numpy(), grad_out=go.numpy(),
+                            logits=logits.detach().numpy(), grad_coef=h.grad.numpy(), grad_proto=feat.grad.numpy())
+
+
 def load_reference(path: str):
     sys.path.insert(0, path)
     from src.d_fine.arch import dfine_decoder as dd  # noqa: E402
@@ -295,6 +310,7 @@ def main() -> None:
         case_module(ref, "module_n_small", 12, 1, 21, 128, 8, [[10, 12], [5, 6]], [6, 6]),
         case_fdr(ref),
         case_mask(ref),
+        case_mask_bwd(ref),
     ]
     for name, arrs in cases:
         if a.only and name not in a.only.split(","):

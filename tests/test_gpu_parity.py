@@ -10,7 +10,8 @@ import numpy as np
 import pytest
 import torch
 
-from util import BF16_RTOL, FP32_RTOL, assert_close, bf16_bits_to_f32, golden, rel_err
+from util import (BF16_RTOL, FP32_RTOL, assert_close, assert_close_elementwise, bf16_bits_to_f32, elementwise_err,
+                  golden, rel_err)
 
 pytestmark = pytest.mark.gpu
 
@@ -441,11 +442,71 @@ def test_mask_gemm(dev):
         assert rel_err(got.cpu().numpy(), want.cpu().numpy()) <= 2e-5, (B, M, K, N)
         gotb = ops.mask_gemm_raw(a, b, torch.bfloat16, False)
         assert rel_err(gotb.float().cpu().numpy(), want.cpu().numpy()) <= BF16_RTOL, (B, M, K, N)
-    # autograd (gradients are plain cuBLAS GEMMs)
-    a = torch.randn(2, 50, 64, device=dev, requires_grad=True)
-    b = torch.randn(2, 64, 8, 16, device=dev, requires_grad=True)
-    dfine_b200.mask_logits(a, b, out_dtype=torch.float32).sum().backward()
-    assert a.grad.shape == a.shape and b.grad.shape == b.shape
+
+
+def test_mask_gemm_backward(dev):
+    """dfine_mask_gemm_bwd (both contractions on tcgen05) against the reference's gradients (golden,
+    autograd of the einsum at dfine_decoder.py:940), against the oracle and against fp32 bmm at the
+    config-4 shapes (Q = 300 regular / 200 denoising / 500 bench queries; ragged M and N edges)."""
+    import dfine_b200
+    import dfine_b200.ops as ops
+    from oracle import cpu_oracle as O
+    g = golden("mask_bwd")
+    coef = _t(g["coef"], dev).requires_grad_(True)
+    proto = _t(g["proto"], dev).requires_grad_(True)
+    out = dfine_b200.mask_logits(coef, proto, out_dtype=torch.float32)
+    assert_close(out.detach().cpu().numpy(), g["logits"], 2e-5, "mask logits (K = 128)")
+    out.backward(_t(g["grad_out"], dev))
+    # through autograd the gradients pass through bf16 (mask_logits casts its operands to bf16, as autocast
+    # does for the reference's einsum): bf16 tolerance
+    assert coef.grad.dtype == torch.float32 and proto.grad.dtype == torch.float32
+    assert_close(coef.grad.cpu().numpy(), g["grad_coef"], BF16_RTOL, "grad_coef (golden, autograd)")
+    assert_close(proto.grad.cpu().numpy(), g["grad_proto"], BF16_RTOL, "grad_proto (golden, autograd)")
+    # the kernels themselves: inputs and grad_out are bf16-representable, so products are exact and the
+    # fp32 results differ from the reference's only by the accumulation order
+    cb, pb, gb = (_t(g[k], dev).to(torch.bfloat16) for k in ("coef", "proto", "grad_out"))
+    gc, gp = ops.mask_gemm_bwd_raw(cb, pb.flatten(2), gb.flatten(2), proto_dtype=torch.float32)
+    assert_close(gc.cpu().numpy(), g["grad_coef"], 2e-5, "grad_coef (golden)")
+    assert_close(gp.cpu().numpy().reshape(g["grad_proto"].shape), g["grad_proto"], 2e-5, "grad_proto (golden)")
+    torch.manual_seed(2)
+    for (B, M, K, N) in [(2, 500, 256, 160 * 160), (2, 300, 256, 160 * 160), (3, 200, 128, 1000), (1, 77, 128, 264),
+                         (16, 300, 256, 25600)]:
+        a = torch.randn(B, M, K, device=dev).to(torch.bfloat16)
+        b = torch.randn(B, K, N, device=dev).to(torch.bfloat16)
+        go = torch.randn(B, M, N, device=dev).to(torch.bfloat16)
+        # matched-rows-only upstream gradient (what the criterion sends: dfine_criterion.py:336)
+        if M == 300:
+            keep = torch.zeros(B, M, 1, device=dev, dtype=torch.bfloat16)
+            keep[:, ::29] = 1
+            go = go * keep
+        gc, gp = ops.mask_gemm_bwd_raw(a, b, go, proto_dtype=torch.float32)
+        # float64 reference: the kernels' only error is the fp32 accumulation order of a 25600- (grad_coef) or
+        # M-term (grad_proto) sum; elementwise bound |a-b| <= 2e-5 (|b| + RMS)
+        want_c = torch.bmm(go.double(), b.double().transpose(1, 2))
+        want_p = torch.bmm(a.double().transpose(1, 2), go.double())
+        if M == 300:   # rows without an upstream gradient are exactly zero; the others are compared on their own scale
+            assert not gc[:, 1::29].any() and not gc[:, 2::29].any()
+            gc_c, want_cc = gc[:, ::29], want_c[:, ::29]
+        else:
+            gc_c, want_cc = gc, want_c
+        assert elementwise_err(gc_c.cpu().numpy(), want_cc.cpu().numpy(), 2e-5) <= 1.0, ("grad_coef", B, M, K, N)
+        assert elementwise_err(gp.cpu().numpy(), want_p.cpu().numpy(), 2e-5) <= 1.0, ("grad_proto", B, M, K, N)
+        assert rel_err(gc.cpu().numpy(), want_c.cpu().numpy()) <= 2e-5, ("grad_coef", B, M, K, N)
+        assert rel_err(gp.cpu().numpy(), want_p.cpu().numpy()) <= 2e-5, ("grad_proto", B, M, K, N)
+        if B * M * N <= 4_000_000:
+            oc, op = O.mask_gemm_bwd(a.float().cpu().numpy(), b.float().cpu().numpy(), go.float().cpu().numpy())
+            assert rel_err(gc.cpu().numpy(), oc) <= 2e-5 and rel_err(gp.cpu().numpy(), op) <= 2e-5
+        _, gpb = ops.mask_gemm_bwd_raw(a, b, go, want_coef=False)
+        assert gpb.dtype == torch.bfloat16
+        assert rel_err(gpb.float().cpu().numpy(), want_p.cpu().numpy()) <= BF16_RTOL
+        gc2, none = ops.mask_gemm_bwd_raw(a, b, go, want_proto=False)
+        assert none is None and torch.equal(gc2.isfinite(), gc.isfinite())
+        assert rel_err(gc2.cpu().numpy(), want_c.cpu().numpy()) <= 2e-5
+    # shapes the backward kernels do not take fail loudly (no silent library fallback)
+    a = torch.randn(1, 8, 64, device=dev).to(torch.bfloat16)
+    with pytest.raises(dfine_b200.DfineB200Error):
+        ops.mask_gemm_bwd_raw(a, torch.randn(1, 64, 16, device=dev).to(torch.bfloat16),
+                              torch.randn(1, 8, 16, device=dev).to(torch.bfloat16))
 
 
 def test_packed_linear_matches_two_linears(dev):

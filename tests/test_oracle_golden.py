@@ -118,6 +118,12 @@ def test_mask_assembly():
     g = golden("mask")
     assert_close(O.mask_gemm(g["coef"], g["proto"]), g["logits"], FP32_RTOL, "logits")
     assert_close(O.mask_gemm(g["coef"], g["proto"], True), g["probs"], FP32_RTOL, "probs")
+    # backward of the contraction (autograd of dfine_decoder.py:940)
+    g = golden("mask_bwd")
+    assert_close(O.mask_gemm(g["coef"], g["proto"]), g["logits"], FP32_RTOL, "logits (K=128)")
+    gc, gp = O.mask_gemm_bwd(g["coef"], g["proto"], g["grad_out"])
+    assert_close(gc, g["grad_coef"], FP32_RTOL, "grad_coef")
+    assert_close(gp, g["grad_proto"], FP32_RTOL, "grad_proto")
 
 
 def test_linear_wgrad_restatement_matches_torch_autograd():
