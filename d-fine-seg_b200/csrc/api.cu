@@ -24,6 +24,8 @@ int launch_fdr(bool, const void*, int, const float*, const float*, const float*,
 int launch_pack_linear(const float*, const float*, int, const float*, const float*, int, int, void*, void*, int,
                        cudaStream_t);
 int launch_mask_gemm(const void*, const void*, void*, int, int, int, int, int, int, cudaStream_t);
+int launch_lsap(const float*, long long, long long, long long, const int32_t*, int, int, long long*, long long*,
+                long long, cudaStream_t);
 int launch_mask_gemm_bwd(const void*, const void*, const void*, float*, void*, int, int, int, int, int,
                          cudaStream_t);
 int launch_colsum(const void*, int, long long, int, long long, float*, cudaStream_t);
@@ -563,6 +565,25 @@ int dfine_mask_gemm_bwd(const void* coef, const void* proto, const void* grad_ou
   }
   return cuda_rc(launch_mask_gemm_bwd(coef, proto, grad_out, grad_coef, grad_proto, B, M, K, N, gp_dtype,
                                       (cudaStream_t)stream), fn);
+}
+
+int dfine_lsap(const float* cost, int64_t stride_b, int64_t stride_q, int64_t stride_t, const int32_t* n_targets,
+               int B, int Q, int64_t* out_q, int64_t* out_t, int64_t out_stride, void* stream) {
+  const char* fn = "dfine_lsap";
+  int rc;
+  if (B <= 0 || Q <= 0 || out_stride <= 0) {
+    set_error("%s: B, Q and out_stride must be positive (got %d, %d, %lld)", fn, B, Q, (long long)out_stride);
+    return DFINE_E_SHAPE;
+  }
+  if (!n_targets) {
+    set_error("%s: n_targets (host) is NULL", fn);
+    return DFINE_E_NULL;
+  }
+  if ((rc = require_device(cost, "cost", fn))) return rc;
+  if ((rc = require_device(out_q, "out_q", fn))) return rc;
+  if ((rc = require_device(out_t, "out_t", fn))) return rc;
+  return cuda_rc(launch_lsap(cost, stride_b, stride_q, stride_t, n_targets, B, Q, (long long*)out_q,
+                             (long long*)out_t, out_stride, (cudaStream_t)stream), fn);
 }
 
 }  // extern "C"

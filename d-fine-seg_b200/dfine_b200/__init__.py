@@ -2,10 +2,12 @@
 
 Python here is host plumbing around the C-ABI library libdfine_b200.so
 (include/dfine_b200.h): multi-scale deformable attention forward / backward, the FDR box
-decode and the tcgen05 mask-prototype GEMM.  No CPU fallback exists.
+decode, the tcgen05 mask-prototype GEMM (forward and backward) and the criterion's Hungarian
+assignment on the device.  No CPU fallback exists.
 """
-from . import _lib, build, grad_sync, ops
+from . import _lib, build, criterion, grad_sync, ops
 from ._lib import DfineB200Error, library_path
+from .criterion import patch_criterion, unpatch_criterion
 from .modules import Integral, MSDeformableAttention, patch_model, unpatch_model
 from .ops import (fdr_decode, fdr_integral, fdr_project, mask_logits, msda_core, msda_fused,
                   msda_fused_packed)
@@ -13,6 +15,6 @@ from .ops import (fdr_decode, fdr_integral, fdr_project, mask_logits, msda_core,
 __all__ = [
     "MSDeformableAttention", "Integral", "patch_model", "unpatch_model", "msda_core",
     "msda_fused", "msda_fused_packed", "fdr_project", "fdr_integral", "fdr_decode", "mask_logits", "library_path",
-    "DfineB200Error", "ops", "build", "grad_sync",
+    "DfineB200Error", "ops", "build", "grad_sync", "criterion", "patch_criterion", "unpatch_criterion",
 ]
 __version__ = "0.1.0"

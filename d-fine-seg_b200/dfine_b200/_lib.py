@@ -52,6 +52,8 @@ _SIGNATURES = {
                                   c_void_p, c_int, c_void_p]),
     "dfine_mask_gemm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                     c_int, c_int, c_void_p]),
+    "dfine_lsap": (c_int, [c_void_p, c_int64, c_int64, c_int64, _I32P, c_int, c_int, c_void_p, c_void_p, c_int64,
+                           c_void_p]),
     "dfine_mask_gemm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                     c_int, c_int, c_void_p]),
 }

@@ -949,3 +949,29 @@ def mask_logits(coef: torch.Tensor, mask_feat: torch.Tensor, apply_sigmoid: bool
     b = mask_feat.to(torch.bfloat16).reshape(B, C, hh * ww).contiguous()
     out = _MaskFn.apply(a, b, out_dtype or torch.bfloat16, apply_sigmoid)
     return out.reshape(B, Q, hh, ww)
+
+
+# --------------------------------------------------------------------------------------
+# K5  Hungarian matching on the device
+# --------------------------------------------------------------------------------------
+def lsap(cost: torch.Tensor, n_targets: Sequence[int]):
+    """Batched rectangular assignment, index-identical to scipy.optimize.linear_sum_assignment applied
+    to torch.nan_to_num(cost[b, :, :n_targets[b]], nan=1.0) (reference src/d_fine/matcher.py:112-116).
+
+    cost: float32 CUDA tensor [B, Q, T] (any strides), n_targets: per-image target counts (host ints).
+    Returns (q_idx, t_idx): int64 CUDA tensors [B, K], K = max_b min(Q, n_targets[b]); pair k of image b is
+    (q_idx[b, k], t_idx[b, k]) in ascending query order, -1 beyond min(Q, n_targets[b])."""
+    _require_cuda(cost)
+    if cost.dtype != torch.float32 or cost.dim() != 3:
+        raise TypeError("lsap: cost must be a float32 tensor [B, Q, T]")
+    B, Q, T = cost.shape
+    n = [int(v) for v in n_targets]
+    if len(n) != B or any(v < 0 or v > T for v in n):
+        raise ValueError(f"lsap: n_targets must hold {B} counts in [0, {T}]")
+    K = max(1, max(min(Q, v) for v in n))
+    out = torch.empty((2, B, K), dtype=torch.int64, device=cost.device)
+    with torch.cuda.device_of(cost), _timed("lsap", cost):
+        rc = _lib.lib().dfine_lsap(cost.data_ptr(), cost.stride(0), cost.stride(1), cost.stride(2),
+                                   _lib.i32_array(n), B, Q, out[0].data_ptr(), out[1].data_ptr(), K, _stream(cost))
+    check(rc, "dfine_lsap")
+    return out[0], out[1]

@@ -246,6 +246,25 @@ DFINE_API int dfine_mask_gemm_bwd(const void* coef, const void* proto, const voi
                         float* grad_coef, void* grad_proto, int B, int M, int K, int N, int gp_dtype,
                         void* stream);
 
+/* --------------------------------------------------------------------------
+ * K5  Hungarian matching on the device (criterion host-sync removal).
+ *
+ * Replaces, per image,  C.cpu()  +  scipy.optimize.linear_sum_assignment(c[i])  of
+ * HungarianMatcher.forward (src/d_fine/matcher.py:108-116), including torch.nan_to_num(C, nan=1.0)
+ * (:114).  The assignment is index-identical to scipy's rectangular LSAP solver (same float64
+ * arithmetic, same tie rules); one CTA solves one image.
+ *
+ * cost       float32, element (b, q, t) at cost[b*stride_b + q*stride_q + t*stride_t] (elements):
+ *            the image's own block of the matching cost, Q queries x n_targets[b] targets
+ * n_targets  HOST int32 [B] (0 <= n <= 65535; B <= 1024)
+ * out_q      int64 [B, out_stride]: query index of the k-th matched pair of image b, ascending;
+ *            positions >= min(Q, n_targets[b]) are filled with -1
+ * out_t      int64 [B, out_stride]: target index of the k-th pair
+ * -------------------------------------------------------------------------- */
+DFINE_API int dfine_lsap(const float* cost, int64_t stride_b, int64_t stride_q, int64_t stride_t,
+               const int32_t* n_targets, int B, int Q, int64_t* out_q, int64_t* out_t,
+               int64_t out_stride, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

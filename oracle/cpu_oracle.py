@@ -205,6 +205,22 @@ def mask_gemm_bwd(coef, proto, grad_out):
     return np.einsum("bmn,bkn->bmk", g, p), np.einsum("bmk,bmn->bkn", coef, g).reshape(B, K, *tail)
 
 
+def lsap(cost) -> Tuple[np.ndarray, np.ndarray]:
+    """Rectangular linear-sum assignment of one float32 cost matrix [queries, targets] exactly as
+    scipy.optimize.linear_sum_assignment solves it (reference src/d_fine/matcher.py:115): returns
+    (query indices ascending, target indices), int64."""
+    c = _c32(cost)
+    nq, nt = c.shape
+    k = min(nq, nt)
+    oq, ot = np.empty(k, np.int64), np.empty(k, np.int64)
+    fn = lib().oracle_lsap
+    fn.restype = ctypes.c_int
+    fn.argtypes = [_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
+    rc = fn(_f(c), nq, nt, nt, oq.ctypes.data, ot.ctypes.data)
+    assert rc == k, rc
+    return oq, ot
+
+
 def linear_wgrad(grad_y: np.ndarray, x: np.ndarray):
     """Weight and bias gradient of y = x W^T + b (autograd of the two nn.Linear of MSDeformableAttention,
     reference src/d_fine/arch/dfine_decoder.py:87-88, :139-147): dW = grad_y^T x, db = sum over the rows of

@@ -383,3 +383,101 @@ int oracle_mask_gemm(const float* coef, const float* proto, float* out, int B, i
   }
   return 0;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Rectangular linear-sum assignment: the Hungarian step of the criterion's matcher
+ * (reference src/d_fine/matcher.py:112-116 calls scipy.optimize.linear_sum_assignment on
+ * torch.nan_to_num(C, nan=1.0) per image).  The arithmetic lives in a third-party dependency
+ * of the reference: SciPy (requirements.txt:22 pins scipy==1.15.1; this image has 1.18.1),
+ * scipy/optimize/rectangular_lsap/rectangular_lsap.cpp -- D. F. Crouse, "On implementing 2D
+ * rectangular assignment algorithms", IEEE TAES 52(4), 2016: shortest augmenting paths with
+ * dual variables u, v.  Restated here sequentially (float64, the matrix transposed when it has
+ * more rows than columns, `remaining` filled in reverse and shrunk by swap-with-last, ties for
+ * the minimal path cost resolved in favour of an unassigned column) and PINNED against
+ * scipy.optimize.linear_sum_assignment itself in tests/test_lsap.py (random, integer-tie,
+ * constant and duplicated-row matrices).
+ *
+ * cost: float32 [nq][nt] with row stride `ld` (NaN -> 1, +-inf -> +-FLT_MAX as nan_to_num does);
+ * out_q / out_t: min(nq, nt) pairs in ascending query order.  Returns the number of pairs, or -1.
+ * ------------------------------------------------------------------------------------------ */
+#include <float.h>
+
+static double lsap_at(const float* cost, int64_t ld, int q, int t) {
+  float c = cost[(int64_t)q * ld + t];
+  if (c != c) c = 1.0f;
+  else if (c == INFINITY) c = FLT_MAX;
+  else if (c == -INFINITY) c = -FLT_MAX;
+  return (double)c;
+}
+
+int oracle_lsap(const float* cost, int nq, int nt, int64_t ld, int64_t* out_q, int64_t* out_t) {
+  if (nq <= 0 || nt <= 0) return nq < 0 || nt < 0 ? -1 : 0;
+  const int transposed = nt < nq;          /* rows = the shorter side */
+  const int nr = transposed ? nt : nq, nc = transposed ? nq : nt;
+  double* u = (double*)calloc((size_t)nr, sizeof(double));
+  double* v = (double*)calloc((size_t)nc, sizeof(double));
+  double* spc = (double*)malloc((size_t)nc * sizeof(double));
+  int* path = (int*)malloc((size_t)nc * sizeof(int));
+  int* col4row = (int*)malloc((size_t)nr * sizeof(int));
+  int* row4col = (int*)malloc((size_t)nc * sizeof(int));
+  int* remaining = (int*)malloc((size_t)nc * sizeof(int));
+  char* SR = (char*)malloc((size_t)nr);
+  char* SC = (char*)malloc((size_t)nc);
+  int rc = 0;
+  for (int j = 0; j < nc; ++j) { path[j] = -1; row4col[j] = -1; }
+  for (int i = 0; i < nr; ++i) col4row[i] = -1;
+  for (int cur = 0; cur < nr && rc == 0; ++cur) {
+    double min_val = 0.0;
+    int num_remaining = nc, sink = -1, i = cur;
+    for (int it = 0; it < nc; ++it) remaining[it] = nc - it - 1;
+    memset(SR, 0, (size_t)nr);
+    memset(SC, 0, (size_t)nc);
+    for (int j = 0; j < nc; ++j) spc[j] = INFINITY;
+    while (sink == -1) {
+      int index = -1;
+      double lowest = INFINITY;
+      SR[i] = 1;
+      for (int it = 0; it < num_remaining; ++it) {
+        const int j = remaining[it];
+        const double c = transposed ? lsap_at(cost, ld, j, i) : lsap_at(cost, ld, i, j);
+        const double r = min_val + c - u[i] - v[j];
+        if (r < spc[j]) { path[j] = i; spc[j] = r; }
+        if (spc[j] < lowest || (spc[j] == lowest && row4col[j] == -1)) { lowest = spc[j]; index = it; }
+      }
+      min_val = lowest;
+      if (min_val == INFINITY) { rc = -1; break; }
+      const int j = remaining[index];
+      if (row4col[j] == -1) sink = j; else i = row4col[j];
+      SC[j] = 1;
+      remaining[index] = remaining[--num_remaining];
+    }
+    if (rc) break;
+    u[cur] += min_val;
+    for (int k = 0; k < nr; ++k)
+      if (SR[k] && k != cur) u[k] += min_val - spc[col4row[k]];
+    for (int j = 0; j < nc; ++j)
+      if (SC[j]) v[j] -= min_val - spc[j];
+    int j = sink;
+    for (;;) {
+      const int r = path[j];
+      row4col[j] = r;
+      const int t = col4row[r];
+      col4row[r] = j;
+      j = t;
+      if (r == cur) break;
+    }
+  }
+  if (rc == 0) {
+    if (transposed) {        /* pairs (query = col4row[t], t) in ascending query order */
+      int n = 0;
+      for (int q = 0; q < nc; ++q)
+        if (row4col[q] >= 0) { out_q[n] = q; out_t[n] = row4col[q]; ++n; }
+      rc = n;
+    } else {
+      for (int q = 0; q < nr; ++q) { out_q[q] = q; out_t[q] = col4row[q]; }
+      rc = nr;
+    }
+  }
+  free(u); free(v); free(spc); free(path); free(col4row); free(row4col); free(remaining); free(SR); free(SC);
+  return rc;
+}

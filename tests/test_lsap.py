@@ -1,0 +1,305 @@
+"""Matching stage of the criterion: the Hungarian assignment on the device
+(`dfine_lsap`) and the union of the per-layer matches, both index-identical to the reference.
+
+The reference solves the assignment with scipy.optimize.linear_sum_assignment on the host
+(src/d_fine/matcher.py:112-116).  The solver is a third-party dependency (scipy; pinned 1.15.1 by the
+reference, 1.18.1 in this image): the oracle restates its published algorithm (oracle/dfine_oracle.c,
+oracle_lsap) and is PINNED here against scipy itself; the CUDA kernel is then compared with scipy and with
+the oracle on random, integer-tie, constant, duplicated and non-finite cost matrices.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "d-fine-seg_b200"))
+
+from scipy.optimize import linear_sum_assignment  # noqa: E402
+
+
+def _matrix(rng, kind, nq, nt):
+    if kind == 0:      # generic floats
+        c = rng.standard_normal((nq, nt))
+    elif kind == 1:    # small integers: many ties for the minimal path cost
+        c = rng.integers(0, 3, (nq, nt))
+    elif kind == 2:    # constant matrix (scipy: the identity assignment, c.f. scipy issue 11602)
+        c = np.full((nq, nt), float(rng.integers(-2, 3)))
+    elif kind == 3:    # duplicated rows and columns
+        c = rng.integers(0, 4, (nq, nt)).astype(np.float64)
+        c[rng.integers(0, nq)] = c[0]
+        c[:, rng.integers(0, nt)] = c[:, 0]
+    elif kind == 4:    # NaN / +-inf entries: torch.nan_to_num(C, nan=1.0) semantics
+        c = rng.standard_normal((nq, nt))
+        m = rng.random((nq, nt))
+        c[m < 0.08] = np.nan
+        c[(m > 0.08) & (m < 0.11)] = np.inf
+        c[(m > 0.11) & (m < 0.13)] = -np.inf
+    else:              # half-integer grid of detection-like costs
+        c = np.round(rng.standard_normal((nq, nt)) * 2) / 2
+    return np.ascontiguousarray(c, dtype=np.float32)
+
+
+def _scipy(c):
+    """What the reference computes for one image (matcher.py:114-115)."""
+    cc = torch.nan_to_num(torch.from_numpy(c), nan=1.0).numpy()
+    return linear_sum_assignment(cc)
+
+
+def _cases(seed, n, lo=1, hi=40):
+    rng = np.random.default_rng(seed)
+    for trial in range(n):
+        nq, nt = int(rng.integers(lo, hi)), int(rng.integers(lo, hi))
+        yield _matrix(rng, trial % 6, nq, nt)
+
+
+def test_oracle_lsap_pinned_against_scipy():
+    from oracle import cpu_oracle as O
+    n = 0
+    for c in _cases(0, 3000):
+        a, b = _scipy(c)
+        oq, ot = O.lsap(c)
+        assert np.array_equal(a, oq) and np.array_equal(b, ot), (c.shape, n)
+        n += 1
+    rng = np.random.default_rng(1)
+    for trial in range(300):      # the matcher's shape: 300 queries x 1..130 targets
+        c = _matrix(rng, trial % 6, 300, int(rng.integers(1, 130)))
+        a, b = _scipy(c)
+        oq, ot = O.lsap(c)
+        assert np.array_equal(a, oq) and np.array_equal(b, ot), (c.shape, trial)
+    assert n == 3000
+
+
+def _random_layers(rng, g, B, Q, nl, sizes):
+    def layer():
+        out = []
+        for n in sizes:
+            q = torch.randperm(Q, generator=g)[:n].sort().values
+            t = torch.randperm(n, generator=g) if rng.random() < 0.5 else torch.arange(n)
+            out.append((q.long(), t.long()))
+        return out
+    base = layer()
+    return [base] + [(base if rng.random() < 0.4 else layer()) for _ in range(nl - 1)]
+
+
+def test_go_indices_identical_to_reference():
+    """`_get_go_indices` (dfine_criterion.py:371-392) without the per-pair `.item()` walk: same pairs, same
+    order, same dtype on >= 1000 random images, count ties included (more than 16 pairs per image, where the
+    reference's argsort is unstable)."""
+    from baseline import ref_install
+    if not ref_install.installed():
+        pytest.skip("baseline/_ref (the reference's model package) was not installed by build()")
+    ref_install.import_reference()
+    from src.d_fine.dfine_criterion import DFINECriterion
+    from dfine_b200 import criterion as C
+    rng = np.random.default_rng(5)
+    g = torch.Generator().manual_seed(0)
+    total = 0
+    for trial in range(450):
+        B, Q, nl = int(rng.integers(1, 5)), int(rng.integers(3, 300)), int(rng.integers(1, 8))
+        sizes = [int(rng.integers(0, min(Q, 40) + 1)) for _ in range(B)]
+        layers = _random_layers(rng, g, B, Q, nl, sizes)
+        want = DFINECriterion._get_go_indices(None, layers[0], layers[1:])
+        got = C.go_indices_host(layers[0], layers[1:])
+        assert len(got) == len(want) == B
+        for b in range(B):
+            assert got[b][0].dtype == want[b][0].dtype == torch.int64
+            assert torch.equal(got[b][0], want[b][0]) and torch.equal(got[b][1], want[b][1]), (trial, b)
+            total += 1
+    assert total >= 1000
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU
+# ----------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def _solve_batch(mats, dev, Q, T):
+    from dfine_b200 import ops
+    B = len(mats)
+    cost = torch.full((B, Q, T), 7.0, dtype=torch.float32)       # padding is never read
+    for b, c in enumerate(mats):
+        cost[b, :, :c.shape[1]] = torch.from_numpy(c)
+    sizes = [c.shape[1] for c in mats]
+    q, t = ops.lsap(cost.to(dev), sizes)
+    torch.cuda.synchronize()
+    return q.cpu().numpy(), t.cpu().numpy(), sizes
+
+
+@pytest.mark.gpu
+def test_lsap_kernel_identical_to_scipy(dev):
+    """>= 1000 random + adversarial cost matrices per shape family, solved 256 images per launch."""
+    from oracle import cpu_oracle as O
+    rng = np.random.default_rng(11)
+    n_checked = 0
+    for (Q, tmax, n_img) in [(300, 130, 1024), (37, 60, 1024), (12, 12, 512), (5, 300, 256)]:
+        mats = [_matrix(rng, i % 6, Q, int(rng.integers(0 if i % 50 == 49 else 1, tmax + 1))) for i in range(n_img)]
+        for o in range(0, n_img, 256):
+            chunk = mats[o:o + 256]
+            T = max(1, max(c.shape[1] for c in chunk))
+            q, t, sizes = _solve_batch(chunk, dev, Q, T)
+            for b, c in enumerate(chunk):
+                k = min(Q, sizes[b])
+                assert (q[b, k:] == -1).all() and (t[b, k:] == -1).all()
+                if k == 0:
+                    continue
+                a, bb = _scipy(c)
+                assert np.array_equal(q[b, :k], a) and np.array_equal(t[b, :k], bb), (Q, c.shape, o + b, (o + b) % 6)
+                if (o + b) % 16 == 0:
+                    oq, ot = O.lsap(c)
+                    assert np.array_equal(q[b, :k], oq) and np.array_equal(t[b, :k], ot)
+                n_checked += 1
+    assert n_checked >= 2500
+
+
+@pytest.mark.gpu
+def test_lsap_strided_cost_and_errors(dev):
+    import dfine_b200
+    from dfine_b200 import ops
+    rng = np.random.default_rng(3)
+    c = torch.from_numpy(rng.standard_normal((4, 20, 50)).astype(np.float32)).to(dev)
+    view = c.transpose(1, 2)                     # [4, 50, 20] with non-trivial strides
+    q, t = ops.lsap(view, [20, 7, 0, 13])
+    for b, n in enumerate([20, 7, 0, 13]):
+        if n == 0:
+            assert (q[b] == -1).all()
+            continue
+        a, bb = linear_sum_assignment(view[b, :, :n].cpu().numpy())
+        assert np.array_equal(q[b, :len(a)].cpu().numpy(), a) and np.array_equal(t[b, :len(a)].cpu().numpy(), bb)
+    with pytest.raises(ValueError):
+        ops.lsap(c, [1, 2, 3])
+    with pytest.raises(TypeError):
+        ops.lsap(c.double(), [1, 2, 3, 4])
+    with pytest.raises(RuntimeError):      # host tensors never reach a kernel: no CPU path
+        ops.lsap(c.cpu(), [1, 2, 3, 4])
+
+
+def _count_syncs(fn):
+    """Host synchronisations of fn(): torch's sync debug mode warns once per synchronising call."""
+    torch.cuda.synchronize()
+    old = torch.cuda.get_sync_debug_mode()
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        torch.cuda.set_sync_debug_mode("warn")
+        try:
+            out = fn()
+        finally:
+            torch.cuda.set_sync_debug_mode(old)
+    torch.cuda.synchronize()
+    return out, sum("synchroniz" in str(x.message).lower() for x in w)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,seg", [("n", False), ("m", False), ("m", True)], ids=["n", "m", "m_seg"])
+def test_patched_criterion_identical(name, seg, dev):
+    """patch_criterion on the reference criterion, fed by the reference model's real outputs: every cost
+    block bit-identical to the block scipy receives in the reference, every assignment and the union over the
+    layers identical, every loss term bit-identical; host synchronisations counted before / after."""
+    from baseline import model_harness as H
+    from baseline import ref_install
+    if not ref_install.installed():
+        pytest.skip("baseline/_ref (the reference's model package) was not installed by build()")
+    import copy
+    import dfine_b200
+    from dfine_b200 import criterion as C
+    ref_install.import_reference()
+    import src.d_fine.matcher as M
+
+    model, loss_fn = H.build(name, dev, 640, seg)
+    model.train(), loss_fn.train()
+    images, targets = H.synthetic_batch(4, 640, dev, seed=7, seg=seg)
+    targets[1] = {k: v[:3] for k, v in targets[1].items()}          # ragged target counts
+    torch.manual_seed(3)
+    with torch.no_grad():
+        out = model(images, targets=targets)
+
+    patched = copy.deepcopy(loss_fn)
+    assert C.patch_criterion(patched) == {"matcher": 1, "go_indices": 1}
+    seen = []
+    orig = M.linear_sum_assignment
+
+    def spy(c):
+        seen.append(np.array(c, copy=True))
+        return orig(c)
+
+    M.linear_sum_assignment = spy
+    try:
+        (want, want_idx), syncs_ref = _count_syncs(lambda: _criterion(loss_fn, out, targets))
+    finally:
+        M.linear_sum_assignment = orig
+    blocks = []
+    lsap = dfine_b200.ops.lsap
+
+    def spy_lsap(cost, sizes):
+        blocks.append((cost.detach().cpu().numpy(), list(sizes)))
+        return lsap(cost, sizes)
+
+    dfine_b200.ops.lsap = spy_lsap
+    try:
+        (got, got_idx), syncs = _count_syncs(lambda: _criterion(patched, out, targets))
+    finally:
+        dfine_b200.ops.lsap = lsap
+    # cost blocks: what scipy saw (after nan_to_num) == the image's block of the device cost
+    n_calls = len(blocks)
+    assert n_calls >= 4 and len(seen) == n_calls * len(targets)
+    for call, (cost, sizes) in enumerate(blocks):
+        for b, n in enumerate(sizes):
+            ref_block = seen[call * len(targets) + b]
+            assert np.array_equal(np.nan_to_num(cost[b, :, :n], nan=1.0), ref_block), (call, b)
+    # assignments (one per matcher call and image) and the union over the layers
+    assert len(want_idx) == len(got_idx)
+    for lw, lg in zip(want_idx, got_idx):
+        for (i0, j0), (i1, j1) in zip(lw, lg):
+            assert i1.is_cuda and torch.equal(i0, i1.cpu()) and torch.equal(j0, j1.cpu())
+    # the loss terms are the reference's code on identical indices: bit-identical values
+    assert sorted(want) == sorted(got)
+    for k in want:
+        assert torch.equal(want[k].detach().cpu(), got[k].detach().cpu()), (k, float(want[k]), float(got[k]))
+    report = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(report):
+        with open(os.path.join(report, "criterion_syncs.jsonl"), "a") as f:
+            f.write('{"model": "%s", "seg": %s, "matcher_calls": %d, "host_syncs_reference": %d, '
+                    '"host_syncs_patched": %d}\n' % (name, str(seg).lower(), n_calls, syncs_ref, syncs))
+    assert syncs < syncs_ref
+    C.unpatch_criterion(patched)
+    assert "forward" not in patched.matcher.__dict__ and "_get_go_indices" not in patched.__dict__
+
+
+def _criterion(loss_fn, out, targets):
+    """Runs the criterion and records every matcher result and the union (`_get_go_indices`)."""
+    rec = []
+    m = loss_fn.matcher
+    m_orig, g_orig = m.forward, loss_fn._get_go_indices
+    m_had, g_had = m.__dict__.get("forward"), loss_fn.__dict__.get("_get_go_indices")
+
+    def m_spy(outputs, tg, **kw):
+        r = m_orig(outputs, tg, **kw)
+        rec.append([(i.clone(), j.clone()) for i, j in r["indices"]])
+        return r
+
+    def g_spy(indices, aux):
+        r = g_orig(indices, aux)
+        rec.append([(i.clone(), j.clone()) for i, j in r])
+        return r
+
+    m.__dict__["forward"] = m_spy
+    loss_fn.__dict__["_get_go_indices"] = g_spy
+    try:
+        with torch.autocast("cuda", enabled=False):
+            losses = loss_fn(out, targets)
+    finally:
+        for obj, key, had in ((m, "forward", m_had), (loss_fn, "_get_go_indices", g_had)):
+            if had is None:
+                obj.__dict__.pop(key, None)
+            else:
+                obj.__dict__[key] = had
+    return losses, rec
