@@ -107,12 +107,18 @@ class HotPath:
         self.wl, self.dev = wl, device
         # data parallel (world > 1): the gradients of the path's own parameters (the two Linears
         # of every layer) are averaged over the ranks each step -- what DDP does for them in the
-        # reference (src/dl/train.py:161-166).  "eager": one NCCL all-reduce enqueued on the compute
-        # stream right after every graph replay; "off": no exchange.  (Capturing the collective
-        # inside the step's CUDA graph measured 1.068 vs 1.079 ms at N = 2 but left the ranks
-        # hanging at process-group teardown, so it is not offered.)
+        # reference (src/dl/train.py:161-166).  "overlap" (measured SLOWER than "eager": 1.041 vs 1.005 ms at
+        # N = 2 -- four latency-bound collectives whose kernels take SMs from the backward cost more than
+        # the one exposed all-reduce they replace; kept selectable): one bucket per decoder layer, its
+        # NCCL all-reduce forked onto a side stream the moment the layer's weight-gradient kernel is
+        # done and captured INSIDE the step's CUDA graph, so it runs under the backward kernels of
+        # the remaining layers (DDP's bucketed overlap; only the first layer's exchange is exposed).
+        # "eager": one all-reduce of everything on the compute stream after every graph replay (fully
+        # exposed); "off": no exchange.  Graphs holding collectives are destroyed before the
+        # process group (HotPath.close) -- leaving them alive hung the ranks at teardown.
         self.world, self.sync_mode = world, (sync_mode if world > 1 else "off")
         self.bucket = None
+        self.lsync = None
         self.mods = []
         for lw in inp["lin"]:
             m = dfine_b200.MSDeformableAttention(wl["C"], wl["H"], len(wl["shapes"]), wl["npts"])
@@ -129,34 +135,52 @@ class HotPath:
         if self.sync_mode != "off":
             from dfine_b200 import grad_sync
             self.bucket = grad_sync.GradBucket(grad_sync.path_parameters(self.mods))
+            if self.sync_mode == "overlap":
+                self.lsync = grad_sync.LayerwiseGradSync(self.mods)
+
+    # every input of a step lives in ONE slab (256-byte aligned slots): the device copy is what the CUDA
+    # graph reads, the pinned host copy is what an end-to-end step sends -- one cudaMemcpyAsync of the
+    # whole slab instead of one small copy per tensor (22 at config 3)
+    _DTYPES = dict(memory=torch.bfloat16, corners=torch.bfloat16)
+
+    def _layout(self, inp: dict):
+        slots, off = [], 0
+        for k in ("memory", "queries", "refs", "corners", "ref_init", "grad_outs", "grad_boxes"):
+            v = inp[k]
+            dt = self._DTYPES.get(k, torch.float32)
+            for i, t in enumerate(v if isinstance(v, list) else [v]):
+                nbytes = t.numel() * torch.empty((), dtype=dt).element_size()
+                slots.append((k, i if isinstance(v, list) else None, dt, tuple(t.shape), off, nbytes))
+                off += (nbytes + 255) & ~255
+        return slots, off
+
+    def _views(self, slab: torch.Tensor, slots):
+        d = {}
+        for k, i, dt, shape, off, nbytes in slots:
+            t = slab[off:off + nbytes].view(dt).view(shape)
+            if i is None:
+                d[k] = t
+            else:
+                d.setdefault(k, []).append(t)
+        return d
 
     def load_device(self, inp: dict):
-        dev = self.dev
-        self.d = dict(
-            memory=inp["memory"].to(dev, torch.bfloat16),
-            queries=[q.to(dev) for q in inp["queries"]],
-            refs=[r.to(dev) for r in inp["refs"]],
-            corners=[c.to(dev, torch.bfloat16) for c in inp["corners"]],
-            ref_init=inp["ref_init"].to(dev),
-            grad_outs=[g.to(dev) for g in inp["grad_outs"]],
-            grad_boxes=[g.to(dev) for g in inp["grad_boxes"]],
-        )
+        slots, total = self._layout(inp)
+        self.d_slab = torch.empty(total, dtype=torch.uint8, device=self.dev)
+        self.d = self._views(self.d_slab, slots)
+        for k, i, dt, shape, off, nbytes in slots:
+            src = inp[k] if i is None else inp[k][i]
+            (self.d[k] if i is None else self.d[k][i]).copy_(src.to(dt))
 
     def pin_host(self, inp: dict):
-        def pin(t, dt=None):
-            t = t.to(dt) if dt is not None else t
-            return t.contiguous().pin_memory()
-        self.host = dict(
-            memory=pin(inp["memory"], torch.bfloat16),
-            queries=[pin(q) for q in inp["queries"]],
-            refs=[pin(r) for r in inp["refs"]],
-            corners=[pin(c, torch.bfloat16) for c in inp["corners"]],
-            ref_init=pin(inp["ref_init"]),
-            grad_outs=[pin(g) for g in inp["grad_outs"]],
-            grad_boxes=[pin(g) for g in inp["grad_boxes"]],
-        )
-        self.h2d_bytes = sum(t.numel() * t.element_size() for v in self.host.values()
-                             for t in (v if isinstance(v, list) else [v]))
+        slots, total = self._layout(inp)
+        self.h_slab = torch.empty(total, dtype=torch.uint8).pin_memory()
+        self.host = self._views(self.h_slab, slots)
+        for k, i, dt, shape, off, nbytes in slots:
+            src = inp[k] if i is None else inp[k][i]
+            (self.host[k] if i is None else self.host[k][i]).copy_(src.to(dt))
+        self.h2d_bytes = total
+        self.h2d_copies = 1
         L = len(inp["queries"])
         self.boxes_host = torch.empty((L, *inp["grad_boxes"][0].shape), dtype=torch.float32).pin_memory()
         self.d2h_bytes = self.boxes_host.numel() * 4
@@ -180,6 +204,8 @@ class HotPath:
                 boxes.append(self.api.fdr_decode(corners[i], d["ref_init"], project, self.reg_scale,
                                                  wl["reg_max"]))
         torch.autograd.backward(outs + boxes, d["grad_outs"] + d["grad_boxes"])
+        if self.lsync is not None:
+            self.lsync.finish()       # the compute stream joins the per-layer exchanges
         return boxes, mem.grad
 
     def step_eager(self, d: dict):
@@ -217,14 +243,26 @@ class HotPath:
         if self.sync_mode == "eager":
             self.bucket.reduce(self.g_grads)
 
+    def close(self):
+        """Drop the CUDA graphs (they hold captured collectives in "overlap" mode) and drain the device:
+        call before torch.distributed.destroy_process_group()."""
+        for st in getattr(self, "sets", []):
+            st.pop("graph", None)
+        self.sets = []
+        self.graph = None
+        if self.lsync is not None:
+            self.lsync.remove()
+        torch.cuda.synchronize(self.dev)
+
     def setup_pipeline(self, inp: dict):
         """Second set of static buffers + graph, a copy stream and events: the H2D copies of
         step i+1 overlap the compute of step i (copies and kernels on separate streams)."""
-        first = dict(d=self.d, graph=self.graph, boxes=self.g_boxes, grads=self.g_grads)
+        first = dict(d=self.d, slab=self.d_slab, graph=self.graph, boxes=self.g_boxes, grads=self.g_grads)
         self.load_device(inp)             # fresh static buffers -> self.d
         self.capture(warmup=3)            # second graph over them
-        second = dict(d=self.d, graph=self.graph, boxes=self.g_boxes, grads=self.g_grads)
-        self.d, self.graph, self.g_boxes, self.g_grads = first["d"], first["graph"], first["boxes"], first["grads"]
+        second = dict(d=self.d, slab=self.d_slab, graph=self.graph, boxes=self.g_boxes, grads=self.g_grads)
+        self.d, self.d_slab, self.graph, self.g_boxes, self.g_grads = (first["d"], first["slab"], first["graph"],
+                                                                        first["boxes"], first["grads"])
         self.sets = [first, second]
         self.copy_stream = torch.cuda.Stream(self.dev)
         for st in self.sets:
@@ -244,12 +282,7 @@ class HotPath:
         comp = torch.cuda.current_stream(self.dev)
         st["done"].synchronize()          # result of the step that last used this set is on the host
         with torch.cuda.stream(self.copy_stream):
-            for k, v in self.host.items():
-                if isinstance(v, list):
-                    for dst, src in zip(st["d"][k], v):
-                        dst.copy_(src, non_blocking=True)
-                else:
-                    st["d"][k].copy_(v, non_blocking=True)
+            st["slab"].copy_(self.h_slab, non_blocking=True)      # ONE copy: every input of the step
             st["copied"].record(self.copy_stream)
         comp.wait_event(st["copied"])
         st["graph"].replay()
@@ -266,12 +299,7 @@ class HotPath:
     def step_e2e(self):
         """Host buffers in, host result out: H2D of every input of the step from pinned
         memory into the graph's static buffers, graph replay, D2H of the decoded boxes."""
-        for k, v in self.host.items():
-            if isinstance(v, list):
-                for dst, src in zip(self.d[k], v):
-                    dst.copy_(src, non_blocking=True)
-            else:
-                self.d[k].copy_(v, non_blocking=True)
+        self.d_slab.copy_(self.h_slab, non_blocking=True)
         self.replay()
         self.boxes_host.copy_(self.g_boxes, non_blocking=True)
         torch.cuda.current_stream(self.dev).synchronize()
@@ -762,7 +790,7 @@ def main():
     ap.add_argument("--full-model-steps", type=int, default=8)
     ap.add_argument("--no-secondary", action="store_true",
                     help="skip the kernel-level legs at the other BASELINE configs")
-    ap.add_argument("--grad-sync", default="eager", choices=["eager", "off"],
+    ap.add_argument("--grad-sync", default="eager", choices=["overlap", "eager", "off"],
                     help="N > 1: NCCL all-reduce of the path's Linear gradients after every step / no exchange")
     ap.add_argument("--launch-list", action="store_true",
                     help="profiling aid: run W+K eager steps of the B200 path and exit (for an ncu launch list)")
@@ -814,6 +842,9 @@ def main():
     hp.setup_pipeline(inp)
     ms_e2e = time_steps(hp.step_e2e_pipelined, args.steps, args.warmup, device, dist_on)
     hp.drain_pipeline()
+    # the box's host -> device ceiling with all ranks copying at once: the same slab, copies back to back
+    ms_h2d = time_steps(lambda: hp.d_slab.copy_(hp.h_slab, non_blocking=True), args.steps, 2, device, dist_on)
+    h2d_ceiling = hp.h2d_bytes * args.steps / (ms_h2d / 1e3) / 1e9
     # ---- eager pass (no graph) with CUDA-event brackets around every C-ABI launch: the
     #      per-kernel durations behind the roofline figures ----
     for _ in range(2):
@@ -849,6 +880,8 @@ def main():
 
     if rank != 0:
         if dist_on:
+            hp.close()
+            torch.distributed.barrier()
             torch.distributed.destroy_process_group()
         return
 
@@ -894,10 +927,18 @@ def main():
                    "parallelism": f"dp{world} (batch-sharded; the kernels need no collective)",
                    "collective": (None if hp.bucket is None else
                                   f"NCCL all-reduce (avg) of the {wl['layers']} layers' Linear gradients, "
-                                  f"{hp.bucket.nbytes} B per step, one bucket, enqueued on the compute "
-                                  f"stream after every graph replay")},
+                                  f"{hp.bucket.nbytes} B per step, " +
+                                  ("one bucket per layer, each forked onto a side stream when the layer's "
+                                   "weight-gradient kernel is done and captured inside the step's CUDA graph "
+                                   "(overlaps the backward of the remaining layers)" if hp.sync_mode == "overlap"
+                                   else "one bucket, enqueued on the compute stream after every graph replay"))},
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": hp.h2d_bytes, "d2h_bytes_per_step": hp.d2h_bytes,
+                "h2d_copies_per_step": hp.h2d_copies,
+                "h2d_gbs_per_gpu": hp.h2d_bytes * args.steps / (ms_e2e / 1e3) / 1e9,
+                "h2d_ceiling_gbs_per_gpu": h2d_ceiling,
+                "h2d_ceiling_note": f"the same pinned slab copied back to back on all {world} ranks at once "
+                                    "(max over ranks): what the host side of this box delivers per GPU",
                 "pipeline": "double-buffered: H2D of step i+1 on a copy stream overlaps the graph "
                             "replay of step i; every step still copies all its inputs from pinned host "
                             "memory and reads its boxes back",
@@ -926,6 +967,8 @@ def main():
                                          f"after 1 warm-up, fp32, oracle/torch_port.py on the host CPU"}
     print(json.dumps(out))
     if dist_on:
+        hp.close()
+        torch.distributed.barrier()
         torch.distributed.destroy_process_group()
 
 

@@ -63,3 +63,75 @@ class GradBucket:
             with torch.no_grad():
                 torch._foreach_copy_(list(grads), [c.view_as(g) for c, g in zip(flat.split(self.numels), grads)])
         return flat
+
+
+class LayerwiseGradSync:
+    """DDP-style overlap for the path's parameters: one bucket per MSDeformableAttention module, reduced on
+    a side stream as soon as the module's last parameter gradient has been accumulated (the backward of
+    decoder layer i+1 finishes before that of layer i starts, reference dfine_decoder.py:470-515), so the
+    all-reduce of layer i+1 runs under the backward kernels of layers i, i-1, ...; only the first layer's
+    exchange is exposed.  Works under CUDA-graph capture (the side stream forks from and re-joins the
+    capturing stream) and with CPU tensors / gloo (no streams: the reduce runs in the hook).
+
+    Usage:  sync = LayerwiseGradSync(modules); ...; loss.backward(); sync.finish()
+    """
+
+    def __init__(self, modules: Iterable[torch.nn.Module], group=None):
+        self.buckets: List[GradBucket] = []
+        self._pending: List[int] = []
+        self._handles = []
+        self._side = None
+        self.group = group
+        for m in modules:
+            params = path_parameters([m])
+            if not params:
+                continue
+            k = len(self.buckets)
+            self.buckets.append(GradBucket(params, group))
+            self._pending.append(len(params))
+            for p in params:
+                self._handles.append(p.register_post_accumulate_grad_hook(self._make_hook(k)))
+        if not self.buckets:
+            raise ValueError("LayerwiseGradSync: no trainable parameters")
+        self.nbytes = sum(b.nbytes for b in self.buckets)
+        self.launched = 0
+
+    def _make_hook(self, k: int):
+        def hook(param):
+            self._pending[k] -= 1
+            if self._pending[k] == 0:
+                self._launch(k)
+        return hook
+
+    def _launch(self, k: int) -> None:
+        bucket = self.buckets[k]
+        self.launched += 1
+        g0 = bucket.params[0].grad
+        if g0 is None or not g0.is_cuda:
+            bucket.reduce()
+            return
+        dev = g0.device
+        if self._side is None:
+            self._side = torch.cuda.Stream(dev)
+        cur = torch.cuda.current_stream(dev)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self._side.wait_event(ev)          # the gradients of this bucket are complete on `cur`
+        with torch.cuda.stream(self._side):
+            bucket.reduce()
+
+    def finish(self) -> None:
+        """Join: the current stream waits for every exchange started by this backward pass; a bucket
+        whose gradients never arrived is an error (every rank must reduce the same buckets)."""
+        missing = [k for k, n in enumerate(self._pending) if n != 0]
+        for k, b in enumerate(self.buckets):
+            self._pending[k] = len(b.params)
+        if missing:
+            raise RuntimeError(f"LayerwiseGradSync.finish: buckets {missing} did not receive all their gradients")
+        if self._side is not None:
+            torch.cuda.current_stream(self._side.device).wait_stream(self._side)
+
+    def remove(self) -> None:
+        for h in self._handles:
+            h.remove()
+        self._handles = []

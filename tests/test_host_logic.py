@@ -226,3 +226,66 @@ def test_grad_bucket_averages_linear_gradients_gloo():
         np.testing.assert_array_equal(y0, y1)
         np.testing.assert_array_equal(z0, y0)
         np.testing.assert_array_equal(z1, y1)
+
+
+def _layerwise_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "d-fine-seg_b200"))
+    from dfine_b200 import grad_sync
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)                       # same parameters on every rank
+    mods = [torch.nn.ModuleDict(dict(sampling_offsets=torch.nn.Linear(8, 12),
+                                     attention_weights=torch.nn.Linear(8, 6))) for _ in range(3)]
+    sync = grad_sync.LayerwiseGradSync(mods)
+    g = torch.Generator().manual_seed(100 + rank)   # different shards -> different gradients
+    x = torch.randn(5, 8, generator=g)
+
+    def loss(ms):
+        return sum((m["sampling_offsets"](x).square().sum() + m["attention_weights"](x).sum()) * (i + 1)
+                   for i, m in enumerate(ms))
+
+    local = torch.autograd.grad(loss(mods), grad_sync.path_parameters(mods))   # no hooks fire here
+    out = []
+    for step in range(2):                      # two passes: the pending counters re-arm in finish()
+        for m in mods:
+            m.zero_grad(set_to_none=True)
+        loss(mods).backward()                  # hooks: one all-reduce per module, last layer first
+        sync.finish()
+        out.append([p.grad.numpy().copy() for p in grad_sync.path_parameters(mods)])
+    q.put((rank, [t.numpy() for t in local], out, sync.launched, sync.nbytes))
+    # a bucket that did not get all its gradients is reported at the join
+    for m in mods:
+        m.zero_grad(set_to_none=True)
+    mods[0]["sampling_offsets"](x).sum().backward()
+    try:
+        sync.finish()
+        q.put((rank, "no error"))
+    except RuntimeError as exc:
+        q.put((rank, str(exc)))
+    dist.destroy_process_group()
+
+
+def test_layerwise_grad_sync_gloo():
+    """world_size 2 over gloo: per-module buckets reduced from autograd hooks leave the rank average in
+    every param.grad, on every step; an incomplete bucket fails loudly at finish()."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_layerwise_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    got = [q.get(timeout=120) for _ in range(4)]
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    res = sorted((g for g in got if len(g) == 5), key=lambda g: g[0])
+    errs = [g for g in got if len(g) == 2]
+    assert len(res) == 2 and len(errs) == 2
+    assert all("did not receive" in e[1] for e in errs)
+    (_, l0, o0, n0, b0), (_, l1, o1, n1, b1) = res
+    assert n0 == n1 == 6 and b0 == b1 == 3 * 4 * (8 * 12 + 12 + 8 * 6 + 6)
+    for step in range(2):
+        for x0, x1, y0, y1 in zip(l0, l1, o0[step], o1[step]):
+            np.testing.assert_allclose(y0, (x0 + x1) / 2, rtol=1e-6, atol=1e-6)
+            np.testing.assert_array_equal(y0, y1)
