@@ -116,9 +116,15 @@ class HotPath:
         # "eager": one all-reduce of everything on the compute stream after every graph replay (fully
         # exposed); "off": no exchange.  Graphs holding collectives are destroyed before the
         # process group (HotPath.close) -- leaving them alive hung the ranks at teardown.
+        # "nvls" (default): NO collective launch -- dfine_multicast_add adds every rank's gradient blocks into
+        # all replicas of a symmetric buffer through its NVLS multicast mapping (multimem.red: the sum over
+        # the ranks is formed inside the NVSwitch); two tiny device-side barriers per step
+        # (grad_sync.NvlsGradExchange).
         self.world, self.sync_mode = world, (sync_mode if world > 1 else "off")
         self.bucket = None
         self.lsync = None
+        self.nvls = None
+        self.nvls_error = None
         self.mods = []
         for lw in inp["lin"]:
             m = dfine_b200.MSDeformableAttention(wl["C"], wl["H"], len(wl["shapes"]), wl["npts"])
@@ -137,6 +143,14 @@ class HotPath:
             self.bucket = grad_sync.GradBucket(grad_sync.path_parameters(self.mods))
             if self.sync_mode == "overlap":
                 self.lsync = grad_sync.LayerwiseGradSync(self.mods)
+            if self.sync_mode == "nvls":
+                P = sum(wl["npts"])
+                n_out, K = 3 * wl["H"] * P, wl["C"]
+                try:
+                    self.nvls = grad_sync.NvlsGradExchange([n_out * K + n_out] * wl["layers"], device)
+                except Exception as exc:  # noqa: BLE001  (no multicast on this box: NCCL after the replay)
+                    self.nvls_error = f"{type(exc).__name__}: {exc}"[:200]
+                    self.sync_mode = "eager"
 
     # every input of a step lives in ONE slab (256-byte aligned slots): the device copy is what the CUDA
     # graph reads, the pinned host copy is what an end-to-end step sends -- one cudaMemcpyAsync of the
@@ -192,6 +206,8 @@ class HotPath:
         corners = [c.detach().requires_grad_(True) for c in d["corners"]]
         for m in self.mods:
             m.zero_grad(set_to_none=True)
+        if self.nvls is not None:
+            self.nvls.begin_step()    # zero the local replica + barrier A (hidden under the forward)
         outs, boxes = [], []
         with torch.autocast("cuda", dtype=torch.bfloat16):
             project = self.api.fdr_project(self.up, self.reg_scale, wl["reg_max"])
@@ -203,10 +219,37 @@ class HotPath:
                 outs.append(m(queries[i], d["refs"][i], value, wl["shapes"]))
                 boxes.append(self.api.fdr_decode(corners[i], d["ref_init"], project, self.reg_scale,
                                                  wl["reg_max"]))
-        torch.autograd.backward(outs + boxes, d["grad_outs"] + d["grad_boxes"])
+        if self.nvls is not None:
+            with self.nvls:           # dW / db of every layer land in the exchange's local blocks
+                torch.autograd.backward(outs + boxes, d["grad_outs"] + d["grad_boxes"])
+            self.nvls.end_step()      # multimem.red into all replicas + barrier B: the rank average
+        else:
+            torch.autograd.backward(outs + boxes, d["grad_outs"] + d["grad_boxes"])
         if self.lsync is not None:
             self.lsync.finish()       # the compute stream joins the per-layer exchanges
         return boxes, mem.grad
+
+    def check_exchange(self):
+        """N > 1 self-check of the in-kernel exchange: the gradients an "nvls" step leaves in param.grad
+        against the same step's local gradients averaged by an NCCL all-reduce.  Max error relative to the
+        largest gradient element."""
+        import torch.distributed as dist
+        if self.nvls is None:
+            return None
+        params = self.bucket.params
+        self.step(self.d)
+        got = [p.grad.detach().clone() for p in params]
+        ex, self.nvls = self.nvls, None
+        try:
+            self.step(self.d)
+        finally:
+            self.nvls = ex
+        err = 0.0
+        for g, p in zip(got, params):
+            want = p.grad.detach().clone()
+            dist.all_reduce(want, op=dist.ReduceOp.AVG)
+            err = max(err, float((g - want).abs().max() / want.abs().max().clamp_min(1e-30)))
+        return err
 
     def step_eager(self, d: dict):
         """step() plus the gradient all-reduce a graph replay is followed by (N > 1)."""
@@ -790,7 +833,7 @@ def main():
     ap.add_argument("--full-model-steps", type=int, default=8)
     ap.add_argument("--no-secondary", action="store_true",
                     help="skip the kernel-level legs at the other BASELINE configs")
-    ap.add_argument("--grad-sync", default="eager", choices=["overlap", "eager", "off"],
+    ap.add_argument("--grad-sync", default="nvls", choices=["nvls", "overlap", "eager", "off"],
                     help="N > 1: NCCL all-reduce of the path's Linear gradients after every step / no exchange")
     ap.add_argument("--launch-list", action="store_true",
                     help="profiling aid: run W+K eager steps of the B200 path and exit (for an ncu launch list)")
@@ -830,6 +873,7 @@ def main():
         print(json.dumps({"launch_list": True, "steps": args.warmup + args.steps}))
         return
 
+    exchange_err = hp.check_exchange() if dist_on else None
     sampler = ClockSampler(local) if rank == 0 else None
     # ---- headline: device-resident step, replayed from a CUDA graph ----
     ops.enable_kernel_timers(False)
@@ -931,7 +975,14 @@ def main():
                                   ("one bucket per layer, each forked onto a side stream when the layer's "
                                    "weight-gradient kernel is done and captured inside the step's CUDA graph "
                                    "(overlaps the backward of the remaining layers)" if hp.sync_mode == "overlap"
-                                   else "one bucket, enqueued on the compute stream after every graph replay"))},
+                                   else "one bucket, enqueued on the compute stream after every graph replay")
+                                  if hp.nvls is None else
+                                  f"none launched: dfine_multicast_add adds every layer's dW / db, scaled by "
+                                  f"1/{world}, into all ranks' replicas of a symmetric buffer with multimem.red "
+                                  f"(NVLS: summed in the switch); {hp.nvls.nbytes} B per step, two device-side "
+                                  f"barriers per step, all inside the CUDA graph"),
+                   "collective_check_max_rel_err_vs_nccl": exchange_err,
+                   "collective_fallback": hp.nvls_error},
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": hp.h2d_bytes, "d2h_bytes_per_step": hp.d2h_bytes,
                 "h2d_copies_per_step": hp.h2d_copies,

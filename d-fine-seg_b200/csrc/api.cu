@@ -30,6 +30,7 @@ int launch_mask_gemm_bwd(const void*, const void*, const void*, float*, void*, i
                          cudaStream_t);
 int launch_colsum(const void*, int, long long, int, long long, float*, cudaStream_t);
 int launch_linear_wgrad(const void*, int64_t, const void*, int64_t, int, int, int, float*, cudaStream_t);
+int launch_multicast_add(const float*, float*, long long, float, cudaStream_t);
 
 static int cuda_rc(int rc, const char* what) {
   if (rc > 0) set_error("%s: CUDA error %d (%s)", what, rc, cudaGetErrorString((cudaError_t)rc));
@@ -405,6 +406,25 @@ int dfine_linear_wgrad(const void* grad_y, int64_t gy_row_stride, const void* x,
   }
   return cuda_rc(launch_linear_wgrad(grad_y, gy_row_stride, x, x_row_stride, (int)M, N, K, dw_db,
                                      (cudaStream_t)stream), fn);
+}
+
+int dfine_multicast_add(const float* src, float* dst_multicast, int64_t n, float scale, void* stream) {
+  const char* fn = "dfine_multicast_add";
+  int rc;
+  if (n <= 0 || (n & 3)) {
+    set_error("%s: n must be a positive multiple of 4 (got %lld)", fn, (long long)n);
+    return DFINE_E_SHAPE;
+  }
+  if ((rc = require_device(src, "src", fn))) return rc;
+  if (!dst_multicast) {     // (a multicast address is not a queryable allocation: NULL / alignment only)
+    set_error("%s: dst_multicast is NULL", fn);
+    return DFINE_E_NULL;
+  }
+  if (!aligned16(src) || !aligned16(dst_multicast)) {
+    set_error("%s: src and dst_multicast must be 16-byte aligned", fn);
+    return DFINE_E_ALIGN;
+  }
+  return cuda_rc(launch_multicast_add(src, dst_multicast, n, scale, (cudaStream_t)stream), fn);
 }
 
 int dfine_pack_linear(const float* w0, const float* b0, int n0, const float* w1, const float* b1, int n1,

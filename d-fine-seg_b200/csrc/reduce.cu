@@ -114,4 +114,32 @@ int launch_pack_linear(const float* w0, const float* b0, int n0, const float* w1
   return (int)cudaGetLastError();
 }
 
+// Data-parallel gradient exchange without a collective launch: every rank adds its own fp32 gradient block,
+// scaled by 1 / world, into the replica of EVERY rank through the NVLS multicast address of a symmetric
+// buffer (multimem.red: the sum over the ranks is formed inside the NVSwitch).  Replaces DDP's all-reduce
+// of the path's Linear gradients (reference src/dl/train.py:161-166).  One float4 per thread, the whole
+// chip issues (NVLink bandwidth per SM is small: a single publishing CTA per tile, tried inside the
+// weight-gradient kernel, put ~30 us per layer on the critical path).
+__global__ void __launch_bounds__(256)
+multicast_add_kernel(const float4* __restrict__ src, float4* __restrict__ dst_mc, long long n4, float scale) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = __ldg(src + i);
+  asm volatile("multimem.red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+               ::"l"(dst_mc + i), "f"(v.x * scale), "f"(v.y * scale), "f"(v.z * scale), "f"(v.w * scale)
+               : "memory");
+}
+
+int launch_multicast_add(const float* src, float* dst_mc, long long n, float scale, cudaStream_t s) {
+  const long long n4 = n / 4;
+  const long long ctas = (n4 + 255) / 256;
+  if (ctas > 0x7fffffffLL) {
+    set_error("multicast_add: %lld elements exceed the grid", n);
+    return DFINE_E_SHAPE;
+  }
+  multicast_add_kernel<<<(unsigned)ctas, 256, 0, s>>>(reinterpret_cast<const float4*>(src),
+                                                      reinterpret_cast<float4*>(dst_mc), n4, scale);
+  return (int)cudaGetLastError();
+}
+
 }  // namespace dfine

@@ -48,6 +48,7 @@ _SIGNATURES = {
     "dfine_fdr_bwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_int, c_int64, c_int, c_void_p]),
     "dfine_linear_wgrad": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p]),
+    "dfine_multicast_add": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_void_p]),
     "dfine_pack_linear": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p,
                                   c_void_p, c_int, c_void_p]),
     "dfine_mask_gemm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,

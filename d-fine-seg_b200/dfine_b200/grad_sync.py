@@ -135,3 +135,92 @@ class LayerwiseGradSync:
         for h in self._handles:
             h.remove()
         self._handles = []
+
+
+class NvlsGradExchange:
+    """The gradient all-reduce of the path's Linears without a collective launch (B200 / NVSwitch).
+
+    One symmetric float32 buffer (torch.distributed._symmetric_memory: a replica on every rank plus an NVLS
+    multicast mapping over all replicas) holds the [dW; db] block of every layer.  While the exchange is
+    active, `ops.linear_wgrad` writes each layer's gradient into a local block and returns views of the
+    REPLICA as the gradients; `end_step` launches `dfine_multicast_add`: every rank adds its blocks, scaled
+    by 1 / world, into ALL replicas with multimem.red through the switch (the sum over the ranks is formed
+    in the NVSwitch), followed by a device-side barrier.  Per step:
+
+        begin_step():  zero the local replica; barrier A   (on a forked side stream: hidden under the step)
+        ... backward: dfine_linear_wgrad per layer into the local blocks ...
+        end_step():    dfine_multicast_add (1.2 MB, one launch); barrier B -> every replica holds the rank
+                       average (DDP's result, reference src/dl/train.py:161-166)
+
+    All of it is capturable in a CUDA graph.  Raises if the device / fabric has no multicast support."""
+
+    def __init__(self, slots: Sequence[int], device: torch.device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("NvlsGradExchange needs an initialised process group")
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.slots = [int(n) for n in slots]                     # floats per layer block (N*K + N)
+        self.offsets, off = [], 0
+        for n in self.slots:
+            self.offsets.append(off)
+            off += (n + 63) & ~63                                 # 256-byte aligned blocks
+        self.total = off
+        self.buf = symm.empty(self.total, dtype=torch.float32, device=device)
+        self.handle = symm.rendezvous(self.buf, self.group)
+        self.mc_ptr = int(self.handle.multicast_ptr)
+        if self.mc_ptr == 0:
+            raise RuntimeError("NvlsGradExchange: no NVLS multicast mapping on this device / fabric")
+        self.scale = 1.0 / self.world
+        self.nbytes = self.total * 4
+        self.local = torch.zeros(self.total, dtype=torch.float32, device=device)   # this rank's own gradients
+        self._next = 0
+        self._side = None
+        self.buf.zero_()
+        self.handle.barrier(channel=0)
+
+    # -- protocol -----------------------------------------------------------------------------
+    def begin_step(self) -> None:
+        """Zero the local replica and meet the other ranks (barrier A) on a side stream forked from the
+        current one: both run under the step's forward / backward kernels; end_step() joins."""
+        self._next = 0
+        dev = self.local.device
+        if self._side is None:
+            self._side = torch.cuda.Stream(dev)
+        self._side.wait_stream(torch.cuda.current_stream(dev))    # after the last reader of the replica
+        with torch.cuda.stream(self._side):
+            self.buf.zero_()
+            self.handle.barrier(channel=0)
+
+    def end_step(self) -> None:
+        from . import _lib
+        if self._next != len(self.slots):
+            raise RuntimeError(f"NvlsGradExchange.end_step: {self._next} of {len(self.slots)} gradient blocks "
+                               "were produced (every rank must produce all of them)")
+        torch.cuda.current_stream(self.local.device).wait_stream(self._side)   # every replica is zero
+        with torch.cuda.device_of(self.local):
+            rc = _lib.lib().dfine_multicast_add(self.local.data_ptr(), self.mc_ptr, self.total, self.scale,
+                                                torch.cuda.current_stream(self.local.device).cuda_stream)
+        _lib.check(rc, "dfine_multicast_add")
+        self.handle.barrier(channel=1)
+
+    # -- called by ops.linear_wgrad --------------------------------------------------------------
+    def next_block(self, n_floats: int):
+        """(local block, replica view) of the next layer's [dW; db] gradient, in backward order."""
+        k = self._next
+        if k >= len(self.slots) or self.slots[k] != n_floats:
+            raise RuntimeError(f"NvlsGradExchange: unexpected gradient block {k} of {n_floats} floats "
+                               f"(configured: {self.slots})")
+        self._next += 1
+        o = self.offsets[k]
+        return self.local[o:o + n_floats], self.buf[o:o + n_floats]
+
+    def __enter__(self):
+        from . import ops
+        ops._WGRAD_EXCHANGE = self
+        return self
+
+    def __exit__(self, *exc):
+        from . import ops
+        ops._WGRAD_EXCHANGE = None
+        return False

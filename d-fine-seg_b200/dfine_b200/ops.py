@@ -19,6 +19,7 @@ _DT = {torch.float32: F32, torch.bfloat16: BF16}
 # Instrumentation used by bench.py: number of kernels launched through the C-ABI, and
 # optional CUDA-event brackets around each launch (on the launching stream).
 LAUNCHES = {"count": 0}
+_WGRAD_EXCHANGE = None     # grad_sync.NvlsGradExchange while a data-parallel step is running
 _TIMERS = None  # None or dict: kernel name -> list of (start_event, end_event)
 
 
@@ -669,6 +670,17 @@ def linear_wgrad(gy: torch.Tensor, x: torch.Tensor):
                          "of 8 and K <= 256")
     M, N = gy.shape
     K = x.shape[1]
+    ex = _WGRAD_EXCHANGE
+    if ex is not None:
+        # data parallel (grad_sync.NvlsGradExchange): the gradient is produced in the exchange's local block;
+        # end_step() adds all blocks into every rank's replica through the NVLS multicast mapping, and the
+        # views returned here (of the replica) hold the rank average after its barrier
+        buf, out = ex.next_block(N * K + N)
+        with torch.cuda.device_of(gy), _timed("linear_wgrad", gy):
+            rc = _lib.lib().dfine_linear_wgrad(gy.data_ptr(), gy.stride(0), x.data_ptr(), x.stride(0), M, N, K,
+                                               buf.data_ptr(), _stream(gy))
+        check(rc, "dfine_linear_wgrad")
+        return out[:N * K].view(N, K), out[N * K:]
     buf = torch.empty(N * K + N, dtype=torch.float32, device=gy.device)
     with torch.cuda.device_of(gy), _timed("linear_wgrad", gy):
         rc = _lib.lib().dfine_linear_wgrad(gy.data_ptr(), gy.stride(0), x.data_ptr(), x.stride(0), M, N, K,

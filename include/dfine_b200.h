@@ -181,6 +181,17 @@ DFINE_API int dfine_colsum(const void* x, int x_dtype, int64_t M, int N, int64_t
 DFINE_API int dfine_linear_wgrad(const void* grad_y, int64_t gy_row_stride, const void* x, int64_t x_row_stride,
                        int64_t M, int N, int K, float* dw_db, void* stream);
 
+/* Data-parallel gradient exchange without a collective launch (replaces DistributedDataParallel's
+ * all-reduce of the path's Linear gradients, reference src/dl/train.py:161-166):
+ *     replica_r[i] += scale * src[i]   for EVERY rank r, i < n
+ * dst_multicast is the NVLS multicast address of a symmetric float32 buffer that has one replica per rank
+ * (e.g. torch.distributed._symmetric_memory: handle.multicast_ptr + offset); the additions are
+ * multimem.red.global.add operations, the sum over the ranks is formed inside the NVSwitch.
+ * Protocol (caller): each rank zeroes its own replica, all ranks pass a barrier, every rank calls this
+ * with its own gradient and scale = 1 / world, all ranks pass a second barrier; then every replica holds
+ * the rank average.  src: float32 device [n], n a multiple of 4, both pointers 16-byte aligned. */
+DFINE_API int dfine_multicast_add(const float* src, float* dst_multicast, int64_t n, float scale, void* stream);
+
 /* Parameters of the concatenated Linear in one launch: w = [w0; w1] ([n0+n1, K]) and
  * b = [b0; b1], float32 in, out_dtype out (bf16 under autocast).  w0/b0 = sampling_offsets,
  * w1/b1 = attention_weights (dfine_decoder.py:80-81); replaces 2 x torch.cat + 2 x cast. */
