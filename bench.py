@@ -480,6 +480,25 @@ def secondary_kernel_legs(device, peak: float, reps: int = 10):
                        (lambda: torch.bmm(go, proto.transpose(1, 2))))
         m4[key] = {"ms": ms, "algorithmic_bytes": nbytes, "frac": nbytes / (ms / 1e3) / 1e9 / peak,
                    "tflops": flops / (ms / 1e3) / 1e12, "cublas_bmm_ms": ms_lib, "vs_cublas": ms_lib / ms}
+    # fused focal + dice over the matched rows: 16 images x 100 denoising rows of 160 x 160 (bf16 logits)
+    Mr = 1600
+    xl = (torch.randn(Mr, N, device=device, generator=g) * 3).to(torch.bfloat16)
+    tl = (torch.rand(Mr, N, device=device, generator=g) < 0.2).float()
+    ms = timed(lambda: ops._MaskLossFn.apply(xl, tl))
+    nb = Mr * N * (2 + 4)
+    m4["mask_loss_fwd"] = {"ms": ms, "rows": Mr, "algorithmic_bytes": nb, "frac": nb / (ms / 1e3) / 1e9 / peak}
+    st = ops._MaskLossFn.apply(xl, tl)
+    gst = torch.randn(Mr, 4, device=device, generator=g)
+    gl = torch.empty_like(xl)
+
+    def bwd():
+        rc = dfine_b200._lib.lib().dfine_mask_loss_bwd(xl.data_ptr(), 1, N, tl.data_ptr(), Mr, N, st.data_ptr(),
+                                                       gst.data_ptr(), gl.data_ptr(), 1,
+                                                       torch.cuda.current_stream(device).cuda_stream)
+        assert rc == 0
+    ms = timed(bwd)
+    nb = Mr * N * (2 + 4 + 2)
+    m4["mask_loss_bwd"] = {"ms": ms, "rows": Mr, "algorithmic_bytes": nb, "frac": nb / (ms / 1e3) / 1e9 / peak}
     out["config4_mask_assembly_bf16"] = m4
     return out
 
@@ -624,6 +643,14 @@ def full_model_leg(device, rank: int, world: int, dist_on: bool, steps: int, war
     del model, patched, arms, patched_loss
     torch.cuda.empty_cache()
 
+    # ---- config 4: D-FINE-m instance segmentation training, 640x640, batch 16 per GPU: reference vs
+    #      patch_model(mask="matched") + patch_criterion (matched-rows-only mask assembly, fused focal + dice) ----
+    try:
+        out["train_config4_seg"] = _seg_train_leg(device, rank, world, dist_on, max(3, steps // 2), warmup, timed)
+    except Exception as exc:  # noqa: BLE001
+        out["train_config4_seg"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+    torch.cuda.empty_cache()
+
     # ---- config 2: D-FINE-s inference, 640x640, batch 64, bf16 autocast (rank 0 only does not matter:
     #      inference needs no collective, every rank runs its own batch) ----
     B = 64
@@ -651,6 +678,51 @@ def full_model_leg(device, rank: int, world: int, dist_on: bool, steps: int, war
     out["infer_config2"] = res
     return out
 
+
+
+def _seg_train_leg(device, rank, world, dist_on, steps, warmup, timed):
+    import copy
+
+    import dfine_b200
+    from baseline import model_harness as MH
+    from dfine_b200 import ops
+    B = 16
+    model, loss_fn = MH.build("m", device, 640, True, seed=0)
+    model.train(), loss_fn.train()
+    patched, ploss = copy.deepcopy(model), copy.deepcopy(loss_fn)
+    counts = dfine_b200.patch_model(patched, mask="matched")
+    counts.update(dfine_b200.patch_criterion(ploss))
+    images, targets = MH.synthetic_batch(B, 640, "cpu", seed=rank_seed(rank), seg=True)
+    host_images = images.pin_memory()
+    host_targets = [{k: v.pin_memory() for k, v in t.items()} for t in targets]
+    h2d = host_images.numel() * 4 + sum(v.numel() * v.element_size() for t in host_targets for v in t.values())
+    res = {"workload": "dfine_m_seg_train_640_b16 (full model + MaskPixelDecoder + mask head, criterion with mask "
+                       "losses, AdamW, clip 0.1, bf16 autocast)", "images_per_gpu": B, "patched_modules": counts,
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
+    for name, (m, crit) in {"reference": (model, loss_fn), "patched": (patched, ploss)}.items():
+        opt = MH.build_optimizer(m, "m")
+        run = m
+        if dist_on:
+            from torch.nn.parallel import DistributedDataParallel as DDP
+            run = DDP(m, device_ids=[device.index], output_device=device.index, find_unused_parameters=False)
+        loss_host = torch.zeros(1).pin_memory()
+
+        def step(run=run, opt=opt, crit=crit):
+            img = host_images.to(device, non_blocking=True)
+            tg = [{k: v.to(device, non_blocking=True) for k, v in t.items()} for t in host_targets]
+            _, _, loss = MH.train_step(run, crit, img, tg, torch.bfloat16, optimizer=opt)
+            loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+
+        torch.cuda.reset_peak_memory_stats(device)
+        n0 = ops.LAUNCHES["count"]
+        ms = timed(step, steps, warmup)
+        res[name] = {"ms_per_step": ms, "imgs_per_s": B * world / (ms / 1e3),
+                     "dfine_b200_launches_per_step": (ops.LAUNCHES["count"] - n0) // (steps + warmup),
+                     "loss_after": float(loss_host),
+                     "peak_memory_gb": torch.cuda.max_memory_allocated(device) / 2 ** 30}
+        del opt, run
+    res["speedup"] = res["patched"]["imgs_per_s"] / res["reference"]["imgs_per_s"]
+    return res
 
 
 class ClockSampler:

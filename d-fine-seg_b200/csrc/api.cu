@@ -24,6 +24,9 @@ int launch_fdr(bool, const void*, int, const float*, const float*, const float*,
 int launch_pack_linear(const float*, const float*, int, const float*, const float*, int, int, void*, void*, int,
                        cudaStream_t);
 int launch_mask_gemm(const void*, const void*, void*, int, int, int, int, int, int, cudaStream_t);
+int launch_mask_loss_fwd(const void*, int, long long, const float*, long long, long long, float*, cudaStream_t);
+int launch_mask_loss_bwd(const void*, int, long long, const float*, long long, long long, const float*, const float*,
+                         void*, int, cudaStream_t);
 int launch_lsap(const float*, long long, long long, long long, const int32_t*, int, int, long long*, long long*,
                 long long, cudaStream_t);
 int launch_mask_gemm_bwd(const void*, const void*, const void*, float*, void*, int, int, int, int, int,
@@ -220,7 +223,6 @@ int dfine_msda_fwd(const void* value, int64_t v_stride_b, int64_t v_stride_l,
   p.out = out;
   p.out_bf16 = out_dtype == DFINE_BF16;
   p.idx_debug = idx_debug;
-  p.tiled = (flags & DFINE_MSDA_TILED) ? 1 : 0;
   if (records) {
     if ((rc = require_device(records, "records", "dfine_msda_fwd"))) return rc;
     if (!aligned16(records)) {
@@ -604,6 +606,65 @@ int dfine_lsap(const float* cost, int64_t stride_b, int64_t stride_q, int64_t st
   if ((rc = require_device(out_t, "out_t", fn))) return rc;
   return cuda_rc(launch_lsap(cost, stride_b, stride_q, stride_t, n_targets, B, Q, (long long*)out_q,
                              (long long*)out_t, out_stride, (cudaStream_t)stream), fn);
+}
+
+static int mask_loss_args(const char* fn, const void* logits, int x_dtype, int64_t& row_stride, const float* tgt,
+                          int64_t M, int64_t N) {
+  int rc;
+  if (M <= 0 || N <= 0 || (N & 3)) {
+    set_error("%s: M and N must be positive, N a multiple of 4 (got %lld, %lld)", fn, (long long)M, (long long)N);
+    return DFINE_E_SHAPE;
+  }
+  if (row_stride == 0) row_stride = N;
+  if (row_stride < N || (row_stride & 3)) {
+    set_error("%s: row_stride %lld must be >= N and a multiple of 4", fn, (long long)row_stride);
+    return DFINE_E_SHAPE;
+  }
+  if (x_dtype != DFINE_F32 && x_dtype != DFINE_BF16) {
+    set_error("%s: x_dtype must be DFINE_F32 or DFINE_BF16", fn);
+    return DFINE_E_UNSUPPORTED;
+  }
+  if ((rc = require_device(logits, "logits", fn))) return rc;
+  if ((rc = require_device(tgt, "tgt", fn))) return rc;
+  if (!aligned16(logits) || !aligned16(tgt)) {
+    set_error("%s: logits and tgt must be 16-byte aligned", fn);
+    return DFINE_E_ALIGN;
+  }
+  return 0;
+}
+
+int dfine_mask_loss_fwd(const void* logits, int x_dtype, int64_t row_stride, const float* tgt, int64_t M, int64_t N,
+                        float* stats, void* stream) {
+  const char* fn = "dfine_mask_loss_fwd";
+  int rc;
+  if ((rc = mask_loss_args(fn, logits, x_dtype, row_stride, tgt, M, N))) return rc;
+  if ((rc = require_device(stats, "stats", fn))) return rc;
+  if (!aligned16(stats)) {
+    set_error("%s: stats must be 16-byte aligned", fn);
+    return DFINE_E_ALIGN;
+  }
+  return cuda_rc(launch_mask_loss_fwd(logits, x_dtype == DFINE_BF16, row_stride, tgt, M, N, stats,
+                                      (cudaStream_t)stream), fn);
+}
+
+int dfine_mask_loss_bwd(const void* logits, int x_dtype, int64_t row_stride, const float* tgt, int64_t M, int64_t N,
+                        const float* stats, const float* gstats, void* grad_logits, int g_dtype, void* stream) {
+  const char* fn = "dfine_mask_loss_bwd";
+  int rc;
+  if ((rc = mask_loss_args(fn, logits, x_dtype, row_stride, tgt, M, N))) return rc;
+  if (g_dtype != DFINE_F32 && g_dtype != DFINE_BF16) {
+    set_error("%s: g_dtype must be DFINE_F32 or DFINE_BF16", fn);
+    return DFINE_E_UNSUPPORTED;
+  }
+  if ((rc = require_device(stats, "stats", fn))) return rc;
+  if ((rc = require_device(gstats, "gstats", fn))) return rc;
+  if ((rc = require_device(grad_logits, "grad_logits", fn))) return rc;
+  if (!aligned16(stats) || !aligned16(gstats) || !aligned16(grad_logits)) {
+    set_error("%s: stats, gstats and grad_logits must be 16-byte aligned", fn);
+    return DFINE_E_ALIGN;
+  }
+  return cuda_rc(launch_mask_loss_bwd(logits, x_dtype == DFINE_BF16, row_stride, tgt, M, N, stats, gstats,
+                                      grad_logits, g_dtype == DFINE_BF16, (cudaStream_t)stream), fn);
 }
 
 }  // extern "C"

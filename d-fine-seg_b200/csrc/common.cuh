@@ -55,12 +55,6 @@ struct MsdaParams {
   int samp_rs, attn_rs;  // row strides (elements) of samp / attn per (b, q); contiguous: 2HP / HP
   int gsamp_rs, gattn_rs;  // same for grad_samp / grad_attn
   int gs_bf16;           // bwd: grad_samp / grad_attn are bf16
-  // tiled kernels (msda_tiled.cuh): per level, byte offset of its head-slice tile inside the
-  // CTA's shared-memory tile region (-1: not staged, gathered from global memory), the rows
-  // one TMA box carries and the number of boxes
-  int tile_off[kMaxLevels], tile_rows[kMaxLevels], tile_loads[kMaxLevels];
-  int tile_bytes;        // total bytes of the staged tiles (= mbarrier transaction count)
-  int tiled;             // fwd: DFINE_MSDA_TILED was requested
 };
 
 // One bilinear sample: integer corner origin + the four fractional factors.
@@ -150,7 +144,6 @@ __device__ __forceinline__ float warp_sum(float v) {
 void set_error(const char* fmt, ...);
 
 int launch_msda_fwd(const MsdaParams& p, int value_dtype, cudaStream_t s);
-int launch_msda_fwd_tiled(MsdaParams p, int value_dtype, cudaStream_t s);   // DFINE_E_UNSUPPORTED: use the plain kernel
 int launch_msda_bwd(const MsdaParams& p, int value_dtype, bool scatter, cudaStream_t s);
 int launch_msda_bwd_value(const MsdaParams& p, void* grad_value, int gv_bf16, int accumulate,
                           cudaStream_t s);

@@ -169,11 +169,6 @@ static int launch_fwd_t(const MsdaParams& p, cudaStream_t s) {
 }
 
 int launch_msda_fwd(const MsdaParams& p, int value_dtype, cudaStream_t s) {
-  // opt-in (DFINE_MSDA_TILED): persistent CTAs with the small levels resident in shared memory
-  if (p.tiled) {
-    const int rt = launch_msda_fwd_tiled(p, value_dtype, s);
-    if (rt != DFINE_E_UNSUPPORTED) return rt;
-  }
   // lanes per corner = bytes of one head slice / 16
   const int lpc = p.c * (value_dtype == DFINE_BF16 ? 2 : 4) / 16;
   if (value_dtype == DFINE_BF16) {

@@ -19,7 +19,6 @@ MSDA_FORCE_ATOMIC = 4
 MSDA_GRAD_SAMP_BF16 = 8
 MSDA_RECORDS_VALID = 16
 MSDA_GRAD_VALUE_ACCUMULATE = 32
-MSDA_TILED = 64
 MSDA_BWD_DOTS_ONLY = 128
 MSDA_BWD_VALUE_ONLY = 256
 E_NULL, E_SHAPE, E_UNSUPPORTED, E_ALIGN = -1, -2, -3, -4
@@ -53,6 +52,9 @@ _SIGNATURES = {
                                   c_void_p, c_int, c_void_p]),
     "dfine_mask_gemm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                     c_int, c_int, c_void_p]),
+    "dfine_mask_loss_fwd": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+    "dfine_mask_loss_bwd": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                                    c_int, c_void_p]),
     "dfine_lsap": (c_int, [c_void_p, c_int64, c_int64, c_int64, _I32P, c_int, c_int, c_void_p, c_void_p, c_int64,
                            c_void_p]),
     "dfine_mask_gemm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,

@@ -19,7 +19,7 @@ LIB_DIR = os.path.join(PKG_DIR, "_C")
 # DFINE_B200_LIB: load another build of the same C-ABI (A/B measurements of kernel variants)
 LIB_PATH = os.environ.get("DFINE_B200_LIB") or os.path.join(LIB_DIR, "libdfine_b200.so")
 
-SOURCES = ["api.cu", "msda_fwd.cu", "msda_fwd_tiled.cu", "msda_bwd.cu", "msda_bwd_value.cu", "fdr.cu", "mask_gemm.cu", "wgrad_gemm.cu", "reduce.cu", "lsap.cu"]
+SOURCES = ["api.cu", "msda_fwd.cu", "msda_bwd.cu", "msda_bwd_value.cu", "fdr.cu", "mask_gemm.cu", "wgrad_gemm.cu", "reduce.cu", "lsap.cu", "mask_loss.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--use_fast_math=false",
@@ -43,7 +43,7 @@ def is_stale() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps = sources() + [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "msda_common.cuh"), os.path.join(CSRC, "tma_util.cuh"), os.path.join(CSRC, "msda_tiled.cuh"), os.path.join(CSRC, "umma_util.cuh"),
+    deps = sources() + [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "msda_common.cuh"), os.path.join(CSRC, "tma_util.cuh"), os.path.join(CSRC, "umma_util.cuh"),
             os.path.join(INCLUDE, "dfine_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 

@@ -16,6 +16,10 @@ reference's own code:
   pairs, the reference's own two ATen CPU operators (its result depends on their unstable sort), a
   vectorised first-occurrence selection, and one copy back.
 
+* `loss_masks` (dfine_criterion.py:314-357): the focal-BCE + dice chain over the matched mask rows as one
+  fused kernel (`dfine_mask_loss_fwd / _bwd`), and -- with `patch_model(model, mask="matched")` -- the mask
+  logits themselves contracted for the matched rows only (`modules.LazyMaskLogits`).
+
 `unpatch_criterion` restores the reference methods.
 """
 from __future__ import annotations
@@ -162,10 +166,43 @@ def _get_go_indices(self, indices, indices_aux_list):
     return go_indices_host(indices, indices_aux_list)
 
 
-def patch_criterion(loss_fn) -> dict:
+def _loss_masks(self, outputs, targets, indices, num_boxes):
+    """DFINECriterion.loss_masks (reference dfine_criterion.py:314-357) for deferred mask logits
+    (modules.LazyMaskLogits): only the matched rows are contracted, and the focal-BCE + dice chain over them
+    is one fused kernel (dfine_mask_loss_fwd / _bwd).  Dense tensors take the same fused loss."""
+    from .modules import LazyMaskLogits
+    if "pred_masks" not in outputs:
+        return {}
+    pm = outputs["pred_masks"]
+    lazy = isinstance(pm, LazyMaskLogits)
+    B, Q, Hm, Wm = pm.shape
+    b_idx, q_idx = self._get_src_permutation_idx(indices)
+    dev = pm.coef.device if lazy else pm.device
+    if b_idx.numel() == 0:
+        zero = (pm.coef.sum() if lazy else pm.sum()) * 0
+        return {"loss_mask_bce": zero, "loss_mask_dice": zero}
+    if lazy:
+        pred_sel = pm.rows(b_idx, q_idx, [int(src.shape[0]) for src, _ in indices])
+    else:
+        pred_sel = pm[b_idx, q_idx]
+    tgt_sel, valid = self._prepare_target_masks(targets, indices, Hm, Wm, device=dev)
+    if valid == 0:
+        zero = pred_sel.sum() * 0
+        return {"loss_mask_bce": zero, "loss_mask_dice": zero}
+    if pred_sel.shape[0] != tgt_sel.shape[0]:
+        raise AssertionError(f"Mismatch between number of selected predictions ({pred_sel.shape[0]})"
+                             f"and target masks ({tgt_sel.shape[0]})")
+    if pred_sel.is_cuda and pred_sel.dtype in (torch.float32, torch.bfloat16) and (Hm * Wm) % 4 == 0:
+        bce, dice = ops.mask_losses(pred_sel, tgt_sel)
+    else:   # dtypes / shapes the fused kernel does not take: the reference's own two functions
+        bce, dice = self._focal_loss_mask(pred_sel, tgt_sel), self._dice_loss(pred_sel, tgt_sel)
+    return {"loss_mask_bce": bce, "loss_mask_dice": dice}
+
+
+def patch_criterion(loss_fn, masks: bool = True) -> dict:
     """Route the matching stage of a built reference criterion through the device.  Returns what was
     patched.  The loss terms themselves stay the reference's code."""
-    done = {"matcher": 0, "go_indices": 0}
+    done = {"matcher": 0, "go_indices": 0, "loss_masks": 0}
     m = getattr(loss_fn, "matcher", None)
     if m is not None and hasattr(m, "cost_bbox") and "_b200_saved" not in m.__dict__:
         m.__dict__["_b200_saved"] = {"forward": m.forward}
@@ -175,6 +212,9 @@ def patch_criterion(loss_fn) -> dict:
         loss_fn.__dict__["_b200_saved"] = {"_get_go_indices": loss_fn.__dict__.get("_get_go_indices", _MISSING)}
         loss_fn.__dict__["_get_go_indices"] = types.MethodType(_get_go_indices, loss_fn)
         done["go_indices"] = 1
+        if masks and hasattr(loss_fn, "loss_masks") and hasattr(loss_fn, "_prepare_target_masks"):
+            loss_fn.__dict__["loss_masks"] = types.MethodType(_loss_masks, loss_fn)
+            done["loss_masks"] = 1
     return done
 
 
@@ -187,3 +227,4 @@ def unpatch_criterion(loss_fn) -> None:
     saved = loss_fn.__dict__.pop("_b200_saved", None)
     if saved:
         loss_fn.__dict__.pop("_get_go_indices", None)
+        loss_fn.__dict__.pop("loss_masks", None)

@@ -137,6 +137,58 @@ def _mask_logits_from_h(self, h, mask_feat):
     return ops.mask_logits(mask_embed, mask_feat)
 
 
+class LazyMaskLogits:
+    """Deferred mask assembly for training.
+
+    The criterion reads `pred_masks` only at the matched (image, query) pairs
+    (`pred_masks[b_idx, q_idx]`, reference dfine_criterion.py:336), but which pairs are matched is known
+    only after the Hungarian step inside the criterion.  With `patch_model(model, mask="matched")` the
+    training forward returns this object in place of the dense [B, Q, h, w] logits of
+    `_mask_logits_from_h` (dfine_decoder.py:937-940): it keeps the mask embeddings `coef` [B, Q, C] and the
+    prototypes `mask_feat` [B, C, h, w]; `rows(b_idx, q_idx, counts)` then contracts ONLY the requested rows
+    (packed per image, one tensor-core GEMM [B, max rows, C] x [B, C, h*w]).  `dense()` gives the reference's
+    tensor (for code that needs all of it)."""
+
+    def __init__(self, coef: torch.Tensor, mask_feat: torch.Tensor):
+        self.coef, self.mask_feat = coef, mask_feat
+
+    @property
+    def shape(self):
+        return torch.Size((self.coef.shape[0], self.coef.shape[1], *self.mask_feat.shape[-2:]))
+
+    def _contract(self, coef):
+        bf16 = (torch.get_autocast_dtype("cuda") == torch.bfloat16 if torch.is_autocast_enabled()
+                else coef.dtype == torch.bfloat16 and self.mask_feat.dtype == torch.bfloat16)
+        K, N = coef.shape[-1], self.mask_feat.shape[-1] * self.mask_feat.shape[-2]
+        if (bf16 or self.mask_feat.dtype == torch.bfloat16) and coef.is_cuda and ops.mask_gemm_bwd_supported(K, N):
+            return ops.mask_logits(coef, self.mask_feat)
+        return torch.einsum("bqc,bchw->bqhw", coef.to(self.mask_feat.dtype), self.mask_feat)
+
+    def dense(self) -> torch.Tensor:
+        return self._contract(self.coef)
+
+    def rows(self, b_idx: torch.Tensor, q_idx: torch.Tensor, counts) -> torch.Tensor:
+        """Logits [M, h, w] of the pairs (b_idx[k], q_idx[k]); the pairs are grouped by image in ascending
+        image order (as `_get_src_permutation_idx` builds them) and counts[b] of them belong to image b
+        (host ints: no synchronisation)."""
+        B, _, C = self.coef.shape
+        R = max(1, max(int(c) for c in counts))
+        dev = self.coef.device
+        r_idx = torch.cat([torch.arange(int(c)) for c in counts]).to(dev, non_blocking=True)
+        slot = b_idx.to(dev) * R + r_idx
+        packed = self.coef.new_zeros((B * R, C)).index_copy(0, slot, self.coef[b_idx, q_idx])
+        out = self._contract(packed.view(B, R, C))
+        return out.reshape(B * R, *out.shape[-2:]).index_select(0, slot)
+
+
+def _lazy_mask_logits_from_h(self, h, mask_feat):
+    """Training-time `_mask_logits_from_h` under mask="matched": the contraction is deferred to the
+    criterion (LazyMaskLogits); evaluation keeps the dense tensor-core contraction."""
+    if not self.training:
+        return _mask_logits_from_h(self, h, mask_feat)
+    return LazyMaskLogits(self.mask_head(h), mask_feat)
+
+
 def _is_msda(m: nn.Module) -> bool:
     return all(hasattr(m, a) for a in ("ms_deformable_attn_core", "sampling_offsets",
                                        "attention_weights", "num_points_list", "num_points_scale"))
@@ -154,8 +206,13 @@ def _swap(m: nn.Module, attr: str, new) -> None:
     m.__dict__[attr] = new
 
 
-def patch_model(model: nn.Module, fused: bool = True, fdr: bool = True, mask: bool = True) -> dict:
+def patch_model(model: nn.Module, fused: bool = True, fdr: bool = True, mask=True) -> dict:
     """Route the decoder hot path of a built reference model through libdfine_b200.so.
+
+    mask: True -- the dense mask contraction on tensor cores (same output dict as the reference);
+    "matched" (opt-in, changes the training output contract: needs `patch_criterion(loss_fn)`) -- in
+    training the dense [B, Q, h, w] logits are never materialised, the criterion contracts only the matched
+    rows (LazyMaskLogits); False -- the reference's einsum.
 
     fused=False only swaps `ms_deformable_attn_core` (the reference's own hook); fused=True
     additionally replaces MSDeformableAttention.forward so that softmax + location
@@ -176,7 +233,8 @@ def patch_model(model: nn.Module, fused: bool = True, fdr: bool = True, mask: bo
             _swap(m, "forward", types.MethodType(_integral_forward, m))
             n["integral"] += 1
         elif mask and hasattr(m, "_mask_logits_from_h") and hasattr(m, "mask_head"):
-            _swap(m, "_mask_logits_from_h", types.MethodType(_mask_logits_from_h, m))
+            _swap(m, "_mask_logits_from_h",
+                  types.MethodType(_lazy_mask_logits_from_h if mask == "matched" else _mask_logits_from_h, m))
             n["mask"] += 1
     return n
 

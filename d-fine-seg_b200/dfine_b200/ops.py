@@ -191,10 +191,9 @@ def _mem_strides(memory: torch.Tensor) -> Tuple[int, int]:
 def msda_forward_raw(memory, spec: LevelSpec, H: int, samp, attn, ref, pts_scale,
                      offset_scale: float, fused: bool, out_dtype: torch.dtype,
                      want_idx: bool = False, samp_rs: int = 0, attn_rs: int = 0,
-                     records: Optional[torch.Tensor] = None, tiled: bool = False):
+                     records: Optional[torch.Tensor] = None):
     """Direct call of dfine_msda_fwd (no autograd).  Returns out [B, Lq, C] (, idx).
-    samp_rs / attn_rs: row strides (elements) when samp / attn alias a wider tensor.
-    tiled: ask for the TMA-staged persistent kernel (DFINE_MSDA_TILED)."""
+    samp_rs / attn_rs: row strides (elements) when samp / attn alias a wider tensor."""
     _require_cuda(memory, samp, attn, ref, pts_scale)
     B, L, C = memory.shape
     c = C // H
@@ -208,7 +207,7 @@ def msda_forward_raw(memory, spec: LevelSpec, H: int, samp, attn, ref, pts_scale
             memory.data_ptr(), sb, sl, spec.hw_c, spec.start_c, spec.npts_c, spec.n_lvl,
             samp.data_ptr(), attn.data_ptr(), _ptr(ref), _ptr(pts_scale), float(offset_scale),
             out.data_ptr(), _ptr(idx), B, Lq, H, c, _dt(memory, "value"), _dt(samp, "samp"),
-            _dt(out, "out"), (MSDA_FUSED_INPUTS if fused else 0) | (_lib.MSDA_TILED if tiled else 0),
+            _dt(out, "out"), (MSDA_FUSED_INPUTS if fused else 0),
             samp_rs, attn_rs, _ptr(records),
             _stream(memory))
     check(rc, "dfine_msda_fwd")
@@ -987,3 +986,56 @@ def lsap(cost: torch.Tensor, n_targets: Sequence[int]):
                                    _lib.i32_array(n), B, Q, out[0].data_ptr(), out[1].data_ptr(), K, _stream(cost))
     check(rc, "dfine_lsap")
     return out[0], out[1]
+
+
+# --------------------------------------------------------------------------------------
+# K6  mask loss over the matched rows (fused focal-BCE + dice statistics)
+# --------------------------------------------------------------------------------------
+class _MaskLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, tgt):
+        M, N = logits.shape
+        stats = torch.empty((M, 4), dtype=torch.float32, device=logits.device)
+        with torch.cuda.device_of(logits), _timed("mask_loss_fwd", logits):
+            rc = _lib.lib().dfine_mask_loss_fwd(logits.data_ptr(), _dt(logits, "logits"), logits.stride(0),
+                                                tgt.data_ptr(), M, N, stats.data_ptr(), _stream(logits))
+        check(rc, "dfine_mask_loss_fwd")
+        ctx.save_for_backward(logits, tgt, stats)
+        return stats
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_stats):
+        logits, tgt, stats = ctx.saved_tensors
+        M, N = logits.shape
+        g_stats = g_stats.to(torch.float32).contiguous()
+        grad = torch.empty((M, N), dtype=logits.dtype, device=logits.device)
+        with torch.cuda.device_of(logits), _timed("mask_loss_bwd", logits):
+            rc = _lib.lib().dfine_mask_loss_bwd(logits.data_ptr(), _dt(logits, "logits"), logits.stride(0),
+                                                tgt.data_ptr(), M, N, stats.data_ptr(), g_stats.data_ptr(),
+                                                grad.data_ptr(), _dt(grad, "grad"), _stream(logits))
+        check(rc, "dfine_mask_loss_bwd")
+        return grad, None
+
+
+def mask_loss_stats(logits: torch.Tensor, tgt: torch.Tensor) -> torch.Tensor:
+    """Per-row statistics of the mask loss (reference dfine_criterion.py:273-312) for logits [M, N]
+    (float32 / bfloat16) and targets [M, N] (float32): [M, 4] = {sum focal, sum p t, sum p, sum t}."""
+    _require_cuda(logits, tgt)
+    if logits.dim() != 2 or tgt.shape != logits.shape:
+        raise ValueError("mask_loss_stats: logits and tgt must be [M, N] tensors of the same shape")
+    if logits.stride(1) != 1:
+        logits = logits.contiguous()
+    tgt = tgt.to(torch.float32).contiguous()
+    return _MaskLossFn.apply(logits, tgt)
+
+
+def mask_losses(logits: torch.Tensor, tgt: torch.Tensor, eps: float = 1e-6):
+    """(loss_mask_bce, loss_mask_dice) of DFINECriterion._focal_loss_mask / _dice_loss
+    (dfine_criterion.py:273-312) for pred_sel [M, h, w] and tgt_sel [M, h, w]."""
+    M = logits.shape[0]
+    st = mask_loss_stats(logits.reshape(M, -1), tgt.reshape(M, -1))
+    n = logits[0].numel()
+    bce = (st[:, 0] / n).mean()
+    dice = (1.0 - (2.0 * st[:, 1] + eps) / (st[:, 2] + st[:, 3] + eps)).mean()
+    return bce, dice

@@ -59,9 +59,6 @@ extern "C" {
                                          (needs DFINE_MSDA_RECORDS_VALID; grad_samp / grad_attn may
                                          be NULL).  The two halves of the backward share no output:
                                          a caller can run them on two streams (ops.py does) */
-#define DFINE_MSDA_TILED 64          /* fwd: persistent CTAs, small pyramid levels staged in shared
-                                       memory by TMA (measured slower than the default kernel at
-                                       D-FINE shapes; kept selectable) */
 #define DFINE_MSDA_GRAD_VALUE_ACCUMULATE 32 /* bwd: grad_value += (the caller's running gradient of
                                                `memory` over the decoder layers, dfine_decoder.py:470-515) */
 
@@ -255,6 +252,26 @@ DFINE_API int dfine_mask_gemm_fwd(const void* coef, const void* proto, void* out
  * K a multiple of 128 and <= 256, N a multiple of 8, M arbitrary (DFINE_E_UNSUPPORTED otherwise). */
 DFINE_API int dfine_mask_gemm_bwd(const void* coef, const void* proto, const void* grad_out,
                         float* grad_coef, void* grad_proto, int B, int M, int K, int N, int gp_dtype,
+                        void* stream);
+
+/* --------------------------------------------------------------------------
+ * K6  mask loss over the matched mask rows: fused focal-BCE + dice statistics.
+ *
+ * Replaces the elementwise / reduction chain of DFINECriterion._focal_loss_mask and _dice_loss
+ * (src/d_fine/dfine_criterion.py:273-312) on pred_sel / tgt_sel of loss_masks (:336-357).
+ *   logits  x_dtype [M, N] (row_stride elements between rows, 0 = N): logits of the matched queries
+ *   tgt     float32 [M, N] contiguous: their ground-truth masks at mask resolution (values in [0, 1])
+ *   stats   float32 [M, 4] = {sum_n focal, sum_n p t, sum_n p, sum_n t} with p = sigmoid(x),
+ *           focal = alpha_t (1 - p_t)^2 BCEWithLogits(x, t), alpha from the row's foreground ratio (:279-282).
+ *           loss_mask_bce = mean_m(stats[m,0] / N); dice_m = 1 - (2 stats[m,1] + eps) / (stats[m,2] + stats[m,3] + eps)
+ * dfine_mask_loss_bwd: grad_logits[m, n] (g_dtype, contiguous [M, N]) from gstats [M, 4] = d loss / d stats
+ *   (the fourth column is ignored: the targets carry no gradient).
+ * N and row_stride multiples of 4, pointers 16-byte aligned.
+ * -------------------------------------------------------------------------- */
+DFINE_API int dfine_mask_loss_fwd(const void* logits, int x_dtype, int64_t row_stride, const float* tgt, int64_t M,
+                        int64_t N, float* stats, void* stream);
+DFINE_API int dfine_mask_loss_bwd(const void* logits, int x_dtype, int64_t row_stride, const float* tgt, int64_t M,
+                        int64_t N, const float* stats, const float* gstats, void* grad_logits, int g_dtype,
                         void* stream);
 
 /* --------------------------------------------------------------------------

@@ -205,6 +205,34 @@ def mask_gemm_bwd(coef, proto, grad_out):
     return np.einsum("bmn,bkn->bmk", g, p), np.einsum("bmk,bmn->bkn", coef, g).reshape(B, K, *tail)
 
 
+def mask_loss(pred, tgt, eps: float = 1e-6):
+    """Focal-BCE and dice loss over matched mask rows, and their gradients w.r.t. the logits (reference
+    src/d_fine/dfine_criterion.py:273-312), float64 numpy: returns (loss_bce, loss_dice, grad_bce, grad_dice,
+    stats [M, 4] = {sum focal, sum p t, sum p, sum t}).  Test infrastructure: the checker of
+    dfine_mask_loss_fwd / _bwd."""
+    x = np.asarray(pred, np.float64).reshape(pred.shape[0], -1)
+    t = np.asarray(tgt, np.float64).reshape(tgt.shape[0], -1)
+    M, N = x.shape
+    fg = t.mean(1, keepdims=True)
+    alpha = 0.5 + 0.25 * np.clip(1 - 2 * fg, -1, 1)
+    p = 1 / (1 + np.exp(-x))
+    bce = np.maximum(x, 0) - x * t + np.log1p(np.exp(-np.abs(x)))
+    pt = p * t + (1 - p) * (1 - t)
+    at = alpha * t + (1 - alpha) * (1 - t)
+    focal = at * (1 - pt) ** 2 * bce
+    stats = np.stack([focal.sum(1), (p * t).sum(1), p.sum(1), t.sum(1)], 1)
+    loss_bce = (stats[:, 0] / N).mean()
+    den = stats[:, 2] + stats[:, 3] + eps
+    loss_dice = (1 - (2 * stats[:, 1] + eps) / den).mean()
+    pq = p * (1 - p)
+    dfocal = at * ((1 - pt) ** 2 * (p - t) - 2 * (1 - pt) * (2 * t - 1) * pq * bce)
+    grad_bce = dfocal / (N * M)
+    g_inter = (-2 / den / M)[:, None]
+    g_psum = ((2 * stats[:, 1] + eps) / den ** 2 / M)[:, None]
+    grad_dice = (g_inter * t + g_psum) * pq
+    return loss_bce, loss_dice, grad_bce.reshape(pred.shape), grad_dice.reshape(pred.shape), stats
+
+
 def lsap(cost) -> Tuple[np.ndarray, np.ndarray]:
     """Rectangular linear-sum assignment of one float32 cost matrix [queries, targets] exactly as
     scipy.optimize.linear_sum_assignment solves it (reference src/d_fine/matcher.py:115): returns

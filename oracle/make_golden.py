@@ -17,6 +17,7 @@ Reference entry points exercised (all imported, nothing restated here):
   src/d_fine/arch/dfine_decoder.py:274  Integral
   src/d_fine/arch/utils.py:119   distance2bbox
   src/d_fine/arch/dfine_decoder.py:937  DFINETransformer._mask_logits_from_h
+  src/d_fine/dfine_criterion.py:273-312  DFINECriterion._focal_loss_mask / _dice_loss
 """
 from __future__ import annotations
 
@@ -278,6 +279,37 @@ def case_mask_bwd(ref):
                             logits=logits.detach().numpy(), grad_coef=h.grad.numpy(), grad_proto=feat.grad.numpy())
 
 
+def case_mask_loss(ref):
+    """DFINECriterion._focal_loss_mask / _dice_loss (dfine_criterion.py:273-312) on matched mask rows:
+    binary targets with small / large / empty / full foreground (the adaptive alpha, :279-282), one row of
+    soft target values, large-magnitude logits; losses and their gradients w.r.t. the logits."""
+    g = torch.Generator().manual_seed(41)
+    M, Hm, Wm = 7, 12, 20
+    pred = (torch.randn(M, Hm, Wm, generator=g) * 3.0)
+    pred[5] *= 12.0                                   # saturated sigmoid / large |x|
+    tgt = torch.zeros(M, Hm, Wm)
+    tgt[0, 2:5, 3:6] = 1                              # small foreground
+    tgt[1, :, :15] = 1                                # large foreground
+    tgt[2] = 0                                        # empty
+    tgt[3] = 1                                        # full
+    tgt[4] = (torch.rand(Hm, Wm, generator=g) < 0.5).float()
+    tgt[5] = (torch.rand(Hm, Wm, generator=g) < 0.3).float()
+    tgt[6] = torch.rand(Hm, Wm, generator=g)          # soft values (float masks)
+    out = dict(pred=pred.numpy().copy(), tgt=tgt.numpy().copy())
+    for name, fn in (("bce", ref.DFINECriterion._focal_loss_mask), ("dice", ref.DFINECriterion._dice_loss)):
+        p = pred.clone().requires_grad_(True)
+        loss = fn(p, tgt)
+        loss.backward()
+        out["loss_" + name] = np.asarray(loss.item(), np.float32)
+        out["grad_" + name] = p.grad.numpy().copy()
+    return "mask_loss", out
+
+
+def _criterion_class():
+    from src.d_fine.dfine_criterion import DFINECriterion  # noqa: E402
+    return DFINECriterion
+
+
 def load_reference(path: str):
     sys.path.insert(0, path)
     from src.d_fine.arch import dfine_decoder as dd  # noqa: E402
@@ -286,7 +318,7 @@ def load_reference(path: str):
         core=au.deformable_attention_core_func_v2, weighting_function=au.weighting_function,
         distance2bbox=au.distance2bbox, MSDeformableAttention=dd.MSDeformableAttention,
         Integral=dd.Integral, TransformerDecoder=dd.TransformerDecoder,
-        DFINETransformer=dd.DFINETransformer)
+        DFINETransformer=dd.DFINETransformer, DFINECriterion=_criterion_class())
 
 
 def main() -> None:
@@ -311,6 +343,7 @@ def main() -> None:
         case_fdr(ref),
         case_mask(ref),
         case_mask_bwd(ref),
+        case_mask_loss(ref),
     ]
     for name, arrs in cases:
         if a.only and name not in a.only.split(","):

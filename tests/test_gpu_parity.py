@@ -383,41 +383,6 @@ def test_full_size_properties(cfg, dev):
     assert (got - 1.0).abs().max().item() <= 1e-5
 
 
-@pytest.mark.parametrize("vdtype", [torch.bfloat16, torch.float32], ids=["bf16", "f32"])
-def test_tiled_forward_matches_plain(vdtype, dev):
-    """DFINE_MSDA_TILED (persistent CTAs, small levels staged in shared memory by TMA): same
-    corner indices bit for bit, same records, outputs equal to the default kernel up to the
-    fp32 summation order.  Shapes: config 3 with ragged segment boundaries (Lq odd), a
-    two-level head_dim-16 model and the 1024^2 pyramid where only the smallest level fits."""
-    import dfine_b200.ops as ops
-    torch.manual_seed(21)
-    for (B, Lq, H, c, shapes, npts) in [
-        (16, 301, 8, 32, [[80, 80], [40, 40], [20, 20]], [3, 6, 3]),
-        (24, 300, 8, 16, [[40, 40], [20, 20]], [6, 6]),
-        (4, 500, 8, 32, [[128, 128], [64, 64], [32, 32]], [4, 4, 4]),
-    ]:
-        spec = ops.level_spec(shapes, npts)
-        P = spec.P
-        mem = torch.randn(B, spec.L, H * c, device=dev).to(vdtype)
-        ref = torch.cat([torch.rand(B, Lq, 2, device=dev) * 1.1 - 0.05,
-                         torch.rand(B, Lq, 2, device=dev) * 0.5 + 0.02], -1)
-        raw_off = torch.randn(B, Lq, H, P, 2, device=dev).to(vdtype)
-        raw_log = torch.randn(B, Lq, H, P, device=dev).to(vdtype)
-        nps = torch.tensor([1.0 / n for n in npts for _ in range(n)], device=dev)
-        outs = []
-        for tiled in (False, True):
-            rec = ops.new_records(mem, spec, H, Lq)
-            rec.zero_()
-            out, idx = ops.msda_forward_raw(mem, spec, H, raw_off, raw_log, ref, nps, 0.5, True,
-                                            torch.float32, want_idx=True, records=rec, tiled=tiled)
-            outs.append((out, idx, rec))
-        (o0, i0, r0), (o1, i1, r1) = outs
-        assert torch.equal(i0, i1), "corner indices differ"
-        assert (i0 < 0).float().mean() > 0.005, "test should exercise out-of-bounds corners"
-        assert torch.equal(r0, r1), "geometry records differ"
-        assert rel_err(o1.cpu().numpy(), o0.cpu().numpy()) <= FP32_RTOL, (B, Lq, c, shapes)
-
-
 def test_mask_gemm(dev):
     """tcgen05 GEMM vs golden (reference einsum on bf16-representable inputs) and vs
     torch.bmm at the config-4 shape; bf16 products are exact in fp32, so only the
@@ -1080,3 +1045,51 @@ def test_no_out_of_bounds_writes(dev):
     assert intact(r_b, N * 16) and intact(r_gc, N * 132 * 4) and intact(r_mo, Bm * M * Nn * 2)
     want = torch.bmm(a.float(), bmat.float())
     assert rel_err(mo.view(Bm, M, Nn).float().cpu().numpy(), want.cpu().numpy()) <= BF16_RTOL
+
+
+@pytest.mark.parametrize("xdt", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_mask_loss_kernel(xdt, dev):
+    """dfine_mask_loss_fwd / _bwd (fused focal-BCE + dice over matched mask rows) against the reference's
+    own losses and gradients (golden: DFINECriterion._focal_loss_mask / _dice_loss, dfine_criterion.py:273-312,
+    binary / empty / full / soft targets, saturated logits) and against the oracle at the mask resolution of
+    config 4 (rows of 160 x 160)."""
+    import dfine_b200.ops as ops
+    from oracle import cpu_oracle as O
+    g = golden("mask_loss")
+    # the kernel computes in fp32 on the logits as stored: for bf16 storage the reference values are
+    # recomputed by the oracle on the rounded logits (the golden pins the oracle, tests/test_oracle_golden.py)
+    pred = _t(g["pred"], dev).to(xdt)
+    tgt = _t(g["tgt"], dev)
+    o_bce, o_dice, o_gb, o_gd, o_stats = O.mask_loss(pred.float().cpu().numpy(), g["tgt"])
+    for which, want_loss, want_grad in (("bce", o_bce, o_gb), ("dice", o_dice, o_gd)):
+        p = pred.clone().requires_grad_(True)
+        bce, dice = ops.mask_losses(p, tgt)
+        loss = bce if which == "bce" else dice
+        loss.backward()
+        assert abs(float(loss) - want_loss) <= 1e-5 * abs(want_loss), (which, float(loss), want_loss)
+        assert p.grad.dtype == xdt
+        assert_close(p.grad.float().cpu().numpy(), want_grad, 1e-5 if xdt == torch.float32 else BF16_RTOL,
+                     f"d loss_mask_{which} / d logits")
+        if xdt == torch.float32:
+            assert abs(float(loss) - float(g["loss_" + which])) <= 1e-5 * abs(float(g["loss_" + which]))
+            assert_close(p.grad.cpu().numpy(), g["grad_" + which], 1e-5, f"golden grad_{which}")
+    st = ops.mask_loss_stats(pred.flatten(1), tgt.flatten(1))
+    assert_close(st.cpu().numpy(), o_stats, 1e-5, "row statistics")
+    # config-4 rows: 37 matched masks of 160 x 160, a strided logits view, rectangle targets
+    torch.manual_seed(5)
+    M, N = 37, 160 * 160
+    big = (torch.randn(M, N + 64, device=dev) * 4).to(xdt)
+    x = big[:, :N]
+    t = torch.zeros(M, 160, 160, device=dev)
+    for m in range(M):
+        t[m, 10 + m:60 + 2 * m, 20:40 + 3 * m] = 1
+    t = t.flatten(1)
+    xg = x.detach().clone().requires_grad_(True)     # (contiguous copy keeps .grad simple)
+    bce, dice = ops.mask_losses(xg.view(M, 160, 160), t.view(M, 160, 160))
+    (bce + 2 * dice).backward()
+    ob, od, ogb, ogd, ost = O.mask_loss(x.float().cpu().numpy(), t.cpu().numpy())
+    assert abs(float(bce) - ob) <= 1e-5 * ob and abs(float(dice) - od) <= 1e-5 * od
+    assert_close(ops.mask_loss_stats(x, t).cpu().numpy(), ost, 1e-5, "row statistics (strided rows)")
+    assert_close(xg.grad.float().cpu().numpy(), ogb + 2 * ogd, 1e-5 if xdt == torch.float32 else BF16_RTOL, "grad")
+    with pytest.raises(ValueError):
+        ops.mask_loss_stats(x, t[:, :100])

@@ -139,3 +139,13 @@ def test_linear_wgrad_restatement_matches_torch_autograd():
     dw, db = O.linear_wgrad(gy.numpy(), x.numpy())
     np.testing.assert_allclose(dw, w.grad.numpy(), rtol=1e-12, atol=1e-12)
     np.testing.assert_allclose(db, b.grad.numpy(), rtol=1e-12, atol=1e-12)
+
+
+def test_mask_loss():
+    # reference: DFINECriterion._focal_loss_mask / _dice_loss, dfine_criterion.py:273-312
+    g = golden("mask_loss")
+    bce, dice, g_bce, g_dice, _ = O.mask_loss(g["pred"], g["tgt"])
+    assert abs(bce - float(g["loss_bce"])) <= FP32_RTOL * abs(float(g["loss_bce"]))
+    assert abs(dice - float(g["loss_dice"])) <= FP32_RTOL * abs(float(g["loss_dice"]))
+    assert_close(g_bce, g["grad_bce"], FP32_RTOL, "d loss_mask_bce / d logits")
+    assert_close(g_dice, g["grad_dice"], FP32_RTOL, "d loss_mask_dice / d logits")
