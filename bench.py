@@ -410,6 +410,7 @@ def secondary_kernel_legs(device, peak: float, reps: int = 10):
     the bench line): config 2 (D-FINE-s inference, B=64, Lq=300: forward only), config 5
     (1024x1024, B=8, Lq=500, 3 levels x 4 points: forward + backward) and the config-4 mask
     assembly (16 x 500 x 256 x 160^2, bf16 out).  Same back-to-back timing as kernel_leg."""
+    import dfine_b200
     from dfine_b200 import ops
     H, c = 8, 32
     out = {}
