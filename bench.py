@@ -677,8 +677,61 @@ def full_model_leg(device, rank: int, world: int, dist_on: bool, steps: int, war
     res["d2h_bytes_per_step"] = (box_host.numel() + logit_host.numel()) * 4
     res["speedup"] = res["patched"]["imgs_per_s"] / res["reference"]["imgs_per_s"]
     out["infer_config2"] = res
+    # the patched model replayed from a CUDA graph (dfine_b200.GraphedInference: same kernels, one launch)
+    try:
+        graphed = dfine_b200.GraphedInference(patched, host_images.to(device), amp_dtype=torch.bfloat16)
+
+        def gstep():
+            o = graphed(host_images.to(device, non_blocking=True))
+            box_host.copy_(o["pred_boxes"], non_blocking=True)
+            logit_host.copy_(o["pred_logits"], non_blocking=True)
+
+        ms = timed(gstep, steps, warmup)
+        res["patched_graphed"] = {"ms_per_step": ms, "imgs_per_s": B * world / (ms / 1e3)}
+        res["speedup_graphed"] = res["patched_graphed"]["imgs_per_s"] / res["reference"]["imgs_per_s"]
+        del graphed
+    except Exception as exc:  # noqa: BLE001
+        res["patched_graphed"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
+    del model, patched
+    torch.cuda.empty_cache()
+
+    # ---- config 1's model and shape on this GPU: D-FINE-n, batch 1 (latency; the reference's own config-1 run is
+    #      the CPU one, see cpu_baseline / BASELINE.md) ----
+    try:
+        out["infer_config1_shape_gpu"] = _latency_leg(device, rank, world, steps, warmup, timed)
+    except Exception as exc:  # noqa: BLE001
+        out["infer_config1_shape_gpu"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
     return out
 
+
+def _latency_leg(device, rank, world, steps, warmup, timed):
+    import copy
+
+    import dfine_b200
+    from baseline import model_harness as MH
+    model, _ = MH.build("n", device, 640, False, seed=0)
+    model.eval()
+    patched = copy.deepcopy(model)
+    dfine_b200.patch_model(patched)
+    images, _ = MH.synthetic_batch(1, 640, "cpu", seed=rank_seed(rank))
+    host_images = images.pin_memory()
+    res = {"workload": "dfine_n_infer_640_b1 (full model, eval, no_grad, bf16 autocast; latency)", "images_per_gpu": 1,
+           "h2d_bytes_per_step": host_images.numel() * 4}
+    box_host = torch.empty(1, 300, 4).pin_memory()
+    graphed = dfine_b200.GraphedInference(patched, host_images.to(device), amp_dtype=torch.bfloat16)
+    for name, fn in {"reference": lambda x: MH.infer_step(model, x, torch.bfloat16),
+                     "patched": lambda x: MH.infer_step(patched, x, torch.bfloat16),
+                     "patched_graphed": graphed}.items():
+        def step(fn=fn):
+            o = fn(host_images.to(device, non_blocking=True))
+            box_host.copy_(o["pred_boxes"], non_blocking=True)
+            torch.cuda.current_stream(device).synchronize()     # latency: the result is on the host
+
+        ms = timed(step, max(steps, 20), warmup)
+        res[name] = {"ms_per_image": ms, "imgs_per_s": world / (ms / 1e3)}
+    res["speedup"] = res["reference"]["ms_per_image"] / res["patched"]["ms_per_image"]
+    res["speedup_graphed"] = res["reference"]["ms_per_image"] / res["patched_graphed"]["ms_per_image"]
+    return res
 
 
 def _seg_train_leg(device, rank, world, dist_on, steps, warmup, timed):

@@ -8,12 +8,12 @@ assignment on the device.  No CPU fallback exists.
 from . import _lib, build, criterion, grad_sync, ops
 from ._lib import DfineB200Error, library_path
 from .criterion import patch_criterion, unpatch_criterion
-from .modules import Integral, MSDeformableAttention, patch_model, unpatch_model
+from .modules import GraphedInference, Integral, LazyMaskLogits, MSDeformableAttention, patch_model, unpatch_model
 from .ops import (fdr_decode, fdr_integral, fdr_project, mask_logits, msda_core, msda_fused,
                   msda_fused_packed)
 
 __all__ = [
-    "MSDeformableAttention", "Integral", "patch_model", "unpatch_model", "msda_core",
+    "MSDeformableAttention", "Integral", "patch_model", "unpatch_model", "GraphedInference", "LazyMaskLogits", "msda_core",
     "msda_fused", "msda_fused_packed", "fdr_project", "fdr_integral", "fdr_decode", "mask_logits", "library_path",
     "DfineB200Error", "ops", "build", "grad_sync", "criterion", "patch_criterion", "unpatch_criterion",
 ]

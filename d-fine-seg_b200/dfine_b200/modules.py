@@ -250,3 +250,67 @@ def unpatch_model(model: nn.Module) -> None:
                 m.__dict__.pop(attr, None)
             else:
                 m.__dict__[attr] = old
+
+
+class GraphedInference:
+    """CUDA-graph replay of a model's evaluation forward ("graph-captured eval loop").
+
+    At small batch the reference's inference (src/infer/torch_model.py:303-344: eval, no_grad, optional
+    autocast) is launch-bound: the decoder loop (dfine_decoder.py:470-515) alone issues several hundred tiny
+    kernels per image.  The forward is captured once over static input / output buffers and replayed with
+    ONE launch per call; the kernels and their arithmetic are exactly those of the eager call (results are
+    bit-identical).  Works for a reference model with or without `patch_model`.
+
+        g = GraphedInference(model, example_images, amp_dtype=torch.bfloat16)
+        out = g(images)          # dict of tensors, valid until the next call
+
+    One graph per input shape (a new shape triggers a re-capture).  Inference only."""
+
+    def __init__(self, model: nn.Module, example: torch.Tensor, amp_dtype: Optional[torch.dtype] = None,
+                 warmup: int = 3):
+        if not example.is_cuda:
+            raise RuntimeError("GraphedInference needs CUDA tensors (there is no CPU path)")
+        self.model, self.amp_dtype, self.warmup = model, amp_dtype, warmup
+        self._graphs = {}
+        self._capture(example)
+
+    def _forward(self, x):
+        with torch.no_grad():
+            if self.amp_dtype is not None:
+                with torch.autocast("cuda", dtype=self.amp_dtype):
+                    return self.model(x)
+            return self.model(x)
+
+    def _capture(self, example: torch.Tensor):
+        if self.model.training:
+            raise RuntimeError("GraphedInference: call model.eval() first (inference only)")
+        dev = example.device
+        # The reference keeps its evaluation-size constants (HybridEncoder.pos_embed<i>, hybrid_encoder.py:458;
+        # DFINETransformer.anchors / valid_mask) as plain tensor attributes on the host and moves them with
+        # `.to(device)` in every forward -- a pageable host -> device copy, illegal under capture.  Placing
+        # them on the device once makes those `.to()` calls no-ops (values unchanged).
+        for m in self.model.modules():
+            for k, v in list(vars(m).items()):
+                if torch.is_tensor(v) and not v.is_cuda:
+                    setattr(m, k, v.to(dev))
+        static_in = example.detach().clone()
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(self.warmup):
+                self._forward(static_in)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_out = self._forward(static_in)
+        self._graphs[(tuple(example.shape), example.dtype)] = (graph, static_in, static_out)
+
+    def __call__(self, images: torch.Tensor):
+        key = (tuple(images.shape), images.dtype)
+        if key not in self._graphs:
+            self._capture(images)
+        graph, static_in, static_out = self._graphs[key]
+        static_in.copy_(images, non_blocking=True)
+        graph.replay()
+        return static_out

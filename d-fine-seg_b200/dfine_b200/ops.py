@@ -811,10 +811,22 @@ def fdr_project(up: torch.Tensor, reg_scale: torch.Tensor, reg_max: int = 32) ->
     return out
 
 
+_DEV_SCALARS = {}
+
+
 def _as_dev_scalar(v, like: torch.Tensor) -> torch.Tensor:
     if isinstance(v, torch.Tensor):
         return v.detach().to(device=like.device, dtype=torch.float32).reshape(-1)[:1].contiguous()
-    return torch.tensor([float(v)], dtype=torch.float32, device=like.device)
+    # Python scalars: one device tensor per (value, device), created once -- a fresh torch.tensor(...) would
+    # be a pageable host -> device copy on every call (a sync, and illegal under CUDA-graph capture)
+    key = (float(v), like.device)
+    t = _DEV_SCALARS.get(key)
+    if t is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("dfine_b200: scalar constant requested for the first time during CUDA-graph "
+                               "capture; run one eager warm-up call first")
+        t = _DEV_SCALARS[key] = torch.tensor([float(v)], dtype=torch.float32, device=like.device)
+    return t
 
 
 class _FdrFn(torch.autograd.Function):

@@ -532,3 +532,31 @@ def test_optimizer_steps_track_reference(dev, H, deterministic):
     assert abs(losses[0][0] - losses[1][0]) <= 1e-3 * abs(losses[0][0]), losses     # same weights: bf16 tolerance
     for a, b in zip(*losses):
         assert abs(a - b) <= 5e-2 * abs(a), losses
+
+
+@pytest.mark.parametrize("name,seg,batch", [("n", False, 1), ("s", False, 4), ("m", True, 2)], ids=["n_b1", "s_b4", "m_seg_b2"])
+def test_graphed_inference_bit_identical(name, seg, batch, dev, H):
+    """GraphedInference (CUDA-graph replay of the evaluation forward): the replayed
+    outputs equal the eager outputs of the same patched model bit for bit, for fresh inputs, and match the
+    unpatched reference within the inference tolerance."""
+    import dfine_b200
+    model, _ = H.build(name, dev, 640, seg)
+    model.eval()
+    patched = copy.deepcopy(model)
+    dfine_b200.patch_model(patched)
+    x0, _ = H.synthetic_batch(batch, 640, dev, seed=1, seg=seg)
+    x1, _ = H.synthetic_batch(batch, 640, dev, seed=2, seg=seg)
+    g = dfine_b200.GraphedInference(patched, x0, amp_dtype=torch.bfloat16)
+    for x in (x1, x0):
+        eager = H.infer_step(patched, x, torch.bfloat16)
+        got = g(x)
+        torch.cuda.synchronize()
+        assert sorted(got) == sorted(eager)
+        for k in eager:
+            assert torch.equal(got[k], eager[k]), k
+    want = H.infer_step(model, x0, torch.bfloat16)
+    for k in want:
+        assert _scale_err(got[k].float(), want[k].float()) <= 2e-2, k
+    with pytest.raises(RuntimeError):
+        patched.train()
+        dfine_b200.GraphedInference(patched, x0)
