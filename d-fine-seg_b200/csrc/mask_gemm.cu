@@ -30,6 +30,8 @@
 //       sums meet in L2 (red.global.add, like wgrad_gemm.cu).
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "umma_util.cuh"
 
@@ -280,6 +282,233 @@ mask_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------
+// Forward with the prototype tile RESIDENT in shared memory (K <= 256: every shipped mask head).
+// The kernel above pulls, per 128 x 256 output tile, its [128 x K] slice of coef AND the whole
+// [K x 256] prototype tile through L2: 192 KB of operands per 64 KB of output, 1.64 GB per call at
+// config 4 -- it runs at the L2 -> SM ingest limit (~12 TB/s), not at the HBM limit.  Here a CTA
+// takes a UNIT = (image, 256-pixel column block): the prototype tile is loaded ONCE (4 k-blocks of
+// 32 KB, each its own barrier pair) and reused by all ceil(M / 128) row tiles; only the small coef
+// k-blocks (16 KB) stream through a ring.  Operand ingest per output tile: 96 KB.  A prototype
+// k-block is released by the MMAs of the unit's LAST row tile, so the next unit's k-block 0 is in
+// flight while this unit's k-blocks 1..3 are still being consumed.
+// ---------------------------------------------------------------------------------------
+constexpr int BR_KB = 4;                                   // resident prototype k-blocks (K <= 256)
+constexpr int BR_A_STAGES = 4;
+// Epilogue warps: one per TMEM lane quarter.  (Two per quarter -- each draining 128 of the tile's 256
+// columns -- need 64 KB of store buffers, which leaves room for only a 2-stage coef ring: measured 157.8 us
+// against 130.8 us, the MMAs then starve on the coef loads.)
+constexpr int BR_EPI_WARPS = 4;
+constexpr int BR_THREADS = 64 + 32 * BR_EPI_WARPS;
+constexpr int BR_EPI_BYTES = BR_EPI_WARPS * 2 * EPI_BUF_BYTES;   // 64 KiB
+constexpr int BR_SMEM_BYTES = BR_KB * B_BYTES + BR_A_STAGES * A_BYTES + BR_EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+template <bool kOutBf16>
+__global__ void __launch_bounds__(BR_THREADS, 1)
+mask_gemm_bres_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                      const __grid_constant__ CUtensorMap map_o, int B, int M, int K, int N,
+                      int apply_sigmoid) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  unsigned char* smem_b = smem;                              // [BR_KB][B_BYTES]
+  unsigned char* smem_a = smem + BR_KB * B_BYTES;            // [BR_A_STAGES][A_BYTES]
+  unsigned char* smem_epi = smem_a + BR_A_STAGES * A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + BR_EPI_BYTES);
+  uint64_t* b_full = bars;                      // [BR_KB]
+  uint64_t* b_empty = bars + BR_KB;             // [BR_KB]
+  uint64_t* a_full = bars + 2 * BR_KB;          // [BR_A_STAGES]
+  uint64_t* a_empty = a_full + BR_A_STAGES;     // [BR_A_STAGES]
+  uint64_t* tmem_full = a_empty + BR_A_STAGES;  // [2]
+  uint64_t* tmem_empty = tmem_full + 2;         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+  const int n_tiles = (N + BLOCK_N - 1) / BLOCK_N;
+  const int k_blocks = K / BLOCK_K;             // <= BR_KB
+  const long long units = (long long)B * n_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < BR_KB; ++i) {
+      mbar_init(smem_u32(&b_full[i]), 1);
+      mbar_init(smem_u32(&b_empty[i]), 1);
+    }
+    for (int i = 0; i < BR_A_STAGES; ++i) {
+      mbar_init(smem_u32(&a_full[i]), 1);
+      mbar_init(smem_u32(&a_empty[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&tmem_full[i]), 1);
+      mbar_init(smem_u32(&tmem_empty[i]), BR_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+      int stage = 0;
+      uint32_t aphase = 0, uphase = 0;
+      for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+        const int nt = (int)(u % n_tiles);
+        const int b = (int)(u / n_tiles);
+        for (int mt = 0; mt < m_tiles; ++mt) {
+          for (int kb = 0; kb < k_blocks; ++kb) {
+            if (mt == 0) {
+              // this unit's prototype k-block (once the previous unit's last row tile is done with the slot)
+              mbar_wait(smem_u32(&b_empty[kb]), uphase ^ 1);
+              const uint32_t fb = smem_u32(&b_full[kb]);
+              mbar_expect_tx(fb, B_BYTES);
+              const uint32_t sb = smem_u32(smem_b + kb * B_BYTES);
+#pragma unroll
+              for (int j = 0; j < BLOCK_N / 64; ++j)
+                tma_load_3d(&map_b, sb + j * B_BOX_BYTES, fb, nt * BLOCK_N + j * 64, kb * BLOCK_K, b);
+            }
+            mbar_wait(smem_u32(&a_empty[stage]), aphase ^ 1);
+            const uint32_t fa = smem_u32(&a_full[stage]);
+            mbar_expect_tx(fa, A_BYTES);
+            tma_load_3d(&map_a, smem_u32(smem_a + stage * A_BYTES), fa, kb * BLOCK_K, mt * BLOCK_M, b);
+            if (++stage == BR_A_STAGES) {
+              stage = 0;
+              aphase ^= 1;
+            }
+          }
+        }
+        uphase ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0, as = 0;
+      uint32_t aphase = 0, uphase = 0, tphase = 0;
+      for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+        for (int mt = 0; mt < m_tiles; ++mt) {
+          mbar_wait(smem_u32(&tmem_empty[as]), tphase ^ 1);
+          tcgen05_fence_after();
+          const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+          for (int kb = 0; kb < k_blocks; ++kb) {
+            if (mt == 0) mbar_wait(smem_u32(&b_full[kb]), uphase);
+            mbar_wait(smem_u32(&a_full[stage]), aphase);
+            tcgen05_fence_after();
+            const uint32_t sa = smem_u32(smem_a + stage * A_BYTES);
+            const uint32_t sb = smem_u32(smem_b + kb * B_BYTES);
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              const uint64_t da = make_desc(sa + k * UMMA_K * 2, 16, 1024);
+              const uint64_t db = make_desc(sb + k * UMMA_K * 128, B_BOX_BYTES, 1024);
+              umma_bf16(tmem_d, da, db, make_idesc(false, true, BLOCK_N), (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(smem_u32(&a_empty[stage]));
+            if (mt == m_tiles - 1) umma_commit(smem_u32(&b_empty[kb]));   // last reader of this k-block
+            if (++stage == BR_A_STAGES) {
+              stage = 0;
+              aphase ^= 1;
+            }
+          }
+          umma_commit(smem_u32(&tmem_full[as]));
+          if (++as == 2) {
+            as = 0;
+            tphase ^= 1;
+          }
+        }
+        uphase ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue (as in mask_gemm_kernel) =====================
+    const int wq = warp & 3;                   // TMEM lane quarter this warp may access
+    const int chalf = (warp - 2) >> 2;         // which 128 columns of the tile this warp drains
+    constexpr int COLS = kOutBf16 ? 64 : 32;
+    unsigned char* my_buf = smem_epi + (warp - 2) * 2 * EPI_BUF_BYTES;
+    int as = 0;
+    uint32_t tphase = 0;
+    int buf = 0;
+    for (long long u = blockIdx.x; u < units; u += gridDim.x) {
+      const int nt = (int)(u % n_tiles);
+      const int b = (int)(u / n_tiles);
+      for (int mt = 0; mt < m_tiles; ++mt) {
+        const int row0 = mt * BLOCK_M + wq * 32;
+        mbar_wait(smem_u32(&tmem_full[as]), tphase);
+        tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + as * BLOCK_N + ((uint32_t)(wq * 32) << 16);
+        for (int c0 = chalf * (BLOCK_N / 2); c0 < (chalf + 1) * (BLOCK_N / 2); c0 += COLS) {
+          const int col0 = nt * BLOCK_N + c0;
+          const bool store = row0 < M && col0 < N;
+          uint32_t packed[32];
+#pragma unroll
+          for (int half = 0; half < COLS / 32; ++half) {
+            uint32_t r[32];
+            tmem_ld_32x32(taddr + c0 + half * 32, r);
+            if (apply_sigmoid) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                r[i] = __float_as_uint(1.0f / (1.0f + __expf(-__uint_as_float(r[i]))));
+            }
+            if (kOutBf16) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const __nv_bfloat162 v =
+                    __floats2bfloat162_rn(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+                packed[half * 16 + i] = *reinterpret_cast<const uint32_t*>(&v);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) packed[i] = r[i];
+            }
+          }
+          if (store) {
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+            unsigned char* dst = my_buf + buf * EPI_BUF_BYTES + lane * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              *reinterpret_cast<uint4*>(dst + ((j ^ (lane & 7)) << 4)) =
+                  make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&map_o, smem_u32(my_buf + buf * EPI_BUF_BYTES), col0, row0, b);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            buf ^= 1;
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[as]));
+        if (++as == 2) {
+          as = 0;
+          tphase ^= 1;
+        }
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(TMEM_COLS));
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // grad_coef[b, m, k] = sum_n go[b, m, n] * proto[b, k, n]
 // One CTA per (image, 128-row tile of queries, split of the n range); 192 threads, same roles
 // as above.  A = go box [128 m][64 n] (K-major), B = proto box [K channels][64 n] (K-major):
@@ -504,6 +733,26 @@ int launch_mask_gemm(const void* coef, const void* proto, void* out, int B, int 
     return rc;
 
   const int sms = sm_count();
+  if (K <= BR_KB * BLOCK_K && !getenv("DFINE_MASK_GEMM_STREAMING")) {
+    // prototype tile resident in shared memory, reused by all row tiles of the unit
+    static PerDeviceOnce configured;
+    if (!configured.done()) {
+      cudaError_t e = cudaFuncSetAttribute(mask_gemm_bres_kernel<true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, BR_SMEM_BYTES);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(mask_gemm_bres_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 BR_SMEM_BYTES);
+      if (e != cudaSuccess) return (int)e;
+      configured.mark();
+    }
+    const long long units = (long long)B * ((N + BLOCK_N - 1) / BLOCK_N);
+    const int g = (int)(units < sms ? units : sms);
+    if (obf)
+      mask_gemm_bres_kernel<true><<<g, BR_THREADS, BR_SMEM_BYTES, s>>>(map_a, map_b, map_o, B, M, K, N, apply_sigmoid);
+    else
+      mask_gemm_bres_kernel<false><<<g, BR_THREADS, BR_SMEM_BYTES, s>>>(map_a, map_b, map_o, B, M, K, N, apply_sigmoid);
+    return (int)cudaGetLastError();
+  }
   const long long tiles = (long long)B * ((M + BLOCK_M - 1) / BLOCK_M) * ((N + BLOCK_N - 1) / BLOCK_N);
   const int grid = (int)(tiles < sms ? tiles : sms);
   if ((rc = configure_gemm<false>())) return rc;
