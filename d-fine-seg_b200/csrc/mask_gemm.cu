@@ -299,6 +299,7 @@ constexpr int BR_A_STAGES = 4;
 // against 130.8 us, the MMAs then starve on the coef loads.)
 constexpr int BR_EPI_WARPS = 4;
 constexpr int BR_THREADS = 64 + 32 * BR_EPI_WARPS;
+constexpr int BR_COLS_PER_WARP = BLOCK_N / (BR_EPI_WARPS / 4);   // columns of a tile one epilogue warp drains
 constexpr int BR_EPI_BYTES = BR_EPI_WARPS * 2 * EPI_BUF_BYTES;   // 64 KiB
 constexpr int BR_SMEM_BYTES = BR_KB * B_BYTES + BR_A_STAGES * A_BYTES + BR_EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
@@ -444,7 +445,7 @@ mask_gemm_bres_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         mbar_wait(smem_u32(&tmem_full[as]), tphase);
         tcgen05_fence_after();
         const uint32_t taddr = tmem_base + as * BLOCK_N + ((uint32_t)(wq * 32) << 16);
-        for (int c0 = chalf * (BLOCK_N / 2); c0 < (chalf + 1) * (BLOCK_N / 2); c0 += COLS) {
+        for (int c0 = chalf * BR_COLS_PER_WARP; c0 < (chalf + 1) * BR_COLS_PER_WARP; c0 += COLS) {
           const int col0 = nt * BLOCK_N + c0;
           const bool store = row0 < M && col0 < N;
           uint32_t packed[32];
