@@ -34,6 +34,12 @@ int launch_mask_gemm_bwd(const void*, const void*, const void*, float*, void*, i
 int launch_colsum(const void*, int, long long, int, long long, float*, cudaStream_t);
 int launch_linear_wgrad(const void*, int64_t, const void*, int64_t, int, int, int, float*, cudaStream_t);
 int launch_multicast_add(const float*, float*, long long, float, cudaStream_t);
+int launch_linear_fwd(const void*, int, int64_t, const float*, int64_t, const void*, const void*, int, void*, int, int64_t,
+                      void*, int, int, int, int, cudaStream_t);
+int launch_gate_fwd(const float*, int64_t, const float*, int64_t, const void*, const void*, int, const float*,
+                    const float*, float, float*, int64_t, int, int, cudaStream_t);
+int launch_ffn_out_fwd(const void*, int64_t, const void*, const void*, int, const float*, int64_t, const float*,
+                       const float*, float, float*, int64_t, int, int, int, cudaStream_t);
 
 static int cuda_rc(int rc, const char* what) {
   if (rc > 0) set_error("%s: CUDA error %d (%s)", what, rc, cudaGetErrorString((cudaError_t)rc));
@@ -408,6 +414,135 @@ int dfine_linear_wgrad(const void* grad_y, int64_t gy_row_stride, const void* x,
   }
   return cuda_rc(launch_linear_wgrad(grad_y, gy_row_stride, x, x_row_stride, (int)M, N, K, dw_db,
                                      (cudaStream_t)stream), fn);
+}
+
+static int dtype_ok(int dt, const char* what, const char* fn) {
+  if (dt != DFINE_F32 && dt != DFINE_BF16) {
+    set_error("%s: %s must be DFINE_F32 or DFINE_BF16 (got %d)", fn, what, dt);
+    return DFINE_E_UNSUPPORTED;
+  }
+  return 0;
+}
+
+int dfine_linear_fwd(const void* x, int x_dtype, int64_t x_row_stride, const float* x_add, int64_t xadd_row_stride,
+                     const void* w, const void* bias, int bias_dtype, void* y, int y_dtype, int64_t y_row_stride,
+                     void* x_bf16_out, int64_t M, int N, int K, int relu, void* stream) {
+  const char* fn = "dfine_linear_fwd";
+  int rc;
+  if (M <= 0 || M > 0x7fffffffLL || N <= 0 || K <= 0) {
+    set_error("%s: need 0 < M < 2^31, N > 0, K > 0 (got %lld, %d, %d)", fn, (long long)M, N, K);
+    return DFINE_E_SHAPE;
+  }
+  if ((rc = dtype_ok(x_dtype, "x_dtype", fn)) || (rc = dtype_ok(bias_dtype, "bias_dtype", fn)) ||
+      (rc = dtype_ok(y_dtype, "y_dtype", fn)))
+    return rc;
+  if (x_row_stride == 0) x_row_stride = K;
+  if (xadd_row_stride == 0) xadd_row_stride = K;
+  if (y_row_stride == 0) y_row_stride = N;
+  if (x_row_stride < K || xadd_row_stride < K || y_row_stride < N || (x_row_stride & 7) || (xadd_row_stride & 3) ||
+      (y_row_stride & 7)) {
+    set_error("%s: row strides (%lld, %lld, %lld) must be >= (K, K, N) and multiples of 8 (x_add: 4) elements", fn,
+              (long long)x_row_stride, (long long)xadd_row_stride, (long long)y_row_stride);
+    return DFINE_E_SHAPE;
+  }
+  if (x_add && x_dtype == DFINE_BF16) {
+    set_error("%s: x_add needs float32 x (a bf16 input is loaded by TMA as it is)", fn);
+    return DFINE_E_UNSUPPORTED;
+  }
+  if (x_bf16_out && x_dtype == DFINE_BF16) {
+    set_error("%s: x_bf16_out needs float32 x", fn);
+    return DFINE_E_UNSUPPORTED;
+  }
+  if ((rc = require_device(x, "x", fn)) || (rc = require_device(w, "w", fn)) || (rc = require_device(bias, "bias", fn)) ||
+      (rc = require_device(y, "y", fn)))
+    return rc;
+  if (x_add && (rc = require_device(x_add, "x_add", fn))) return rc;
+  if (x_bf16_out && (rc = require_device(x_bf16_out, "x_bf16_out", fn))) return rc;
+  if (!aligned16(x) || !aligned16(w) || !aligned16(y) || (x_add && !aligned16(x_add)) ||
+      (x_bf16_out && !aligned16(x_bf16_out))) {
+    set_error("%s: x, x_add, w, y and x_bf16_out must be 16-byte aligned", fn);
+    return DFINE_E_ALIGN;
+  }
+  return cuda_rc(launch_linear_fwd(x, x_dtype == DFINE_BF16, x_row_stride, x_add, xadd_row_stride, w, bias,
+                                   bias_dtype == DFINE_BF16, y, y_dtype == DFINE_BF16, y_row_stride, x_bf16_out, (int)M,
+                                   N, K, relu, (cudaStream_t)stream), fn);
+}
+
+static int ln_common(const char* fn, int64_t M, int C, const float* ln_w, const float* ln_b, const float* out,
+                     int64_t* out_rs) {
+  int rc;
+  if (M <= 0 || M > 0x7fffffffLL || C <= 0 || (C & 63) || C > 256) {
+    set_error("%s: need 0 < M < 2^31 and C a multiple of 64, <= 256 (got %lld, %d)", fn, (long long)M, C);
+    return (C > 256 || (C & 63)) ? DFINE_E_UNSUPPORTED : DFINE_E_SHAPE;
+  }
+  if (*out_rs == 0) *out_rs = C;
+  if (*out_rs < C || (*out_rs & 3)) {
+    set_error("%s: out row stride %lld must be >= C and a multiple of 4", fn, (long long)*out_rs);
+    return DFINE_E_SHAPE;
+  }
+  if ((rc = require_device(ln_w, "ln_weight", fn)) || (rc = require_device(ln_b, "ln_bias", fn)) ||
+      (rc = require_device(out, "out", fn)))
+    return rc;
+  if (!aligned16(out)) {
+    set_error("%s: out must be 16-byte aligned", fn);
+    return DFINE_E_ALIGN;
+  }
+  return 0;
+}
+
+int dfine_gate_fwd(const float* x1, int64_t x1_row_stride, const float* x2, int64_t x2_row_stride, const void* w,
+                   const void* bias, int bias_dtype, const float* ln_weight, const float* ln_bias, float eps, float* out,
+                   int64_t out_row_stride, int64_t M, int C, void* stream) {
+  const char* fn = "dfine_gate_fwd";
+  int rc;
+  if ((rc = ln_common(fn, M, C, ln_weight, ln_bias, out, &out_row_stride))) return rc;
+  if ((rc = dtype_ok(bias_dtype, "bias_dtype", fn))) return rc;
+  if (x1_row_stride == 0) x1_row_stride = C;
+  if (x2_row_stride == 0) x2_row_stride = C;
+  if (x1_row_stride < C || x2_row_stride < C || (x1_row_stride & 3) || (x2_row_stride & 3)) {
+    set_error("%s: input row strides (%lld, %lld) must be >= C and multiples of 4", fn, (long long)x1_row_stride,
+              (long long)x2_row_stride);
+    return DFINE_E_SHAPE;
+  }
+  if ((rc = require_device(x1, "x1", fn)) || (rc = require_device(x2, "x2", fn)) || (rc = require_device(w, "w", fn)) ||
+      (rc = require_device(bias, "bias", fn)))
+    return rc;
+  if (!aligned16(x1) || !aligned16(x2) || !aligned16(w)) {
+    set_error("%s: x1, x2 and w must be 16-byte aligned", fn);
+    return DFINE_E_ALIGN;
+  }
+  return cuda_rc(launch_gate_fwd(x1, x1_row_stride, x2, x2_row_stride, w, bias, bias_dtype == DFINE_BF16, ln_weight,
+                                 ln_bias, eps, out, out_row_stride, (int)M, C, (cudaStream_t)stream), fn);
+}
+
+int dfine_ffn_out_fwd(const void* h, int64_t h_row_stride, const void* w, const void* bias, int bias_dtype,
+                      const float* residual, int64_t res_row_stride, const float* ln_weight, const float* ln_bias,
+                      float eps, float* out, int64_t out_row_stride, int64_t M, int C, int F, void* stream) {
+  const char* fn = "dfine_ffn_out_fwd";
+  int rc;
+  if ((rc = ln_common(fn, M, C, ln_weight, ln_bias, out, &out_row_stride))) return rc;
+  if ((rc = dtype_ok(bias_dtype, "bias_dtype", fn))) return rc;
+  if (F <= 0 || (F & 63)) {
+    set_error("%s: F must be a positive multiple of 64 (got %d)", fn, F);
+    return DFINE_E_UNSUPPORTED;
+  }
+  if (h_row_stride == 0) h_row_stride = F;
+  if (res_row_stride == 0) res_row_stride = C;
+  if (h_row_stride < F || (h_row_stride & 7) || res_row_stride < C || (res_row_stride & 3)) {
+    set_error("%s: row strides (%lld, %lld) must be >= (F, C) and multiples of (8, 4)", fn, (long long)h_row_stride,
+              (long long)res_row_stride);
+    return DFINE_E_SHAPE;
+  }
+  if ((rc = require_device(h, "h", fn)) || (rc = require_device(w, "w", fn)) || (rc = require_device(bias, "bias", fn)) ||
+      (rc = require_device(residual, "residual", fn)))
+    return rc;
+  if (!aligned16(h) || !aligned16(w) || !aligned16(residual)) {
+    set_error("%s: h, w and residual must be 16-byte aligned", fn);
+    return DFINE_E_ALIGN;
+  }
+  return cuda_rc(launch_ffn_out_fwd(h, h_row_stride, w, bias, bias_dtype == DFINE_BF16, residual, res_row_stride,
+                                    ln_weight, ln_bias, eps, out, out_row_stride, (int)M, C, F, (cudaStream_t)stream),
+                 fn);
 }
 
 int dfine_multicast_add(const float* src, float* dst_multicast, int64_t n, float scale, void* stream) {

@@ -19,10 +19,10 @@ LIB_DIR = os.path.join(PKG_DIR, "_C")
 # DFINE_B200_LIB: load another build of the same C-ABI (A/B measurements of kernel variants)
 LIB_PATH = os.environ.get("DFINE_B200_LIB") or os.path.join(LIB_DIR, "libdfine_b200.so")
 
-SOURCES = ["api.cu", "msda_fwd.cu", "msda_bwd.cu", "msda_bwd_value.cu", "fdr.cu", "mask_gemm.cu", "wgrad_gemm.cu", "reduce.cu", "lsap.cu", "mask_loss.cu"]
+SOURCES = ["api.cu", "msda_fwd.cu", "msda_bwd.cu", "msda_bwd_value.cu", "fdr.cu", "mask_gemm.cu", "wgrad_gemm.cu", "reduce.cu", "lsap.cu", "mask_loss.cu", "linear_fused.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--use_fast_math=false",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
 ]
 
 
@@ -60,7 +60,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
     for src in sources():
         obj = os.path.join(LIB_DIR, os.path.basename(src).replace(".cu", ".o"))
-        cmd = [nvcc, "-ccbin", host, *[f for f in NVCC_FLAGS if f != "--use_fast_math=false"],
+        cmd = [nvcc, "-ccbin", host, *NVCC_FLAGS,
                *os.environ.get("DFINE_NVCC_EXTRA", "").split(),   # e.g. -DDFINE_BV_PROF (debug builds)
                "-I", INCLUDE, "-I", CSRC, "-c", src, "-o", obj]
         if verbose:

@@ -24,12 +24,14 @@ from . import ops
 
 
 def _fused_forward(self, query: torch.Tensor, reference_points: torch.Tensor, value,
-                   value_spatial_shapes):
+                   value_spatial_shapes, query_pos: Optional[torch.Tensor] = None):
     """MSDeformableAttention.forward (reference dfine_decoder.py:119-178).
 
     query [bs, Lq, C]; reference_points [bs, Lq, 1, 4] (cx, cy, w, h) or [bs, Lq, n_levels, 2];
     value: tuple of per-level views [bs, H, c, h_l*w_l] from TransformerDecoder.value_op;
     value_spatial_shapes: [[h_l, w_l], ...].  Returns [bs, Lq, C].
+    query_pos (extension, used by the patched decoder layer): the positional embedding the caller would
+    have added to the query (with_pos_embed, dfine_decoder.py:245); the add runs inside the Linear's kernel.
     """
     bs, Lq = query.shape[:2]
     P = sum(self.num_points_list)
@@ -39,11 +41,15 @@ def _fused_forward(self, query: torch.Tensor, reference_points: torch.Tensor, va
         # through row strides, its gradient is written by the backward kernel in one piece
         so, aw = self.sampling_offsets, self.attention_weights
         if ops.packed_linear_supported(query, so.weight, so.bias, aw.weight, aw.bias):
-            raw = ops.packed_linear(query, so.weight, so.bias, aw.weight, aw.bias)
+            raw = ops.packed_linear(query, so.weight, so.bias, aw.weight, aw.bias, x_add=query_pos)
         else:   # parameters in another dtype / layout: concatenate with torch
+            if query_pos is not None:
+                query = query + query_pos
             raw = ops.fused_linear(query, torch.cat([so.weight, aw.weight], 0), torch.cat([so.bias, aw.bias], 0))
         return ops.msda_fused_packed(value, value_spatial_shapes, raw, reference_points,
                                      self.num_points_scale, self.num_points_list, self.offset_scale)
+    if query_pos is not None:
+        query = query + query_pos
     if last == 2:
         # legacy RT-DETR branch (dfine_decoder.py:149-155); not used by D-FINE.  Location
         # arithmetic stays in torch, sampling runs in the plain-mode kernel.
@@ -189,6 +195,63 @@ def _lazy_mask_logits_from_h(self, h, mask_feat):
     return LazyMaskLogits(self.mask_head(h), mask_feat)
 
 
+def _layer_tail_fusable(self, target: torch.Tensor) -> bool:
+    """The Gate / FFN / LayerNorm tail of a decoder layer can run in the fused kernels: inference (no autograd),
+    bf16 autocast (the kernels restate exactly that arithmetic), ReLU FFN, shapes the kernels take."""
+    if torch.is_grad_enabled() or not target.is_cuda or target.dtype != torch.float32:
+        return False
+    if not (torch.is_autocast_enabled() and torch.get_autocast_dtype("cuda") == torch.bfloat16):
+        return False
+    if self.training and any(d.p > 0 for d in (self.dropout2, self.dropout3, self.dropout4)):
+        return False
+    C = target.shape[-1]
+    g = getattr(self, "gateway", None)
+    if g is None or not isinstance(getattr(g, "gate", None), nn.Linear) or not isinstance(self.activation, nn.ReLU):
+        return False
+    Fdim = self.linear1.out_features
+    return (C % 64 == 0 and C <= 256 and Fdim % 64 == 0 and tuple(g.gate.weight.shape) == (2 * C, 2 * C)
+            and g.norm.elementwise_affine and self.norm3.elementwise_affine
+            and ops.linear_fwd_supported(target, Fdim))
+
+
+def _layer_forward(self, target, reference_points, value, spatial_shapes, attn_mask=None, query_pos_embed=None):
+    """TransformerDecoderLayer.forward (reference dfine_decoder.py:232-256), same signature and results.
+
+    Self-attention and norm1 are the reference's modules.  The cross-attention receives the positional embedding
+    separately (the add happens inside the fused Linear).  In inference under bf16 autocast the rest of the layer
+    is three launches: Gate (cat + Linear + sigmoid + mix + LayerNorm), linear1 + ReLU, linear2 + residual +
+    clamp + norm3; in training the reference modules run (autograd)."""
+    q = k = self.with_pos_embed(target, query_pos_embed)
+    target2, _ = self.self_attn(q, k, value=target, attn_mask=attn_mask)
+    target = target + self.dropout1(target2)
+    target = self.norm1(target)
+
+    ca = self.cross_attn
+    if "_b200_saved" in ca.__dict__ and "forward" in ca.__dict__["_b200_saved"]:
+        target2 = _fused_forward(ca, target, reference_points, value, spatial_shapes, query_pos=query_pos_embed)
+    else:
+        target2 = ca(self.with_pos_embed(target, query_pos_embed), reference_points, value, spatial_shapes)
+
+    if _layer_tail_fusable(self, target):
+        g = self.gateway
+        target = ops.gate_fwd(target.contiguous(), target2.float().contiguous(), ops.bf16_param(g.gate.weight),
+                              ops.bf16_param(g.gate.bias), g.norm.weight, g.norm.bias, g.norm.eps)
+        h = ops.linear_fwd(target, ops.bf16_param(self.linear1.weight), ops.bf16_param(self.linear1.bias), relu=True)
+        return ops.ffn_out_fwd(h, ops.bf16_param(self.linear2.weight), ops.bf16_param(self.linear2.bias), target,
+                               self.norm3.weight, self.norm3.bias, self.norm3.eps)
+
+    target = self.gateway(target, self.dropout2(target2))
+    target2 = self.forward_ffn(target)
+    target = target + self.dropout4(target2)
+    return self.norm3(target.clamp(min=-65504, max=65504))
+
+
+def _is_decoder_layer(m: nn.Module) -> bool:
+    return all(hasattr(m, a) for a in ("self_attn", "norm1", "cross_attn", "gateway", "linear1", "linear2", "norm3",
+                                       "dropout1", "dropout2", "dropout3", "dropout4", "with_pos_embed",
+                                       "forward_ffn", "activation"))
+
+
 def _is_msda(m: nn.Module) -> bool:
     return all(hasattr(m, a) for a in ("ms_deformable_attn_core", "sampling_offsets",
                                        "attention_weights", "num_points_list", "num_points_scale"))
@@ -206,7 +269,7 @@ def _swap(m: nn.Module, attr: str, new) -> None:
     m.__dict__[attr] = new
 
 
-def patch_model(model: nn.Module, fused: bool = True, fdr: bool = True, mask=True) -> dict:
+def patch_model(model: nn.Module, fused: bool = True, fdr: bool = True, mask=True, layer: bool = False) -> dict:
     """Route the decoder hot path of a built reference model through libdfine_b200.so.
 
     mask: True -- the dense mask contraction on tensor cores (same output dict as the reference);
@@ -217,10 +280,16 @@ def patch_model(model: nn.Module, fused: bool = True, fdr: bool = True, mask=Tru
     fused=False only swaps `ms_deformable_attn_core` (the reference's own hook); fused=True
     additionally replaces MSDeformableAttention.forward so that softmax + location
     arithmetic run inside the kernel.  Parameters, buffers and state-dict keys are untouched.
+    layer=True (with fused=True) additionally replaces TransformerDecoderLayer.forward (dfine_decoder.py:232-256):
+    the positional add is folded into the cross-attention's Linear kernel, and in inference under bf16 autocast
+    the Gate, the FFN and their LayerNorms run as three fused tensor-core launches.
     Returns the number of patched modules per kind.
     """
-    n = {"msda": 0, "integral": 0, "mask": 0}
+    n = {"msda": 0, "integral": 0, "mask": 0, "layer": 0}
     for m in model.modules():
+        if layer and fused and _is_decoder_layer(m) and _is_msda(m.cross_attn):
+            _swap(m, "forward", types.MethodType(_layer_forward, m))
+            n["layer"] += 1
         if _is_msda(m):
             method = getattr(m, "method", "default")
             if method != "default":

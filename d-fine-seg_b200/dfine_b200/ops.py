@@ -596,30 +596,168 @@ class _LinearFn(torch.autograd.Function):
         return gx, gw, gb
 
 
+def linear_fwd_supported(x: torch.Tensor, N: int, x_add: Optional[torch.Tensor] = None) -> bool:
+    """Shapes / dtypes dfine_linear_fwd takes (include/dfine_b200.h): x float32 (optionally + float32 x_add) or
+    bfloat16, rows of K = x.shape[-1] elements with K % 64 == 0, N splitting into equal tiles of <= 512 columns."""
+    if os.environ.get("DFINE_LINEAR_FWD", "1") == "0":     # A/B switch: cast kernel + cuBLAS GEMM
+        return False
+    K = x.shape[-1]
+    tiles = (N + 511) // 512
+    if N % tiles or (N // tiles) % 32 or K % 64 or x.numel() == 0:
+        return False
+    if not (x.is_cuda and x.dtype in _DT and x.is_contiguous() and x.data_ptr() % 16 == 0):
+        return False
+    if x_add is not None and not (x.dtype == torch.float32 and x_add.dtype == torch.float32 and x_add.is_cuda
+                                  and x_add.shape == x.shape and x_add.is_contiguous()
+                                  and x_add.data_ptr() % 16 == 0):
+        return False
+    return True
+
+
+def linear_fwd(x: torch.Tensor, w_bf16: torch.Tensor, bias: torch.Tensor, x_add: Optional[torch.Tensor] = None,
+               relu: bool = False, out_dtype: torch.dtype = torch.bfloat16, save_input: bool = False):
+    """act(bf16(x [+ x_add]) @ w^T + bias) in one tcgen05 launch (dfine_linear_fwd): the arithmetic of
+    F.linear under torch.autocast(bfloat16).  x [..., K] float32 / bfloat16, w_bf16 [N, K] bfloat16, bias [N]
+    float32 / bfloat16.  Returns y [..., N] (out_dtype), and with save_input also the bfloat16 operand rows
+    [M, K] (what dfine_linear_wgrad needs in the backward)."""
+    _require_cuda(x, w_bf16, bias)
+    N, K = w_bf16.shape
+    if w_bf16.dtype != torch.bfloat16 or not w_bf16.is_contiguous() or x.shape[-1] != K or bias.numel() != N:
+        raise ValueError("linear_fwd: need a contiguous bfloat16 weight [N, K], x [..., K] and bias [N]")
+    if not linear_fwd_supported(x, N, x_add):
+        raise ValueError(f"linear_fwd: unsupported input (x {tuple(x.shape)} {x.dtype}, N = {N}); "
+                         "see linear_fwd_supported")
+    M = x.numel() // K
+    y = torch.empty((*x.shape[:-1], N), dtype=out_dtype, device=x.device)
+    xs = torch.empty((M, K), dtype=torch.bfloat16, device=x.device) if save_input and x.dtype == torch.float32 else None
+    with torch.cuda.device_of(x), _timed("linear_fwd", x):
+        rc = _lib.lib().dfine_linear_fwd(x.data_ptr(), _DT[x.dtype], K, _ptr(x_add), K, w_bf16.data_ptr(),
+                                         bias.data_ptr(), _dt(bias, "bias"), y.data_ptr(), _DT[out_dtype], N,
+                                         _ptr(xs), M, N, K, int(bool(relu)), _stream(x))
+    check(rc, "dfine_linear_fwd")
+    if save_input:
+        return y, (xs if xs is not None else x.reshape(M, K))
+    return y
+
+
+def gate_fwd(x1: torch.Tensor, x2: torch.Tensor, w_bf16: torch.Tensor, bias: torch.Tensor, ln_weight: torch.Tensor,
+             ln_bias: torch.Tensor, eps: float) -> torch.Tensor:
+    """Gate.forward of the reference (dfine_decoder.py:258-271) under bf16 autocast as ONE launch
+    (dfine_gate_fwd): LayerNorm(g1 * x1 + g2 * x2) with [g1 | g2] = sigmoid(cat(x1, x2) @ w^T + bias).
+    x1, x2 float32 [..., C]; w_bf16 [2C, 2C] bfloat16; bias [2C]; LayerNorm parameters float32 [C]."""
+    _require_cuda(x1, x2, w_bf16, bias, ln_weight, ln_bias)
+    C = x1.shape[-1]
+    if (x1.dtype != torch.float32 or x2.dtype != torch.float32 or x1.shape != x2.shape or not x1.is_contiguous()
+            or not x2.is_contiguous() or w_bf16.dtype != torch.bfloat16 or tuple(w_bf16.shape) != (2 * C, 2 * C)
+            or not w_bf16.is_contiguous() or ln_weight.dtype != torch.float32 or ln_bias.dtype != torch.float32):
+        raise ValueError("gate_fwd: need contiguous float32 x1, x2 [..., C], bfloat16 w [2C, 2C], float32 LayerNorm "
+                         "parameters")
+    M = x1.numel() // C
+    out = torch.empty_like(x1)
+    with torch.cuda.device_of(x1), _timed("gate_fwd", x1):
+        rc = _lib.lib().dfine_gate_fwd(x1.data_ptr(), C, x2.data_ptr(), C, w_bf16.data_ptr(), bias.data_ptr(),
+                                       _dt(bias, "bias"), ln_weight.data_ptr(), ln_bias.data_ptr(), float(eps),
+                                       out.data_ptr(), C, M, C, _stream(x1))
+    check(rc, "dfine_gate_fwd")
+    return out
+
+
+def ffn_out_fwd(h: torch.Tensor, w_bf16: torch.Tensor, bias: torch.Tensor, residual: torch.Tensor,
+                ln_weight: torch.Tensor, ln_bias: torch.Tensor, eps: float) -> torch.Tensor:
+    """linear2 + residual + clamp + norm3 of TransformerDecoderLayer.forward (dfine_decoder.py:251-253) under
+    bf16 autocast as ONE launch (dfine_ffn_out_fwd).  h bfloat16 [..., F]; w_bf16 [C, F]; residual float32 [..., C]."""
+    _require_cuda(h, w_bf16, bias, residual, ln_weight, ln_bias)
+    C, F = w_bf16.shape
+    if (h.dtype != torch.bfloat16 or not h.is_contiguous() or h.shape[-1] != F or residual.dtype != torch.float32
+            or not residual.is_contiguous() or residual.shape[-1] != C or w_bf16.dtype != torch.bfloat16
+            or not w_bf16.is_contiguous() or residual.numel() // C != h.numel() // F):
+        raise ValueError("ffn_out_fwd: need contiguous bfloat16 h [..., F], bfloat16 w [C, F], float32 residual [..., C]")
+    M = h.numel() // F
+    out = torch.empty_like(residual)
+    with torch.cuda.device_of(h), _timed("ffn_out_fwd", h):
+        rc = _lib.lib().dfine_ffn_out_fwd(h.data_ptr(), F, w_bf16.data_ptr(), bias.data_ptr(), _dt(bias, "bias"),
+                                          residual.data_ptr(), C, ln_weight.data_ptr(), ln_bias.data_ptr(), float(eps),
+                                          out.data_ptr(), C, M, C, F, _stream(h))
+    check(rc, "dfine_ffn_out_fwd")
+    return out
+
+
+_BF16_CACHE = {}
+
+
+def bf16_param(p: torch.Tensor) -> torch.Tensor:
+    """A contiguous bfloat16 copy of a parameter, cached until the parameter is modified in place (inference:
+    autocast casts the weights of every Linear on every call; here once)."""
+    if p.dtype == torch.bfloat16 and p.is_contiguous():
+        return p
+    key = (p.data_ptr(), tuple(p.shape), p.dtype)
+    hit = _BF16_CACHE.get(key)
+    if hit is not None and hit[0] == p._version:
+        return hit[1]
+    if len(_BF16_CACHE) > 512:
+        _BF16_CACHE.clear()
+    t = p.detach().to(torch.bfloat16).contiguous()
+    _BF16_CACHE[key] = (p._version, t)
+    return t
+
+
+_PACK_CACHE = {}
+
+
+def _packed_params(w0, b0, w1, b1, cdt, x):
+    """[w0; w1], [b0; b1] in the compute dtype (dfine_pack_linear).  Without autograd (inference) the result is
+    cached until one of the parameters is modified in place."""
+    cache = not torch.is_grad_enabled()
+    key = (w0.data_ptr(), w1.data_ptr(), b0.data_ptr(), b1.data_ptr(), cdt)
+    ver = (w0._version, b0._version, w1._version, b1._version)
+    if cache:
+        hit = _PACK_CACHE.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1], hit[2]
+    n0, n1, K = w0.shape[0], w1.shape[0], w0.shape[1]
+    w = torch.empty((n0 + n1, K), dtype=cdt, device=x.device)
+    b = torch.empty((n0 + n1,), dtype=cdt, device=x.device)
+    with torch.cuda.device_of(x), _timed("pack_linear", x):
+        rc = _lib.lib().dfine_pack_linear(w0.data_ptr(), b0.data_ptr(), n0, w1.data_ptr(), b1.data_ptr(),
+                                          n1, K, w.data_ptr(), b.data_ptr(), _DT[cdt], _stream(x))
+    check(rc, "dfine_pack_linear")
+    if cache:
+        if len(_PACK_CACHE) > 64:
+            _PACK_CACHE.clear()
+        _PACK_CACHE[key] = (ver, w, b)
+    return w, b
+
+
 class _PackedLinearFn(torch.autograd.Function):
-    """The two Linears of MSDeformableAttention as ONE GEMM: y = x [W0; W1]^T + [b0; b1].  The
-    parameters stay separate tensors (state-dict compatible); they are concatenated and cast to
-    the compute dtype by one kernel (dfine_pack_linear), the GEMMs are cuBLAS, the bias gradient
-    is dfine_colsum, and the parameter gradients are returned as views of one [N0+N1, K] GEMM
-    result."""
+    """The two Linears of MSDeformableAttention as ONE GEMM: y = (x [+ x_add]) [W0; W1]^T + [b0; b1].  The
+    parameters stay separate tensors (state-dict compatible); they are concatenated and cast to the compute
+    dtype by one kernel (dfine_pack_linear).  Under bf16 autocast the forward is dfine_linear_fwd (tcgen05: the
+    positional add, the fp32 -> bf16 cast of the query, the GEMM and the bias in one launch; it also emits the
+    bf16 operand rows for the backward); otherwise a cuBLAS GEMM.  Backward: cuBLAS for the input gradient,
+    dfine_linear_wgrad for dW and db, returned as views of one [N0+N1, K] result."""
 
     @staticmethod
-    def forward(ctx, x, w0, b0, w1, b1):
+    def forward(ctx, x, x_add, w0, b0, w1, b1):
         cdt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x.dtype
         if cdt not in _DT:
             raise TypeError(f"packed_linear: compute dtype {cdt} not supported (see packed_linear_supported)")
-        n0, n1, K = w0.shape[0], w1.shape[0], w0.shape[1]
-        w = torch.empty((n0 + n1, K), dtype=cdt, device=x.device)
-        b = torch.empty((n0 + n1,), dtype=cdt, device=x.device)
-        with torch.cuda.device_of(x), _timed("pack_linear", x):
-            rc = _lib.lib().dfine_pack_linear(w0.data_ptr(), b0.data_ptr(), n0, w1.data_ptr(), b1.data_ptr(),
-                                              n1, K, w.data_ptr(), b.data_ptr(), _DT[cdt], _stream(x))
-        check(rc, "dfine_pack_linear")
-        x2 = x.reshape(-1, x.shape[-1]).to(cdt)
-        y = torch.nn.functional.linear(x2, w, b)
+        n0, n1 = w0.shape[0], w1.shape[0]
+        w, b = _packed_params(w0, b0, w1, b1, cdt, x)
+        need_x = any(ctx.needs_input_grad[2:])
+        xc = x.contiguous()
+        ac = x_add.contiguous() if x_add is not None else None
+        if cdt == torch.bfloat16 and xc.dtype == torch.float32 and linear_fwd_supported(xc, n0 + n1, ac):
+            if need_x:
+                y, x2 = linear_fwd(xc, w, b, x_add=ac, save_input=True)
+            else:
+                y, x2 = linear_fwd(xc, w, b, x_add=ac), None
+        else:
+            xs = x if x_add is None else x + x_add
+            x2 = xs.reshape(-1, xs.shape[-1]).to(cdt)
+            y = torch.nn.functional.linear(x2, w, b).reshape(*x.shape[:-1], n0 + n1)
         ctx.save_for_backward(x2, w)
-        ctx.x_shape, ctx.x_dtype, ctx.n0 = x.shape, x.dtype, n0
-        return y.reshape(*x.shape[:-1], n0 + n1)
+        ctx.x_shape, ctx.x_dtype, ctx.n0, ctx.has_add = x.shape, x.dtype, n0, x_add is not None
+        return y
 
     @staticmethod
     @torch.autograd.function.once_differentiable
@@ -628,14 +766,19 @@ class _PackedLinearFn(torch.autograd.Function):
         g2 = g.reshape(-1, g.shape[-1])
         if g2.dtype != w.dtype:
             g2 = g2.to(w.dtype)
-        gx = _mm(g2, w, ctx.x_dtype).reshape(ctx.x_shape)
-        if linear_wgrad_supported(g2, x2):
-            gw, gb = linear_wgrad(g2, x2)      # dW and db in one tensor-core launch
-        else:
-            gw = _mm(g2.t(), x2, torch.float32)
-            gb = colsum(g2) if colsum_supported(g2) else g2.float().sum(0)
+        gx = _mm(g2, w, ctx.x_dtype).reshape(ctx.x_shape) if (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]) \
+            else None
+        gw = gb = None
+        if any(ctx.needs_input_grad[2:]):
+            if linear_wgrad_supported(g2, x2):
+                gw, gb = linear_wgrad(g2, x2)      # dW and db in one tensor-core launch
+            else:
+                gw = _mm(g2.t(), x2, torch.float32)
+                gb = colsum(g2) if colsum_supported(g2) else g2.float().sum(0)
         n0 = ctx.n0
-        return gx, gw[:n0], gb[:n0], gw[n0:], gb[n0:]
+        if gw is None:
+            return gx, (gx if ctx.has_add else None), None, None, None, None
+        return gx, (gx if ctx.has_add else None), gw[:n0], gb[:n0], gw[n0:], gb[n0:]
 
 
 def packed_linear_supported(x, w0, b0, w1, b1) -> bool:
@@ -646,8 +789,9 @@ def packed_linear_supported(x, w0, b0, w1, b1) -> bool:
         and x.is_cuda and w0.shape[1] == w1.shape[1]
 
 
-def packed_linear(x, w0, b0, w1, b1):
-    return _PackedLinearFn.apply(x, w0, b0, w1, b1)
+def packed_linear(x, w0, b0, w1, b1, x_add=None):
+    """(x [+ x_add]) @ [w0; w1]^T + [b0; b1]  (x_add: the decoder layer's query_pos_embed, dfine_decoder.py:245)."""
+    return _PackedLinearFn.apply(x, x_add, w0, b0, w1, b1)
 
 
 def linear_wgrad_supported(gy: torch.Tensor, x: torch.Tensor) -> bool:

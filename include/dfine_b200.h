@@ -178,6 +178,45 @@ DFINE_API int dfine_colsum(const void* x, int x_dtype, int64_t M, int N, int64_t
 DFINE_API int dfine_linear_wgrad(const void* grad_y, int64_t gy_row_stride, const void* x, int64_t x_row_stride,
                        int64_t M, int N, int K, float* dw_db, void* stream);
 
+/* --------------------------------------------------------------------------
+ * The decoder layer's Linears with their elementwise neighbours fused in (tcgen05; bf16 operands,
+ * fp32 accumulation: the arithmetic of the reference under torch.autocast(bfloat16)).
+ *
+ * dfine_linear_fwd   y = act(bf16(x [+ x_add]) w^T + bias)
+ *   replaces, for MSDeformableAttention (dfine_decoder.py:139-147): the caller's with_pos_embed add
+ *   (:245, :227-228), autocast's fp32 -> bf16 cast of the query, the concatenated sampling_offsets /
+ *   attention_weights GEMM and its bias; for the FFN (:229-230): linear1 + ReLU.
+ *     x          x_dtype [M, K] (x_row_stride elements between rows, 0 = K)
+ *     x_add      float32 [M, K] or NULL (query_pos_embed); float32 x only
+ *     w          bf16 [N, K] contiguous (nn.Linear layout; dfine_pack_linear writes it)
+ *     bias       bias_dtype [N]
+ *     y          y_dtype [M, N] (y_row_stride, 0 = N)
+ *     x_bf16_out bf16 [M, K] contiguous or NULL: the rounded operand rows, the input
+ *                dfine_linear_wgrad needs in the backward (float32 x only)
+ *   K a multiple of 64; N splits into ceil(N / 512) equal tiles, each a multiple of 32 columns;
+ *   strides multiples of 8 (x_add: 4); pointers 16-byte aligned.
+ *
+ * dfine_gate_fwd     out = LayerNorm(g1 * x1 + g2 * x2),  [g1 | g2] = sigmoid([x1 | x2] w^T + bias)
+ *   replaces Gate.forward (dfine_decoder.py:258-271): cat, cast, Linear(2C, 2C), sigmoid, chunk,
+ *   two multiplies, add, LayerNorm.  x1, x2, out float32 [M, C]; w bf16 [2C, 2C]; bias [2C].
+ *
+ * dfine_ffn_out_fwd  out = LayerNorm(clamp(residual + (h w^T + bias), -65504, 65504))
+ *   replaces linear2, the residual add, the clamp and norm3 of TransformerDecoderLayer.forward
+ *   (dfine_decoder.py:251-253).  h bf16 [M, F] (the output of dfine_linear_fwd with relu = 1);
+ *   w bf16 [C, F]; residual, out float32 [M, C].
+ *
+ * C a multiple of 64, <= 256; F a multiple of 64.  Forward only (inference; training keeps the
+ * reference modules and their autograd).  DFINE_E_UNSUPPORTED for other shapes. */
+DFINE_API int dfine_linear_fwd(const void* x, int x_dtype, int64_t x_row_stride, const float* x_add,
+                     int64_t xadd_row_stride, const void* w, const void* bias, int bias_dtype, void* y, int y_dtype,
+                     int64_t y_row_stride, void* x_bf16_out, int64_t M, int N, int K, int relu, void* stream);
+DFINE_API int dfine_gate_fwd(const float* x1, int64_t x1_row_stride, const float* x2, int64_t x2_row_stride,
+                   const void* w, const void* bias, int bias_dtype, const float* ln_weight, const float* ln_bias,
+                   float eps, float* out, int64_t out_row_stride, int64_t M, int C, void* stream);
+DFINE_API int dfine_ffn_out_fwd(const void* h, int64_t h_row_stride, const void* w, const void* bias, int bias_dtype,
+                      const float* residual, int64_t res_row_stride, const float* ln_weight, const float* ln_bias,
+                      float eps, float* out, int64_t out_row_stride, int64_t M, int C, int F, void* stream);
+
 /* Data-parallel gradient exchange without a collective launch (replaces DistributedDataParallel's
  * all-reduce of the path's Linear gradients, reference src/dl/train.py:161-166):
  *     replica_r[i] += scale * src[i]   for EVERY rank r, i < n

@@ -1,0 +1,282 @@
+"""GPU parity of the fused decoder-layer kernels through the C-ABI:
+dfine_linear_fwd, dfine_gate_fwd, dfine_ffn_out_fwd against the reference's own op sequence under
+torch.autocast(bfloat16) on the same GPU (reference src/d_fine/arch/dfine_decoder.py:139-147, :227-256,
+:258-271), and the patched TransformerDecoderLayer / full model in inference.
+
+Tolerances: every kernel rounds where the reference rounds (operands and Linear outputs to bf16); what is left is
+the fp32 summation order inside the GEMM, which can move a Linear output by ONE bf16 ulp (2^-8 relative).
+bf16 outputs: every element within one bf16 ulp of the reference (+ an absolute slack of 2^-8 of the tensor's
+RMS for results that cancel), and >= 99 % bit-identical.  LayerNorm outputs (fp32, O(1)): <= 1e-2 of the
+tensor's max (north star bf16 tolerance), measured values are logged.
+"""
+import copy
+import json
+import os
+import sys
+
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "d-fine-seg_b200"))
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def _log(rec):
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "layer_parity.jsonl"), "a") as f:
+        f.write(json.dumps(rec) + "\n")
+
+
+def _bf16_close(got: torch.Tensor, want: torch.Tensor, what: str, ulps: float = 1.0):
+    g, w = got.float(), want.float()
+    rms = float(w.pow(2).mean().sqrt())
+    tol = ulps * (2.0 ** -7) * w.abs() + (2.0 ** -8) * rms
+    bad = (g - w).abs() > tol
+    same = float((g == w).float().mean())
+    assert not bool(bad.any()), f"{what}: {int(bad.sum())} elements beyond one bf16 ulp, worst {float((g - w).abs().max()):.3e}"
+    assert same >= 0.99, f"{what}: only {same:.4f} of the elements bit-identical"
+    return same
+
+
+def _scale_err(a, b):
+    return float((a.double() - b.double()).abs().max()) / max(float(b.double().abs().max()), 1e-30)
+
+
+@pytest.mark.parametrize("M,N,K,pos,relu,out_dtype", [
+    (1500, 288, 256, True, False, torch.bfloat16),     # MSDA packed Linear, D-FINE-s/m/l/x (tail rows: 1500 = 11*128 + 92)
+    (16000, 288, 256, True, False, torch.bfloat16),    # config 3 (B = 32, Lq = 500)
+    (600, 288, 128, True, False, torch.bfloat16),      # D-FINE-n (hidden 128)
+    (900, 288, 256, False, False, torch.float32),      # no positional rows, float32 result
+    (1300, 1024, 256, False, True, torch.bfloat16),    # FFN linear1 + ReLU (two N tiles of 512)
+    (700, 512, 128, False, True, torch.bfloat16),      # FFN linear1 of D-FINE-n
+    (130, 64, 64, True, False, torch.bfloat16),        # smallest shape
+])
+def test_linear_fwd_matches_autocast_linear(M, N, K, pos, relu, out_dtype, dev):
+    from dfine_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(M + N + K)
+    x = torch.randn(M, K, device=dev, generator=g)
+    p = torch.randn(M, K, device=dev, generator=g) if pos else None
+    w = torch.randn(N, K, device=dev, generator=g) * 0.05
+    b = torch.randn(N, device=dev, generator=g) * 0.5
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        want = F.linear(x + p if pos else x, w, b)
+        if relu:
+            want = F.relu(want)
+    y, xs = ops.linear_fwd(x, w.bfloat16(), b.bfloat16(), x_add=p, relu=relu, out_dtype=out_dtype, save_input=True)
+    assert y.dtype == out_dtype and y.shape == (M, N)
+    # the operand rows the backward's weight-gradient kernel reads: exactly bf16(x + pos)
+    assert torch.equal(xs, (x + p if pos else x).bfloat16())
+    if out_dtype == torch.float32:
+        same = _bf16_close(y.bfloat16(), want, "linear_fwd (f32 out, rounded)")
+        # the fp32 result itself against an fp32-accumulated reference of the same bf16 operands
+        ref32 = (x + p if pos else x).bfloat16().float() @ w.bfloat16().float().t() + b.bfloat16().float()
+        assert _scale_err(y, ref32) <= 1e-5
+    else:
+        same = _bf16_close(y, want, "linear_fwd")
+    _log({"test": "linear_fwd", "M": M, "N": N, "K": K, "bit_identical": same})
+    # bf16 input rows (TMA-loaded A operand) give the same result as the in-kernel conversion
+    y2 = ops.linear_fwd((x + p if pos else x).bfloat16(), w.bfloat16(), b.bfloat16(), relu=relu, out_dtype=out_dtype)
+    assert torch.equal(y2, y)
+
+
+def test_linear_fwd_rejects_what_it_cannot_run(dev):
+    from dfine_b200 import ops
+    from dfine_b200._lib import DfineB200Error
+    x = torch.randn(64, 96, device=dev)                     # K not a multiple of 64
+    with pytest.raises(ValueError):
+        ops.linear_fwd(x, torch.zeros(64, 96, device=dev, dtype=torch.bfloat16), torch.zeros(64, device=dev))
+    with pytest.raises(RuntimeError):
+        ops.linear_fwd(x.cpu(), torch.zeros(64, 96, dtype=torch.bfloat16), torch.zeros(64))
+    assert issubclass(DfineB200Error, RuntimeError)
+
+
+class _RefGate(nn.Module):
+    """Gate of the reference (dfine_decoder.py:258-271), restated op for op."""
+
+    def __init__(self, d):
+        super().__init__()
+        self.gate = nn.Linear(2 * d, 2 * d)
+        self.norm = nn.LayerNorm(d)
+
+    def forward(self, x1, x2):
+        gates = torch.sigmoid(self.gate(torch.cat([x1, x2], dim=-1)))
+        g1, g2 = gates.chunk(2, dim=-1)
+        return self.norm(g1 * x1 + g2 * x2)
+
+
+def _gate_module(H, C, dev):
+    """The reference's own Gate class when baseline/_ref is installed, else the restatement above."""
+    try:
+        from baseline import ref_install
+        if ref_install.installed():
+            ref_install.import_reference()
+            from src.d_fine.arch.dfine_decoder import Gate
+            return Gate(C).to(dev), "reference"
+    except Exception:
+        pass
+    return _RefGate(C).to(dev), "restated"
+
+
+@pytest.mark.parametrize("M,C", [(1500, 256), (16000, 256), (700, 128), (97, 64)])
+def test_gate_fwd_matches_reference_gate(M, C, dev):
+    from dfine_b200 import ops
+    torch.manual_seed(M + C)
+    gate, kind = _gate_module(None, C, dev)
+    with torch.no_grad():       # trained-like parameters (the reference initialises the gate to a constant 0.5)
+        gate.gate.weight.normal_(0, 0.05)
+        gate.gate.bias.normal_(0, 0.5)
+        gate.norm.weight.normal_(1.0, 0.2)
+        gate.norm.bias.normal_(0, 0.2)
+    x1 = torch.randn(M, C, device=dev) * 1.5
+    x2 = torch.randn(M, C, device=dev) * 0.7 + 0.1
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        want = gate(x1, x2)
+    assert want.dtype == torch.float32
+    got = ops.gate_fwd(x1, x2, gate.gate.weight.detach().bfloat16(), gate.gate.bias.detach().bfloat16(),
+                       gate.norm.weight.detach(), gate.norm.bias.detach(), gate.norm.eps)
+    assert got.dtype == torch.float32 and got.shape == want.shape
+    e = _scale_err(got, want)
+    # a gate value that lands one bf16 ulp away moves the mix by 2^-8 * |x|: the normalised row moves by that much
+    frac_small = float(((got - want).abs() <= 1e-5 * want.abs().max()).float().mean())
+    _log({"test": "gate_fwd", "M": M, "C": C, "ref": kind, "max_err_rel_max": e, "within_1e-5": frac_small})
+    assert e <= 1e-2, e
+    assert frac_small >= 0.9, frac_small
+
+
+@pytest.mark.parametrize("M,C,Fd", [(1500, 256, 1024), (16000, 256, 1024), (700, 128, 512), (97, 64, 64)])
+def test_ffn_tail_matches_reference_ops(M, C, Fd, dev):
+    """linear1 + ReLU (dfine_linear_fwd) and linear2 + residual + clamp + norm3 (dfine_ffn_out_fwd) against
+    TransformerDecoderLayer.forward's last three lines (dfine_decoder.py:251-253) under bf16 autocast."""
+    from dfine_b200 import ops
+    torch.manual_seed(M + C + Fd)
+    l1, l2, norm = nn.Linear(C, Fd).to(dev), nn.Linear(Fd, C).to(dev), nn.LayerNorm(C).to(dev)
+    with torch.no_grad():
+        norm.weight.normal_(1.0, 0.2)
+        norm.bias.normal_(0, 0.2)
+        l2.bias.normal_(0, 0.3)
+    t = torch.randn(M, C, device=dev) * 1.3
+    t[0, :4] = torch.tensor([7e4, -7e4, 65504.0, 3.0], device=dev)      # exercises the clamp
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        h_want = F.relu(l1(t))
+        t2 = l2(h_want)
+        want = norm((t + t2).clamp(min=-65504, max=65504))
+    h = ops.linear_fwd(t, l1.weight.detach().bfloat16(), l1.bias.detach().bfloat16(), relu=True)
+    _bf16_close(h, h_want, "linear1 + relu")
+    # tail kernel on the REFERENCE's hidden rows (isolates it from the one-ulp differences of linear1)
+    got = ops.ffn_out_fwd(h_want.contiguous(), l2.weight.detach().bfloat16(), l2.bias.detach().bfloat16(), t,
+                          norm.weight.detach(), norm.bias.detach(), norm.eps)
+    e = _scale_err(got, want)
+    # and the two kernels chained, as the patched layer runs them
+    got2 = ops.ffn_out_fwd(h, l2.weight.detach().bfloat16(), l2.bias.detach().bfloat16(), t,
+                           norm.weight.detach(), norm.bias.detach(), norm.eps)
+    e2 = _scale_err(got2, want)
+    _log({"test": "ffn_tail", "M": M, "C": C, "F": Fd, "tail_err": e, "chained_err": e2})
+    assert e <= 1e-2 and e2 <= 1e-2, (e, e2)
+
+
+@pytest.fixture(scope="module")
+def H():
+    from baseline import model_harness, ref_install
+    if not ref_install.installed():
+        pytest.skip("baseline/_ref (the reference's model package) was not installed by build()")
+    return model_harness
+
+
+@pytest.mark.parametrize("name,seg,batch", [("n", False, 2), ("s", False, 4), ("m", True, 2)], ids=["n", "s", "m_seg"])
+def test_patched_layer_inference_parity(name, seg, batch, dev, H):
+    """patch_model(layer=True): the reference model's eval forward under bf16 autocast with the whole decoder
+    layer tail (positional add + packed Linear, Gate, FFN, LayerNorms) in the fused kernels, against the
+    unpatched model; and under fp32 (where the layer tail stays on the reference modules) to 1e-5."""
+    import dfine_b200
+    from dfine_b200 import ops
+    model, _ = H.build(name, dev, 640, seg)
+    H.trained_like(model)
+    model.eval()
+    patched = copy.deepcopy(model)
+    counts = dfine_b200.patch_model(patched, layer=True)
+    assert counts["layer"] == len(model.decoder.decoder.layers)
+    images, _ = H.synthetic_batch(batch, 640, dev, seed=11)
+    keys = ["pred_logits", "pred_boxes"] + (["pred_masks"] if seg else [])
+    for amp, tol in ((torch.bfloat16, 1e-2), (None, 1e-5)):
+        ops.enable_kernel_timers(True)
+        want = H.infer_step(model, images, amp)
+        got = H.infer_step(patched, images, amp)
+        names = set(ops.kernel_timers().keys())
+        ops.enable_kernel_timers(False)
+        if amp is not None:
+            assert {"gate_fwd", "ffn_out_fwd", "linear_fwd"} <= names, names
+        else:
+            assert not ({"gate_fwd", "ffn_out_fwd"} & names), names
+        rec = {"test": "layer_inference", "model": name, "amp": str(amp)}
+        for k in keys:
+            assert got[k].shape == want[k].shape and got[k].dtype == want[k].dtype, k
+            rec[k] = _scale_err(got[k].float(), want[k].float())
+            assert rec[k] <= tol, (k, rec[k])
+        _log(rec)
+    # a second copy with only the hot path patched gives the baseline the layer patch is compared with
+    dfine_b200.unpatch_model(patched)
+    again = H.infer_step(patched, images, torch.bfloat16)
+    for k in keys:
+        assert torch.equal(again[k], H.infer_step(model, images, torch.bfloat16)[k]), "unpatch_model did not restore the layer"
+
+
+@pytest.fixture()
+def deterministic():
+    """Deterministic library algorithms for the duration of a test (as in tests/test_gpu_model.py)."""
+    import warnings
+    old = (torch.are_deterministic_algorithms_enabled(), torch.is_deterministic_algorithms_warn_only_enabled(),
+           torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark)
+    torch.use_deterministic_algorithms(True, warn_only=True)
+    torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = True, False
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        yield
+    torch.use_deterministic_algorithms(old[0], warn_only=old[1])
+    torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = old[2], old[3]
+
+
+def test_patched_layer_training_matches_hot_path_patch(dev, H, deterministic):
+    """In training the patched layer keeps the reference's Gate / FFN modules (autograd); the positional add
+    runs inside dfine_linear_fwd and its gradient flows to both the target and the embedding: loss and
+    gradients agree with the model that has only the hot path patched.  Bound per parameter: bf16 tolerance, or
+    4x the run-to-run noise of the hot-path-only model itself (a second copy of it measures that: the backbone's
+    scalar `lab.scale` gradients are sums of cancelling terms and move by more than their own size between two
+    runs of the SAME model)."""
+    import dfine_b200
+    model, loss_fn = H.build("s", dev, 640, False)
+    H.trained_like(model)
+    model.train()
+    a, b, c = copy.deepcopy(model), copy.deepcopy(model), copy.deepcopy(model)
+    dfine_b200.patch_model(a)
+    dfine_b200.patch_model(b, layer=True)
+    dfine_b200.patch_model(c)
+    images, targets = H.synthetic_batch(2, 640, dev, seed=5)
+    res = []
+    for m in (a, b, c):
+        torch.manual_seed(3)
+        m.zero_grad(set_to_none=True)
+        _, _, loss = H.forward_loss(m, loss_fn, images, targets, torch.bfloat16)
+        loss.backward()
+        res.append((float(loss.detach()),
+                    {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}))
+    assert sorted(res[0][1]) == sorted(res[1][1])
+    assert abs(res[0][0] - res[1][0]) <= 1e-2 * abs(res[0][0])
+    errs = sorted(((_scale_err(res[1][1][k], v), _scale_err(res[2][1][k], v), k) for k, v in res[0][1].items()
+                   if float(v.abs().max()) > 0), reverse=True)
+    _log({"test": "layer_training", "loss": [r[0] for r in res], "worst_grad_err": errs[0][0], "its_noise": errs[0][1],
+          "worst_key": errs[0][2],
+          "worst_decoder_err": max(e for e, _, k in errs if k.startswith("decoder."))})
+    for e, noise, k in errs:
+        assert e <= max(5e-2, 4.0 * noise), (k, e, noise)
