@@ -501,7 +501,101 @@ def secondary_kernel_legs(device, peak: float, reps: int = 10):
     nb = Mr * N * (2 + 4 + 2)
     m4["mask_loss_bwd"] = {"ms": ms, "rows": Mr, "algorithmic_bytes": nb, "frac": nb / (ms / 1e3) / 1e9 / peak}
     out["config4_mask_assembly_bf16"] = m4
+    out["config3_decoder_layer_kernels"] = decoder_layer_legs(device, peak, graph_timed(device))
     return out
+
+
+def graph_timed(device, reps: int = 20):
+    """Timer for kernels shorter than their host launch path (10-30 us): `reps` calls are captured into ONE
+    CUDA graph and the replay is bracketed by two events -- device time per call, no host gaps (for the
+    library op sequences it is compared with as well)."""
+    def timed(fn):
+        side = torch.cuda.Stream(device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                fn()
+        torch.cuda.current_stream(device).wait_stream(side)
+        torch.cuda.synchronize(device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(reps):
+                fn()
+        g.replay()
+        torch.cuda.synchronize(device)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        g.replay()
+        e.record()
+        torch.cuda.synchronize(device)
+        del g
+        return s.elapsed_time(e) / reps
+    return timed
+
+
+def decoder_layer_legs(device, peak: float, timed):
+    """The fused Linear kernels of the decoder layer at the config-3 shape
+    (M = B*Lq = 16000 rows, C = 256, FFN 1024), each beside the reference's own op sequence under bf16
+    autocast on the same GPU (library bar: elementwise kernels + cuBLAS).  Both rooflines are reported: the
+    algorithmic HBM bytes (every operand and result touched once) and the tensor-core rate."""
+    import torch.nn.functional as F
+    from dfine_b200 import ops
+    g = torch.Generator(device=device).manual_seed(11)
+    M, C, Fd, N = 16000, 256, 1024, 288
+    x = torch.randn(M, C, device=device, generator=g)
+    pos = torch.randn(M, C, device=device, generator=g)
+    x2 = torch.randn(M, C, device=device, generator=g)
+    w = (torch.randn(N, C, device=device, generator=g) * 0.05)
+    b = torch.randn(N, device=device, generator=g)
+    wg = torch.randn(2 * C, 2 * C, device=device, generator=g) * 0.05
+    bg = torch.randn(2 * C, device=device, generator=g)
+    w1 = torch.randn(Fd, C, device=device, generator=g) * 0.05
+    b1 = torch.randn(Fd, device=device, generator=g)
+    w2 = torch.randn(C, Fd, device=device, generator=g) * 0.05
+    b2 = torch.randn(C, device=device, generator=g)
+    lnw, lnb = torch.ones(C, device=device), torch.zeros(C, device=device)
+    wb, bb, wgb, bgb = w.bfloat16(), b.bfloat16(), wg.bfloat16(), bg.bfloat16()
+    w1b, b1b, w2b, b2b = w1.bfloat16(), b1.bfloat16(), w2.bfloat16(), b2.bfloat16()
+    h = ops.linear_fwd(x, w1b, b1b, relu=True)
+    res = {}
+
+    def entry(ms, nbytes, flops, ms_lib, what):
+        return {"ms": ms, "algorithmic_bytes": nbytes, "frac": nbytes / (ms / 1e3) / 1e9 / peak,
+                "tflops": flops / (ms / 1e3) / 1e12, "reference_ops_ms": ms_lib, "vs_reference_ops": ms_lib / ms,
+                "reference_ops": what}
+
+    def ac(fn):
+        def run():
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                return fn()
+        return run
+
+    res["msda_linear_fwd"] = entry(
+        timed(lambda: ops.linear_fwd(x, wb, bb, x_add=pos)), M * C * 8 + N * C * 2 + M * N * 2, 2.0 * M * N * C,
+        timed(ac(lambda: F.linear(x + pos, w, b))), "add + 3 casts + cuBLAS GEMM (autocast F.linear(x + pos))")
+    res["msda_linear_fwd_train"] = entry(
+        timed(lambda: ops.linear_fwd(x, wb, bb, x_add=pos, save_input=True)),
+        M * C * 8 + N * C * 2 + M * N * 2 + M * C * 2, 2.0 * M * N * C,
+        timed(ac(lambda: F.linear(x + pos, w, b))), "same (autograd keeps the bf16 cast of the input)")
+    res["gate_fwd"] = entry(
+        timed(lambda: ops.gate_fwd(x, x2, wgb, bgb, lnw, lnb, 1e-5)), M * C * 12 + 4 * C * C * 2, 2.0 * M * 4 * C * C,
+        timed(ac(lambda: F.layer_norm((lambda gt: gt[..., :C] * x + gt[..., C:] * x2)(
+            torch.sigmoid(F.linear(torch.cat([x, x2], -1), wg, bg))), (C,), lnw, lnb, 1e-5))),
+        "cat + casts + cuBLAS GEMM + sigmoid + 2 mul + add + LayerNorm (Gate.forward)")
+    res["ffn_linear1_relu"] = entry(
+        timed(lambda: ops.linear_fwd(x, w1b, b1b, relu=True)), M * C * 4 + Fd * C * 2 + M * Fd * 2, 2.0 * M * Fd * C,
+        timed(ac(lambda: F.relu(F.linear(x, w1, b1)))), "casts + cuBLAS GEMM + ReLU")
+    res["ffn_out_fwd"] = entry(
+        timed(lambda: ops.ffn_out_fwd(h, w2b, b2b, x, lnw, lnb, 1e-5)), M * Fd * 2 + C * Fd * 2 + M * C * 8,
+        2.0 * M * Fd * C,
+        timed(ac(lambda: F.layer_norm((x + F.linear(h, w2, b2)).clamp(min=-65504, max=65504), (C,), lnw, lnb, 1e-5))),
+        "cast + cuBLAS GEMM + add + clamp + LayerNorm")
+    tail = res["gate_fwd"]["ms"] + res["ffn_linear1_relu"]["ms"] + res["ffn_out_fwd"]["ms"]
+    tail_ref = res["gate_fwd"]["reference_ops_ms"] + res["ffn_linear1_relu"]["reference_ops_ms"] + \
+        res["ffn_out_fwd"]["reference_ops_ms"]
+    res["layer_tail_total"] = {"ms": tail, "reference_ops_ms": tail_ref, "vs_reference_ops": tail_ref / tail,
+                               "launches": 3}
+    return res
 
 
 def inference_leg(device, steps: int = 30):
@@ -597,7 +691,7 @@ def full_model_leg(device, rank: int, world: int, dist_on: bool, steps: int, war
     model, loss_fn = MH.build("m", device, 640, False, seed=0)
     model.train(), loss_fn.train()
     patched = copy.deepcopy(model)
-    counts = dfine_b200.patch_model(patched)
+    counts = dfine_b200.patch_model(patched, layer=True)
     # the patched arm also routes the criterion's matching stage through the device (dfine_lsap):
     # same assignments, same loss terms, no host round trip of the cost matrices
     patched_loss = copy.deepcopy(loss_fn)
@@ -658,7 +752,7 @@ def full_model_leg(device, rank: int, world: int, dist_on: bool, steps: int, war
     model, _ = MH.build("s", device, 640, False, seed=0)
     model.eval()
     patched = copy.deepcopy(model)
-    dfine_b200.patch_model(patched)
+    dfine_b200.patch_model(patched, layer=True)
     images, _ = MH.synthetic_batch(B, 640, "cpu", seed=rank_seed(rank))
     host_images = images.pin_memory()
     res = {"workload": "dfine_s_infer_640_b64 (full model, eval, no_grad, bf16 autocast)", "images_per_gpu": B,
@@ -712,7 +806,7 @@ def _latency_leg(device, rank, world, steps, warmup, timed):
     model, _ = MH.build("n", device, 640, False, seed=0)
     model.eval()
     patched = copy.deepcopy(model)
-    dfine_b200.patch_model(patched)
+    dfine_b200.patch_model(patched, layer=True)
     images, _ = MH.synthetic_batch(1, 640, "cpu", seed=rank_seed(rank))
     host_images = images.pin_memory()
     res = {"workload": "dfine_n_infer_640_b1 (full model, eval, no_grad, bf16 autocast; latency)", "images_per_gpu": 1,
@@ -744,7 +838,7 @@ def _seg_train_leg(device, rank, world, dist_on, steps, warmup, timed):
     model, loss_fn = MH.build("m", device, 640, True, seed=0)
     model.train(), loss_fn.train()
     patched, ploss = copy.deepcopy(model), copy.deepcopy(loss_fn)
-    counts = dfine_b200.patch_model(patched, mask="matched")
+    counts = dfine_b200.patch_model(patched, mask="matched", layer=True)
     counts.update(dfine_b200.patch_criterion(ploss))
     images, targets = MH.synthetic_batch(B, 640, "cpu", seed=rank_seed(rank), seg=True)
     host_images = images.pin_memory()

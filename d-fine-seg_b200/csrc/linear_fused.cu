@@ -108,22 +108,71 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
 
 __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
-__device__ __forceinline__ float load_bias(const void* b, int bf16, int i) {
-  return bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(b)[i]) : reinterpret_cast<const float*>(b)[i];
+// 32 consecutive bias values starting at a multiple of 32 (one address for the whole warp: broadcast loads)
+__device__ __forceinline__ void load_bias32(const void* b, int bf16, int i0, float (&v)[32]) {
+  if (bf16) {
+    const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(b) + i0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 t = __ldg(p + j);
+      const uint32_t u[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        v[8 * j + 2 * k] = __uint_as_float(u[k] << 16);
+        v[8 * j + 2 * k + 1] = __uint_as_float(u[k] & 0xffff0000u);
+      }
+    }
+  } else {
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(b) + i0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 t = __ldg(p + j);
+      v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+    }
+  }
+}
+
+// 8 consecutive bias values starting at a multiple of 8
+__device__ __forceinline__ void load_bias8(const void* b, int bf16, int i0, float (&v)[8]) {
+  if (bf16) {
+    const uint4 t = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(b) + i0));
+    const uint32_t u[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      v[2 * k] = __uint_as_float(u[k] << 16);
+      v[2 * k + 1] = __uint_as_float(u[k] & 0xffff0000u);
+    }
+  } else {
+    const float4 t0 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(b) + i0));
+    const float4 t1 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(b) + i0 + 4));
+    v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
+  }
+}
+
+// sigmoid of a bf16-representable value, rounded to bf16 (torch.sigmoid on a bf16 tensor: evaluated in fp32,
+// rounded once).  ex2.approx / rcp: the fp32 result is within 2 ulp of the exact one, far below the bf16
+// rounding step that follows.
+__device__ __forceinline__ float sigmoid_bf16(float z) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return bf16_round(r);
 }
 
 // rows [m0, m0+32) x columns [c0, c0+32) of a row-major fp32 matrix -> this thread's row (`lane`) in registers,
-// through the warp's padded staging buffer: coalesced 16-byte loads (4 rows of 128 bytes per instruction)
-__device__ __forceinline__ void load_rows(const float* src, int64_t rs, int m0, int c0, int M, float* stg, int lane,
-                                          float (&v)[32]) {
+// through the warp's padded staging buffer.  fetch_rows: coalesced 16-byte loads (4 rows of 128 bytes per
+// instruction), issued one chunk ahead of their use; stage_rows: the transposition.
+__device__ __forceinline__ void fetch_rows(const float* src, int64_t rs, int m0, int c0, int M, int lane, float4 (&t)[8]) {
   const int srow = lane >> 3, c4 = (lane & 7) * 4;
-  float4 t[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int rr = 4 * i + srow;
     t[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (m0 + rr < M) t[i] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)(m0 + rr) * rs + c0 + c4));
   }
+}
+__device__ __forceinline__ void stage_rows(const float4 (&t)[8], float* stg, int lane, float (&v)[32]) {
+  const int srow = lane >> 3, c4 = (lane & 7) * 4;
   __syncwarp();                        // the previous use of the buffer is over
 #pragma unroll
   for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(stg + (4 * i + srow) * STG_ROW + c4) = t[i];
@@ -168,6 +217,7 @@ __device__ __forceinline__ void store_rows(const float (&v)[32], void* y, int64_
   }
 }
 
+// (10 warps = 3 on some SM sub-partitions of 16 K registers each: 168 registers per thread is the ceiling)
 template <int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
 linear_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_a, const Args a) {
@@ -191,6 +241,41 @@ linear_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
   const int n0 = blockIdx.y * a.n_tile;          // first output feature of this CTA
   const int k_blocks = a.K / BLOCK_K;
   const bool convert = a.a_mode != A_BF16;
+
+  // converter threads: half a warp per row (16 lanes x float4 = 64 k), 16 rows per pass over the 8 warps
+  const int cw = warp - 2;                         // converter / epilogue warp index 0..7 (warps 2..9)
+  const int rsub = lane >> 4, f = lane & 15;
+  const bool has_add = a.a_mode == A_F32 && a.x1 != nullptr;
+  // four register buffers of one k-block each (8 x float4 per thread = 32 KiB per CTA).  One source (x, or the
+  // two halves of the cat): the loads of k-blocks kb+1 .. kb+3 are in flight while kb is converted -- 96 KiB
+  // per SM, what it takes to keep HBM busy from a single wave of CTAs.  With added rows (x + x_add) the buffers
+  // work as two pairs: 64 KiB in flight.
+  float4 b0[8], b1[8], b2[8], b3[8];
+  auto issue_from = [&](const float* src, int64_t rs, int col, float4 (&v)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int m = mt * BLOCK_M + i * 16 + cw * 2 + rsub;
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < a.M) v[i] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)m * rs + col));
+    }
+  };
+  auto issue = [&](int kb, float4 (&v)[8]) {       // x rows of k-block kb (A_F32_CAT: of the half it lies in)
+    const int kk = kb * BLOCK_K;
+    if (a.a_mode == A_F32_CAT && kk >= (a.K >> 1))
+      issue_from(a.x1, a.x1_rs, kk - (a.K >> 1) + 4 * f, v);
+    else
+      issue_from(reinterpret_cast<const float*>(a.x0), a.x0_rs, kk + 4 * f, v);
+  };
+  auto issue_add = [&](int kb, float4 (&v)[8]) { issue_from(a.x1, a.x1_rs, kb * BLOCK_K + 4 * f, v); };
+  if (convert && warp >= 2) {                      // in flight under the barrier / TMEM set-up
+    issue(0, b0);
+    if (has_add) {
+      issue_add(0, b1);
+    } else {
+      if (1 < k_blocks) issue(1, b1);
+      if (2 < k_blocks) issue(2, b2);
+    }
+  }
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < MAX_STAGES; ++i) {
@@ -262,44 +347,14 @@ linear_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
       umma_commit(smem_u32(tmem_full));
     }
   } else {
-    const int cw = warp - 2;                       // 0..7
     // ===================== A converters =====================
     if (convert) {
       int stage = 0;
       uint32_t phase = 0;
-      const int rsub = lane >> 4, f = lane & 15;   // half a warp per row: 16 lanes x float4 = 64 k
-      const int half = a.K >> 1;
-      for (int kb = 0; kb < k_blocks; ++kb) {
+      // the loads of k-block kb + 1 are in flight while k-block kb is converted and stored (the first block's
+      // were issued before the set-up barrier)
+      auto commit = [&](int kb, float4 (&v)[8]) {
         const int kk = kb * BLOCK_K;
-        const float* s0 = reinterpret_cast<const float*>(a.x0);
-        const float* s1 = a.x1;
-        int64_t rs0 = a.x0_rs, rs1 = a.x1_rs;
-        int col = kk + 4 * f;
-        if (a.a_mode == A_F32_CAT) {
-          if (kk >= half) {
-            s0 = a.x1;
-            rs0 = a.x1_rs;
-            col -= half;
-          }
-          s1 = nullptr;
-        }
-        float4 v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int m = mt * BLOCK_M + i * 16 + cw * 2 + rsub;
-          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (m < a.M) v[i] = __ldg(reinterpret_cast<const float4*>(s0 + (int64_t)m * rs0 + col));
-        }
-        if (s1) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int m = mt * BLOCK_M + i * 16 + cw * 2 + rsub;
-            if (m < a.M) {
-              const float4 p = __ldg(reinterpret_cast<const float4*>(s1 + (int64_t)m * rs1 + col));
-              v[i].x += p.x; v[i].y += p.y; v[i].z += p.z; v[i].w += p.w;
-            }
-          }
-        }
         mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
         unsigned char* sa = smem + stage * stage_bytes;
 #pragma unroll
@@ -321,6 +376,35 @@ linear_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
           stage = 0;
           phase ^= 1;
         }
+      };
+      auto add_into = [&](float4 (&v)[8], const float4 (&p)[8]) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { v[i].x += p[i].x; v[i].y += p[i].y; v[i].z += p[i].z; v[i].w += p[i].w; }
+      };
+      if (has_add) {
+        for (int kb = 0; kb < k_blocks; kb += 2) {
+          if (kb + 1 < k_blocks) { issue(kb + 1, b2); issue_add(kb + 1, b3); }
+          add_into(b0, b1);
+          commit(kb, b0);
+          if (kb + 1 < k_blocks) {
+            if (kb + 2 < k_blocks) { issue(kb + 2, b0); issue_add(kb + 2, b1); }
+            add_into(b2, b3);
+            commit(kb + 1, b2);
+          }
+        }
+      } else {
+#define DFINE_LF_STEP(KB, CUR, NXT)                         \
+  if ((KB) < k_blocks) {                                    \
+    if ((KB) + 3 < k_blocks) issue((KB) + 3, NXT);          \
+    commit((KB), CUR);                                      \
+  }
+        for (int kb = 0; kb < k_blocks; kb += 4) {
+          DFINE_LF_STEP(kb, b0, b3)
+          DFINE_LF_STEP(kb + 1, b1, b0)
+          DFINE_LF_STEP(kb + 2, b2, b1)
+          DFINE_LF_STEP(kb + 3, b3, b2)
+        }
+#undef DFINE_LF_STEP
       }
     }
     // ===================== epilogue =====================
@@ -329,6 +413,16 @@ linear_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
     const int m0 = mt * BLOCK_M + wq * 32;         // first row held by this warp
     const int row = wq * 32 + lane;                // row of the tile held by this thread
     float* stg = smem_stg + cw * 32 * STG_ROW;
+    // LayerNorm epilogues: C output columns, this warp owns [cbeg, cend); the fp32 rows the epilogue mixes in
+    // (x1 / x2, the residual) are fetched one 32-column chunk ahead -- the first chunk before the accumulators
+    // are waited for
+    const int C = EPI == EPI_GATE ? a.N / 2 : a.N;
+    const int cbeg = member * (C / 2), cend = cbeg + C / 2;
+    float4 ta[8], tb[8];
+    if constexpr (EPI != EPI_BIAS) {
+      fetch_rows(a.r0, a.r0_rs, m0, cbeg, a.M, lane, ta);
+      if constexpr (EPI == EPI_GATE) fetch_rows(a.r1, a.r1_rs, m0, cbeg, a.M, lane, tb);
+    }
     mbar_wait(smem_u32(tmem_full), 0);
     tcgen05_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16);
@@ -338,42 +432,55 @@ linear_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
         uint32_t r[32];
         tmem_ld_32x32(taddr + c0, r);
         float v[32];
+        load_bias32(a.bias, a.bias_bf16, n0 + c0, v);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float t = __uint_as_float(r[j]) + load_bias(a.bias, a.bias_bf16, n0 + c0 + j);
-          if (a.relu) t = fmaxf(t, 0.f);
-          v[j] = t;
+          const float t = __uint_as_float(r[j]) + v[j];
+          v[j] = a.relu ? fmaxf(t, 0.f) : t;
         }
         store_rows(v, a.y, a.y_rs, a.y_bf16, m0, n0 + c0, a.M, stg, lane);
       }
     } else {
-      // C output columns; this warp owns [member * C/2, (member + 1) * C/2)
-      const int C = EPI == EPI_GATE ? a.N / 2 : a.N;
-      const int cbeg = member * (C / 2), cend = cbeg + C / 2;
       float sum = 0.f;
       for (int c0 = cbeg; c0 < cend; c0 += 32) {
         uint32_t r[32];
         float xv[32], v[32];
+        if (c0 != cbeg) {
+          fetch_rows(a.r0, a.r0_rs, m0, c0, a.M, lane, ta);
+          if constexpr (EPI == EPI_GATE) fetch_rows(a.r1, a.r1_rs, m0, c0, a.M, lane, tb);
+        }
         tmem_ld_32x32(taddr + c0, r);
-        load_rows(a.r0, a.r0_rs, m0, c0, a.M, stg, lane, xv);
+        stage_rows(ta, stg, lane, xv);
         if constexpr (EPI == EPI_GATE) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float z = bf16_round(__uint_as_float(r[j]) + load_bias(a.bias, a.bias_bf16, c0 + j));
-            v[j] = bf16_round(1.0f / (1.0f + expf(-z))) * xv[j];
+          for (int j8 = 0; j8 < 32; j8 += 8) {
+            float bv[8];
+            load_bias8(a.bias, a.bias_bf16, c0 + j8, bv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              v[j8 + j] = __fmul_rn(sigmoid_bf16(bf16_round(__uint_as_float(r[j8 + j]) + bv[j])), xv[j8 + j]);
           }
           tmem_ld_32x32(taddr + C + c0, r);
-          load_rows(a.r1, a.r1_rs, m0, c0, a.M, stg, lane, xv);
+          stage_rows(tb, stg, lane, xv);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float z = bf16_round(__uint_as_float(r[j]) + load_bias(a.bias, a.bias_bf16, C + c0 + j));
-            v[j] = __fadd_rn(v[j], bf16_round(1.0f / (1.0f + expf(-z))) * xv[j]);
+          for (int j8 = 0; j8 < 32; j8 += 8) {
+            float bv[8];
+            load_bias8(a.bias, a.bias_bf16, C + c0 + j8, bv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              v[j8 + j] = __fadd_rn(v[j8 + j], __fmul_rn(sigmoid_bf16(bf16_round(__uint_as_float(r[j8 + j]) + bv[j])),
+                                                          xv[j8 + j]));
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float t = bf16_round(__uint_as_float(r[j]) + load_bias(a.bias, a.bias_bf16, c0 + j));
-            v[j] = fminf(fmaxf(xv[j] + t, -65504.f), 65504.f);
+          for (int j8 = 0; j8 < 32; j8 += 8) {
+            float bv[8];
+            load_bias8(a.bias, a.bias_bf16, c0 + j8, bv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float t = bf16_round(__uint_as_float(r[j8 + j]) + bv[j]);
+              v[j8 + j] = fminf(fmaxf(xv[j8 + j] + t, -65504.f), 65504.f);
+            }
           }
         }
 #pragma unroll

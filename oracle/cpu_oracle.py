@@ -256,3 +256,59 @@ def linear_wgrad(grad_y: np.ndarray, x: np.ndarray):
     g = np.asarray(grad_y, dtype=np.float64).reshape(-1, grad_y.shape[-1])
     xx = np.asarray(x, dtype=np.float64).reshape(-1, x.shape[-1])
     return g.T @ xx, g.sum(0)
+
+
+# ------------------------------------------------------------------------------------------
+# The decoder layer's Linears under torch.autocast(bfloat16): numpy restatement of the reference's
+# op sequence with its rounding points (test infrastructure: the checker of dfine_linear_fwd,
+# dfine_gate_fwd, dfine_ffn_out_fwd; pinned to tests/golden/layer.npz by tests/test_oracle_golden.py)
+# ------------------------------------------------------------------------------------------
+def bf16_round(x) -> np.ndarray:
+    """float32 -> nearest bfloat16 (ties to even) -> float32, the cast autocast applies to the operands and
+    that F.linear applies to its result."""
+    a = np.ascontiguousarray(x, dtype=np.float32)
+    u = a.view(np.uint32).astype(np.uint64)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000).astype(np.uint32)
+    out = r.view(np.float32).copy()
+    nan = np.isnan(a)
+    out[nan] = a[nan]
+    return out.reshape(a.shape)
+
+
+def linear_bf16(x, w, b, x_add=None, relu: bool = False) -> np.ndarray:
+    """F.linear(x [+ x_add], w, b) under autocast(bfloat16) (reference dfine_decoder.py:139-147 with the
+    caller's with_pos_embed :245; linear1 + activation :229-230): the add in float32, operands rounded to
+    bf16, exact products accumulated (float64 here; fp32 in an unspecified order on the device), bias
+    (rounded to bf16) added before the single rounding of the result to bf16."""
+    xs = np.asarray(x, np.float32)
+    if x_add is not None:
+        xs = xs + np.asarray(x_add, np.float32)
+    y = bf16_round(xs).astype(np.float64) @ bf16_round(w).astype(np.float64).T + bf16_round(b).astype(np.float64)
+    y = bf16_round(y.astype(np.float32))
+    return np.maximum(y, 0.0) if relu else y
+
+
+def layer_norm(x, w, b, eps: float) -> np.ndarray:
+    x = np.asarray(x, np.float64)
+    mu = x.mean(-1, keepdims=True)
+    var = ((x - mu) ** 2).mean(-1, keepdims=True)
+    return ((x - mu) / np.sqrt(var + eps) * np.asarray(w, np.float64) + np.asarray(b, np.float64)).astype(np.float32)
+
+
+def gate_fwd(x1, x2, w, b, ln_w, ln_b, eps: float) -> np.ndarray:
+    """Gate.forward (reference dfine_decoder.py:265-271) under autocast(bfloat16): gates =
+    sigmoid(Linear(cat(x1, x2))) is a bf16 tensor (sigmoid evaluated in float32 on the bf16 Linear output,
+    rounded once); gate * x promotes to float32; LayerNorm in float32."""
+    C = np.asarray(x1).shape[-1]
+    z = linear_bf16(np.concatenate([x1, x2], -1), w, b)
+    with np.errstate(over="ignore"):
+        gates = bf16_round((1.0 / (1.0 + np.exp(-z.astype(np.float64)))).astype(np.float32))
+    mix = (gates[..., :C] * np.asarray(x1, np.float32)) + (gates[..., C:] * np.asarray(x2, np.float32))
+    return layer_norm(mix, ln_w, ln_b, eps)
+
+
+def ffn_tail(hidden, w2, b2, residual, ln_w, ln_b, eps: float) -> np.ndarray:
+    """The last lines of TransformerDecoderLayer.forward (reference dfine_decoder.py:251-253) under
+    autocast(bfloat16): linear2 (bf16 result) + residual in float32, clamp to +-65504, norm3."""
+    t2 = linear_bf16(hidden, w2, b2)
+    return layer_norm(np.clip(np.asarray(residual, np.float32) + t2, -65504.0, 65504.0), ln_w, ln_b, eps)

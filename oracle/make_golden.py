@@ -18,6 +18,7 @@ Reference entry points exercised (all imported, nothing restated here):
   src/d_fine/arch/utils.py:119   distance2bbox
   src/d_fine/arch/dfine_decoder.py:937  DFINETransformer._mask_logits_from_h
   src/d_fine/dfine_criterion.py:273-312  DFINECriterion._focal_loss_mask / _dice_loss
+  src/d_fine/arch/dfine_decoder.py:180-256  TransformerDecoderLayer (with_pos_embed, forward_ffn, norm3), :258-271 Gate
 """
 from __future__ import annotations
 
@@ -305,6 +306,51 @@ def case_mask_loss(ref):
     return "mask_loss", out
 
 
+def case_layer(ref):
+    """The decoder layer's Linears as the reference runs them under autocast(bfloat16) (the shipped trainer's
+    AMP and the inference wrapper's half mode): MSDeformableAttention's two Linears on with_pos_embed(target,
+    pos) (dfine_decoder.py:139-147, :245), Gate.forward (:258-271), and the FFN tail of
+    TransformerDecoderLayer.forward (:251-253: forward_ffn, residual, clamp, norm3).  torch CPU autocast: the
+    same rounding points as on CUDA (Linear operands and outputs in bf16, sigmoid on bf16, LayerNorm on fp32)."""
+    g = torch.Generator().manual_seed(51)
+    M, C, Fd, H, P = 150, 256, 1024, 8, 12
+    layer = ref.TransformerDecoderLayer(d_model=C, n_head=H, dim_feedforward=Fd, n_levels=3, n_points=[3, 6, 3])
+    layer.eval()
+    with torch.no_grad():
+        for p_ in layer.parameters():                       # trained-like values everywhere
+            # (weight matrices bf16-representable: autocast rounds them anyway, and the fixture stores 2 bytes each)
+            p_.copy_(bf16r(torch.randn(p_.shape, generator=g) * 0.05) if p_.dim() > 1
+                     else torch.randn(p_.shape, generator=g) * 0.3)
+        for ln in (layer.gateway.norm, layer.norm3):
+            ln.weight.add_(1.0)
+    target = torch.randn(1, M, C, generator=g) * 1.3
+    pos = torch.randn(1, M, C, generator=g)
+    x2 = torch.randn(1, M, C, generator=g) * 0.7 + 0.1
+    target[0, 0, :4] = torch.tensor([7e4, -7e4, 65504.0, 3.0])     # reaches the clamp of :253
+    ca = layer.cross_attn
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        q = layer.with_pos_embed(target, pos)
+        raw = torch.cat([ca.sampling_offsets(q), ca.attention_weights(q)], -1)
+        gate_out = layer.gateway(target, x2)
+        hid = layer.activation(layer.linear1(target))
+        t2 = layer.forward_ffn(target)
+        ffn_out = layer.norm3((target + t2).clamp(min=-65504, max=65504))
+    assert raw.dtype == torch.bfloat16 and hid.dtype == torch.bfloat16
+    assert gate_out.dtype == torch.float32 and ffn_out.dtype == torch.float32
+    f = lambda t: t.detach().float().numpy().copy()
+    h = lambda t: t.detach().to(torch.bfloat16).view(torch.int16).numpy().copy()     # bf16 bit patterns
+    return "layer", dict(
+        target=f(target[0]), pos=f(pos[0]), x2=f(x2[0]),
+        so_w_bf16=h(ca.sampling_offsets.weight), so_b=f(ca.sampling_offsets.bias),
+        aw_w_bf16=h(ca.attention_weights.weight), aw_b=f(ca.attention_weights.bias), raw_bf16=h(raw[0]),
+        gate_w_bf16=h(layer.gateway.gate.weight), gate_b=f(layer.gateway.gate.bias),
+        gate_ln_w=f(layer.gateway.norm.weight), gate_ln_b=f(layer.gateway.norm.bias),
+        gate_eps=np.float32(layer.gateway.norm.eps), gate_out=f(gate_out[0]),
+        w1_bf16=h(layer.linear1.weight), b1=f(layer.linear1.bias), w2_bf16=h(layer.linear2.weight),
+        b2=f(layer.linear2.bias), ln3_w=f(layer.norm3.weight), ln3_b=f(layer.norm3.bias),
+        ln3_eps=np.float32(layer.norm3.eps), hidden_bf16=h(hid[0]), ffn_out=f(ffn_out[0]))
+
+
 def _criterion_class():
     from src.d_fine.dfine_criterion import DFINECriterion  # noqa: E402
     return DFINECriterion
@@ -318,6 +364,7 @@ def load_reference(path: str):
         core=au.deformable_attention_core_func_v2, weighting_function=au.weighting_function,
         distance2bbox=au.distance2bbox, MSDeformableAttention=dd.MSDeformableAttention,
         Integral=dd.Integral, TransformerDecoder=dd.TransformerDecoder,
+        TransformerDecoderLayer=dd.TransformerDecoderLayer,
         DFINETransformer=dd.DFINETransformer, DFINECriterion=_criterion_class())
 
 
@@ -344,6 +391,7 @@ def main() -> None:
         case_mask(ref),
         case_mask_bwd(ref),
         case_mask_loss(ref),
+        case_layer(ref),
     ]
     for name, arrs in cases:
         if a.only and name not in a.only.split(","):

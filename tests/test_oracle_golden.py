@@ -149,3 +149,40 @@ def test_mask_loss():
     assert abs(dice - float(g["loss_dice"])) <= FP32_RTOL * abs(float(g["loss_dice"]))
     assert_close(g_bce, g["grad_bce"], FP32_RTOL, "d loss_mask_bce / d logits")
     assert_close(g_dice, g["grad_dice"], FP32_RTOL, "d loss_mask_dice / d logits")
+
+
+def _layer_golden():
+    g = golden("layer")
+    d = {k: g[k] for k in g.files if not k.endswith("_bf16")}
+    d.update({k[:-5]: bf16_bits_to_f32(g[k]) for k in g.files if k.endswith("_bf16")})
+    return d
+
+
+def _one_bf16_ulp(got, want, what, min_identical=0.999):
+    """Linear outputs are bf16 values: the summation order may move one by a single ulp (2^-8 relative)."""
+    rms = float(np.sqrt(np.mean(np.square(want, dtype=np.float64))))
+    bad = np.abs(got - want) > 2.0 ** -7 * np.abs(want) + 2.0 ** -8 * rms
+    assert not bad.any(), f"{what}: {int(bad.sum())} elements beyond one bf16 ulp"
+    same = float((got == want).mean())
+    assert same >= min_identical, f"{what}: only {same:.5f} bit-identical"
+
+
+def test_layer_linears_match_reference_autocast():
+    # reference: MSDeformableAttention's Linears on with_pos_embed(target, pos) (dfine_decoder.py:139-147, :245),
+    # linear1 + ReLU (:229-230), torch CPU autocast(bfloat16)
+    g = _layer_golden()
+    raw = O.linear_bf16(g["target"], np.concatenate([g["so_w"], g["aw_w"]]), np.concatenate([g["so_b"], g["aw_b"]]),
+                        x_add=g["pos"])
+    _one_bf16_ulp(raw, g["raw"], "packed Linear")
+    _one_bf16_ulp(O.linear_bf16(g["target"], g["w1"], g["b1"], relu=True), g["hidden"], "linear1 + relu")
+
+
+def test_gate_and_ffn_tail_match_reference_autocast():
+    # reference: Gate.forward (dfine_decoder.py:265-271), TransformerDecoderLayer.forward :251-253
+    g = _layer_golden()
+    got = O.gate_fwd(g["target"], g["x2"], g["gate_w"], g["gate_b"], g["gate_ln_w"], g["gate_ln_b"], float(g["gate_eps"]))
+    # a gate that lands one bf16 ulp away (exp / summation order) moves its row by ~2^-8 of the row's scale
+    assert_close(got, g["gate_out"], 1e-3, "gate")
+    assert (np.abs(got - g["gate_out"]) <= 1e-5 * np.abs(g["gate_out"]).max()).mean() >= 0.999
+    got = O.ffn_tail(g["hidden"], g["w2"], g["b2"], g["target"], g["ln3_w"], g["ln3_b"], float(g["ln3_eps"]))
+    assert_close(got, g["ffn_out"], FP32_RTOL, "ffn tail")       # row 0 went through the clamp of :253
