@@ -983,32 +983,84 @@ def time_steps(fn, steps: int, warmup: int, device, dist_on: bool):
 # ------------------------------------------------------------------------------------------
 # CPU arm: the reference's torch path (oracle/torch_port.py), bounded sample
 # ------------------------------------------------------------------------------------------
+def _reference_cpu_step(wl: dict, inp: dict):
+    """One hot-path step through the UNMODIFIED reference (baseline/_ref: the reference's own
+    MSDeformableAttention, TransformerDecoder.value_op, weighting_function, Integral, distance2bbox --
+    src/d_fine/arch/dfine_decoder.py, utils.py) on the host CPU, float32: per decoder layer the module forward +
+    the FDR decode, then the backward of all of it -- the same work the CUDA arm's step does.  Returns a
+    callable, or None when the reference package was not installed by build()."""
+    import types
+    try:
+        from baseline import ref_install
+        if not ref_install.installed():
+            return None
+        ref_install.import_reference()
+        from src.d_fine.arch import dfine_decoder as dd
+        from src.d_fine.arch import utils as au
+    except Exception:  # noqa: BLE001
+        return None
+    H = wl["H"]
+    mods = []
+    for lw in inp["lin"]:
+        m = dd.MSDeformableAttention(wl["C"], H, len(wl["shapes"]), list(wl["npts"]))
+        with torch.no_grad():
+            m.sampling_offsets.weight.copy_(lw["so_w"])
+            m.attention_weights.weight.copy_(lw["aw_w"])
+            m.attention_weights.bias.copy_(lw["aw_b"])
+        mods.append(m)
+    integral = dd.Integral(wl["reg_max"])
+    up, rs = torch.tensor([wl["up"]]), torch.tensor([wl["reg_scale"]])
+    stub = types.SimpleNamespace(num_head=H)
+
+    def step():
+        for m in mods:
+            m.zero_grad(set_to_none=True)
+        mem = inp["memory"].detach().requires_grad_(True)
+        project = au.weighting_function(wl["reg_max"], up, rs)
+        value = dd.TransformerDecoder.value_op(stub, mem, None, None, None, wl["shapes"])
+        outs, gos = [], []
+        for i, m in enumerate(mods):
+            q = inp["queries"][i].detach().requires_grad_(True)
+            pc = inp["corners"][i].detach().requires_grad_(True)
+            outs.append(m(q, inp["refs"][i], value, wl["shapes"]))
+            outs.append(au.distance2bbox(inp["ref_init"], integral(pc, project), rs))
+            gos += [inp["grad_outs"][i], inp["grad_boxes"][i]]
+        torch.autograd.backward(outs, gos)
+    return step
+
+
 def cpu_reference_run(wl: dict, sample_b: int, steps: int, warmup: int, seed: int = 42):
-    from oracle import torch_port as TP  # the only use of oracle/ in this file
+    """Times the path's CPU implementation on the host cores: the unmodified reference when baseline/_ref is
+    present (kind "reference"), else its restatement oracle/torch_port.py (kind "port").  Returns
+    (imgs/s, ms per step, kind)."""
     # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1)
     try:
         torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
     except (AttributeError, OSError):
         torch.set_num_threads(max(1, os.cpu_count() or 1))
     inp = make_inputs(wl, sample_b, seed, "cpu")
-    H, P = wl["H"], sum(wl["npts"])
-    nps = torch.tensor([1.0 / n for n in wl["npts"] for _ in range(n)])
-    ang = torch.arange(H, dtype=torch.float32) * (2.0 * torch.pi / H)
-    dirs = torch.stack([ang.cos(), ang.sin()], -1)
-    dirs = dirs / dirs.abs().max(-1, keepdim=True).values
-    rank = torch.cat([torch.arange(1, n + 1) for n in wl["npts"]]).float()
-    so_b = (dirs[:, None, :] * rank[None, :, None]).reshape(-1)
-    up, rs = torch.tensor([wl["up"]]), torch.tensor([wl["reg_scale"]])
+    kind = "reference"
+    step = _reference_cpu_step(wl, inp)
+    if step is None:
+        kind = "port"
+        from oracle import torch_port as TP  # the only use of oracle/ in this file
+        H, P = wl["H"], sum(wl["npts"])
+        nps = torch.tensor([1.0 / n for n in wl["npts"] for _ in range(n)])
+        ang = torch.arange(H, dtype=torch.float32) * (2.0 * torch.pi / H)
+        dirs = torch.stack([ang.cos(), ang.sin()], -1)
+        dirs = dirs / dirs.abs().max(-1, keepdim=True).values
+        rank = torch.cat([torch.arange(1, n + 1) for n in wl["npts"]]).float()
+        so_b = (dirs[:, None, :] * rank[None, :, None]).reshape(-1)
+        up, rs = torch.tensor([wl["up"]]), torch.tensor([wl["reg_scale"]])
+        lins = [(*(t.detach().requires_grad_(True) for t in (lw["so_w"], so_b, lw["aw_w"], lw["aw_b"])), nps)
+                for lw in inp["lin"]]
 
-    lins = [(*(t.detach().requires_grad_(True) for t in (lw["so_w"], so_b, lw["aw_w"], lw["aw_b"])), nps)
-            for lw in inp["lin"]]
-
-    def step():
-        for t in (x for lin in lins for x in lin[:4]):
-            t.grad = None
-        TP.hot_path_step(inp["memory"], inp["queries"], inp["refs"], lins, wl["shapes"], wl["npts"], H,
-                         inp["corners"], inp["ref_init"], up, rs, inp["grad_outs"], inp["grad_boxes"],
-                         train=True)
+        def step():
+            for t in (x for lin in lins for x in lin[:4]):
+                t.grad = None
+            TP.hot_path_step(inp["memory"], inp["queries"], inp["refs"], lins, wl["shapes"], wl["npts"], H,
+                             inp["corners"], inp["ref_init"], up, rs, inp["grad_outs"], inp["grad_boxes"],
+                             train=True)
 
     for _ in range(warmup):
         step()
@@ -1016,24 +1068,28 @@ def cpu_reference_run(wl: dict, sample_b: int, steps: int, warmup: int, seed: in
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    return sample_b * steps / dt, dt / steps * 1e3
+    return sample_b * steps / dt, dt / steps * 1e3, kind
 
 
 def run_reference_arm(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_b = args.cpu_sample
-    v, ms = cpu_reference_run(wl, sample_b, args.steps, args.warmup)
+    sample_b = args.cpu_sample or wl["B"]
+    v, ms, kind = cpu_reference_run(wl, sample_b, args.steps, args.warmup)
     cores = torch.get_num_threads()
+    what = ("the unmodified reference modules (baseline/_ref/src/d_fine/arch)" if kind == "reference"
+            else "reference call sequence restated in oracle/torch_port.py")
     sample = (f"{sample_b} of {wl['B']} images per step, {args.steps} steps, fp32, torch "
-              f"{torch.__version__} CPU, reference call sequence restated in oracle/torch_port.py")
+              f"{torch.__version__} CPU, {what}")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "sample_images_per_step": sample_b, "device": "cpu"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": args.workload, "images_per_gpu": wl["B"], "queries": wl["Lq"],
+                   "levels": wl["shapes"], "points": wl["npts"], "decoder_layers": wl["layers"],
+                   "sample_images_per_step": sample_b, "device": "cpu", "value_dtype": "f32"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -1045,7 +1101,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-sample", type=int, default=4, help="images per CPU-baseline step")
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="images per CPU-baseline step (0 = the workload's full batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager", action="store_true", help="skip the eager-PyTorch GPU bar")
     ap.add_argument("--no-full-model", action="store_true",
@@ -1230,12 +1287,14 @@ def main():
         except Exception as exc:  # noqa: BLE001
             out["gpu_eager_reference"] = {"error": str(exc)[:200]}
     if world == 1 and not args.no_cpu_baseline:
-        v, cms = cpu_reference_run(wl, args.cpu_sample, 2, 1)
+        nb = args.cpu_sample or wl["B"]
+        v, cms, kind = cpu_reference_run(wl, nb, 5, 1)
         cores = torch.get_num_threads()
-        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
                                "ms_per_step": cms,
-                               "sample": f"{args.cpu_sample} of {wl['B']} images per step, 2 timed steps "
-                                         f"after 1 warm-up, fp32, oracle/torch_port.py on the host CPU"}
+                               "sample": f"{nb} of {wl['B']} images per step, 5 timed steps after 1 warm-up, fp32, "
+                                         + ("the unmodified reference modules (baseline/_ref) on the host CPU"
+                                            if kind == "reference" else "oracle/torch_port.py on the host CPU")}
     print(json.dumps(out))
     if dist_on:
         hp.close()
