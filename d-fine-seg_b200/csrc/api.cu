@@ -34,6 +34,8 @@ int launch_mask_gemm_bwd(const void*, const void*, const void*, float*, void*, i
 int launch_colsum(const void*, int, long long, int, long long, float*, cudaStream_t);
 int launch_linear_wgrad(const void*, int64_t, const void*, int64_t, int, int, int, float*, cudaStream_t);
 int launch_multicast_add(const float*, float*, long long, float, cudaStream_t);
+int launch_lqe(const void*, int, const void*, int, const float*, const float*, const float*, const float*, void*,
+               long long, int, int, int, cudaStream_t);
 int launch_linear_fwd(const void*, int, int64_t, const float*, int64_t, const void*, const void*, int, void*, int, int64_t,
                       void*, int, int, int, int, cudaStream_t);
 int launch_gate_fwd(const float*, int64_t, const float*, int64_t, const void*, const void*, int, const float*,
@@ -543,6 +545,29 @@ int dfine_ffn_out_fwd(const void* h, int64_t h_row_stride, const void* w, const 
   return cuda_rc(launch_ffn_out_fwd(h, h_row_stride, w, bias, bias_dtype == DFINE_BF16, residual, res_row_stride,
                                     ln_weight, ln_bias, eps, out, out_row_stride, (int)M, C, F, (cudaStream_t)stream),
                  fn);
+}
+
+int dfine_lqe_fwd(const void* corners, int c_dtype, const void* scores, int s_dtype, const float* w1, const float* b1,
+                  const float* w2, const float* b2, void* out, int64_t N, int num_classes, int k, int hidden,
+                  int reg_max, int emulate_bf16, void* stream) {
+  const char* fn = "dfine_lqe_fwd";
+  int rc;
+  if (N < 0 || num_classes <= 0) {
+    set_error("%s: N must be >= 0 and num_classes > 0 (got %lld, %d)", fn, (long long)N, num_classes);
+    return DFINE_E_SHAPE;
+  }
+  if (k != 4 || hidden != 64 || reg_max < 4 || reg_max > 39) {
+    set_error("%s: built for k = 4, hidden = 64, 4 <= reg_max <= 39 (got %d, %d, %d)", fn, k, hidden, reg_max);
+    return DFINE_E_UNSUPPORTED;
+  }
+  if ((rc = dtype_ok(c_dtype, "c_dtype", fn)) || (rc = dtype_ok(s_dtype, "s_dtype", fn))) return rc;
+  if (N == 0) return 0;
+  const void* ptrs[7] = {corners, scores, w1, b1, w2, b2, out};
+  const char* names[7] = {"corners", "scores", "w1", "b1", "w2", "b2", "out"};
+  for (int i = 0; i < 7; ++i)
+    if ((rc = require_device(ptrs[i], names[i], fn))) return rc;
+  return cuda_rc(launch_lqe(corners, c_dtype == DFINE_BF16, scores, s_dtype == DFINE_BF16, w1, b1, w2, b2, out, N,
+                            reg_max, num_classes, emulate_bf16 != 0, (cudaStream_t)stream), fn);
 }
 
 int dfine_multicast_add(const float* src, float* dst_multicast, int64_t n, float scale, void* stream) {

@@ -53,6 +53,8 @@ _SIGNATURES = {
                                c_float, c_void_p, c_int64, c_int64, c_int, c_void_p]),
     "dfine_ffn_out_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p,
                                   c_float, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]),
+    "dfine_lqe_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                              c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dfine_multicast_add": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_void_p]),
     "dfine_pack_linear": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p,
                                   c_void_p, c_int, c_void_p]),

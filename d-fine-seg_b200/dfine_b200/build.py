@@ -19,7 +19,7 @@ LIB_DIR = os.path.join(PKG_DIR, "_C")
 # DFINE_B200_LIB: load another build of the same C-ABI (A/B measurements of kernel variants)
 LIB_PATH = os.environ.get("DFINE_B200_LIB") or os.path.join(LIB_DIR, "libdfine_b200.so")
 
-SOURCES = ["api.cu", "msda_fwd.cu", "msda_bwd.cu", "msda_bwd_value.cu", "fdr.cu", "mask_gemm.cu", "wgrad_gemm.cu", "reduce.cu", "lsap.cu", "mask_loss.cu", "linear_fused.cu"]
+SOURCES = ["api.cu", "msda_fwd.cu", "msda_bwd.cu", "msda_bwd_value.cu", "fdr.cu", "mask_gemm.cu", "wgrad_gemm.cu", "reduce.cu", "lsap.cu", "mask_loss.cu", "linear_fused.cu", "lqe.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",

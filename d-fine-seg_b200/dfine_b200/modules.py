@@ -246,6 +246,28 @@ def _layer_forward(self, target, reference_points, value, spatial_shapes, attn_m
     return self.norm3(target.clamp(min=-65504, max=65504))
 
 
+def _lqe_forward(self, scores, pred_corners):
+    """LQE.forward (reference dfine_decoder.py:307-313), same signature.  Inference on CUDA with the reference's
+    LQE(4, 64, 2, reg_max) shape: one fused launch; otherwise (training, other shapes, float16) the reference's
+    own op sequence."""
+    layers = getattr(self.reg_conf, "layers", None)
+    amp = torch.is_autocast_enabled()
+    ok = (not torch.is_grad_enabled() and scores.is_cuda and pred_corners.is_cuda and self.k == 4
+          and layers is not None and len(layers) == 2 and isinstance(self.reg_conf.act, nn.ReLU)
+          and layers[0].out_features == 64 and layers[1].out_features == 1 and self.reg_max <= 39
+          and scores.dtype in (torch.float32, torch.bfloat16) and pred_corners.dtype in (torch.float32, torch.bfloat16)
+          and (not amp or torch.get_autocast_dtype("cuda") == torch.bfloat16)
+          and (amp or (scores.dtype == torch.float32 and pred_corners.dtype == torch.float32)))
+    if not ok:
+        B, L, _ = pred_corners.size()
+        prob = F.softmax(pred_corners.reshape(B, L, 4, self.reg_max + 1), dim=-1)
+        prob_topk, _ = prob.topk(self.k, dim=-1)
+        stat = torch.cat([prob_topk, prob_topk.mean(dim=-1, keepdim=True)], dim=-1)
+        return scores + self.reg_conf(stat.reshape(B, L, -1))
+    return ops.lqe_fwd(scores, pred_corners, layers[0].weight, layers[0].bias, layers[1].weight, layers[1].bias,
+                       k=self.k, reg_max=self.reg_max, emulate_bf16=amp)
+
+
 def _is_decoder_layer(m: nn.Module) -> bool:
     return all(hasattr(m, a) for a in ("self_attn", "norm1", "cross_attn", "gateway", "linear1", "linear2", "norm3",
                                        "dropout1", "dropout2", "dropout3", "dropout4", "with_pos_embed",
@@ -282,11 +304,16 @@ def patch_model(model: nn.Module, fused: bool = True, fdr: bool = True, mask=Tru
     arithmetic run inside the kernel.  Parameters, buffers and state-dict keys are untouched.
     layer=True (with fused=True) additionally replaces TransformerDecoderLayer.forward (dfine_decoder.py:232-256):
     the positional add is folded into the cross-attention's Linear kernel, and in inference under bf16 autocast
-    the Gate, the FFN and their LayerNorms run as three fused tensor-core launches.
+    the Gate, the FFN and their LayerNorms run as three fused tensor-core launches, and LQE.forward
+    (:307-313) as one.
     Returns the number of patched modules per kind.
     """
-    n = {"msda": 0, "integral": 0, "mask": 0, "layer": 0}
+    n = {"msda": 0, "integral": 0, "mask": 0, "layer": 0, "lqe": 0}
     for m in model.modules():
+        if layer and type(m).__name__ == "LQE" and hasattr(m, "reg_conf") and hasattr(m, "k"):
+            _swap(m, "forward", types.MethodType(_lqe_forward, m))
+            n["lqe"] += 1
+            continue
         if layer and fused and _is_decoder_layer(m) and _is_msda(m.cross_attn):
             _swap(m, "forward", types.MethodType(_layer_forward, m))
             n["layer"] += 1

@@ -682,6 +682,29 @@ def ffn_out_fwd(h: torch.Tensor, w_bf16: torch.Tensor, bias: torch.Tensor, resid
     return out
 
 
+def lqe_fwd(scores: torch.Tensor, pred_corners: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor,
+            b2: torch.Tensor, k: int = 4, reg_max: int = 32, emulate_bf16: bool = False) -> torch.Tensor:
+    """LQE.forward of the reference (dfine_decoder.py:307-313) as ONE launch (dfine_lqe_fwd, inference):
+    scores [..., num_classes] + MLP(cat(topk(softmax(pred_corners [..., 4*(reg_max+1)]), k), mean)).
+    w1 [hidden, 4(k+1)], b1 [hidden], w2 [1, hidden], b2 [1]: float32 parameters of reg_conf."""
+    _require_cuda(scores, pred_corners, w1, b1, w2, b2)
+    nc = scores.shape[-1]
+    N = scores.numel() // nc
+    if pred_corners.numel() != N * 4 * (reg_max + 1):
+        raise ValueError("lqe_fwd: pred_corners must hold 4*(reg_max+1) logits per row of scores")
+    if any(t.dtype != torch.float32 for t in (w1, b1, w2, b2)):
+        raise TypeError("lqe_fwd: the MLP's parameters must be float32")
+    sc, pc = scores.contiguous(), pred_corners.contiguous()
+    out = torch.empty_like(sc)
+    with torch.cuda.device_of(sc), _timed("lqe_fwd", sc):
+        rc = _lib.lib().dfine_lqe_fwd(pc.data_ptr(), _dt(pc, "pred_corners"), sc.data_ptr(), _dt(sc, "scores"),
+                                      w1.contiguous().data_ptr(), b1.contiguous().data_ptr(),
+                                      w2.contiguous().data_ptr(), b2.contiguous().data_ptr(), out.data_ptr(), N, nc,
+                                      int(k), int(w1.shape[0]), int(reg_max), int(bool(emulate_bf16)), _stream(sc))
+    check(rc, "dfine_lqe_fwd")
+    return out
+
+
 def bf16_param(p: torch.Tensor) -> torch.Tensor:
     """A contiguous bfloat16 copy of a parameter, cached ON the parameter object until it is modified in place
     (inference: autocast casts the weights of every Linear on every call; here once).  The cache lives and dies

@@ -217,6 +217,20 @@ DFINE_API int dfine_ffn_out_fwd(const void* h, int64_t h_row_stride, const void*
                       const float* residual, int64_t res_row_stride, const float* ln_weight, const float* ln_bias,
                       float eps, float* out, int64_t out_row_stride, int64_t M, int C, int F, void* stream);
 
+/* LQE head, forward (inference): out = scores + reg_conf(cat(topk(softmax(pred_corners), k), mean(topk)))
+ * replaces LQE.forward (dfine_decoder.py:307-313; MLP :33-46): softmax over the reg_max+1 bins of the 4
+ * edges (the FDR head's softmax), top-k probabilities per edge and their mean, a 4(k+1) -> hidden -> 1 MLP
+ * with ReLU, broadcast add to the class scores.
+ *   corners  c_dtype [N, 4*(reg_max+1)]   pred_corners
+ *   scores   s_dtype [N, num_classes];  out: same dtype and shape (may alias scores)
+ *   w1 float32 [hidden, 4*(k+1)], b1 [hidden], w2 [hidden] (= reg_conf.layers[1].weight[0]), b2 [1]
+ *   emulate_bf16 != 0: the arithmetic of torch.autocast(bfloat16) (statistics, parameters and each Linear's
+ *   output rounded to bf16).  Built for k = 4, hidden = 64 (the reference's LQE(4, 64, 2, reg_max)),
+ *   reg_max <= 39; DFINE_E_UNSUPPORTED otherwise. */
+DFINE_API int dfine_lqe_fwd(const void* corners, int c_dtype, const void* scores, int s_dtype, const float* w1,
+                  const float* b1, const float* w2, const float* b2, void* out, int64_t N, int num_classes, int k,
+                  int hidden, int reg_max, int emulate_bf16, void* stream);
+
 /* Data-parallel gradient exchange without a collective launch (replaces DistributedDataParallel's
  * all-reduce of the path's Linear gradients, reference src/dl/train.py:161-166):
  *     replica_r[i] += scale * src[i]   for EVERY rank r, i < n

@@ -232,6 +232,65 @@ def test_ffn_tail_matches_reference_ops(M, C, Fd, dev):
     assert e <= 1e-2 and e2 <= 1e-2, (e, e2)
 
 
+def _ref_lqe(scores, pred_corners, l1, l2, k=4, reg_max=32):
+    """LQE.forward (dfine_decoder.py:307-313), restated op for op."""
+    B, L, _ = pred_corners.size()
+    prob = F.softmax(pred_corners.reshape(B, L, 4, reg_max + 1), dim=-1)
+    prob_topk, _ = prob.topk(k, dim=-1)
+    stat = torch.cat([prob_topk, prob_topk.mean(dim=-1, keepdim=True)], dim=-1)
+    return scores + l2(F.relu(l1(stat.reshape(B, L, -1))))
+
+
+@pytest.mark.parametrize("amp", [False, True], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("B,L,nc", [(3, 300, 80), (1, 37, 5), (64, 300, 80)])
+def test_lqe_fwd_matches_reference_ops(B, L, nc, amp, dev):
+    from dfine_b200 import ops
+    torch.manual_seed(B + L + nc)
+    l1, l2 = nn.Linear(20, 64).to(dev), nn.Linear(64, 1).to(dev)
+    with torch.no_grad():
+        l2.weight.normal_(0, 0.3)       # (the reference initialises the output layer to zero)
+        l2.bias.normal_(0, 0.3)
+    pc = torch.randn(B, L, 132, device=dev) * 3.0
+    pc[0, 0] = 0.0                      # uniform distribution: all ties
+    pc[0, 1, :33] = 80.0
+    pc[0, 2, 5] = 60.0                  # one-hot
+    sc = torch.randn(B, L, nc, device=dev)
+    if amp:
+        pc, sc = pc.bfloat16(), sc.bfloat16()
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            want = _ref_lqe(sc, pc, l1, l2)
+    else:
+        with torch.no_grad():
+            want = _ref_lqe(sc, pc, l1, l2)
+    got = ops.lqe_fwd(sc, pc, l1.weight.detach(), l1.bias.detach(), l2.weight.detach(), l2.bias.detach(),
+                      emulate_bf16=amp)
+    assert got.dtype == want.dtype and got.shape == want.shape
+    if amp:
+        # The library GEMMs behind the reference's two tiny Linears (K = 20 and 64, N = 1) do not accumulate
+        # the same way at every M (measured: at M = 19200 a quarter of the quality scores come out 1-2 bf16
+        # ulps from the fp32-accumulated value, at M = 900 none do), so the bound against the reference is
+        # the north star's bf16 tolerance ...
+        assert _scale_err(got.float(), want.float()) <= 1e-2
+        # ... and the kernel's own arithmetic is pinned bit for bit to the op sequence with fp32 accumulation
+        # and the rounding points of autocast made explicit:
+        r = lambda t: t.bfloat16().float()
+        with torch.no_grad():
+            prob = F.softmax(pc.float().reshape(B, L, 4, 33), dim=-1)
+            tk, _ = prob.topk(4, dim=-1)
+            stat = torch.cat([tk, tk.mean(-1, keepdim=True)], -1).reshape(B, L, 20)
+            h = F.relu(r(r(stat) @ r(l1.weight).t() + r(l1.bias)))
+            q = r(h @ r(l2.weight).t() + r(l2.bias))
+            emul = (sc.float() + q).bfloat16()
+        same = float((got == emul).float().mean())
+        assert same >= 0.999, same
+        _bf16_close(got, emul, "lqe (bf16) vs fp32-accumulated restatement")
+    else:
+        e = _scale_err(got, want)
+        assert e <= 1e-5, e
+        same = float((got == want).float().mean())
+    _log({"test": "lqe_fwd", "B": B, "L": L, "nc": nc, "amp": amp, "bit_identical": same})
+
+
 @pytest.fixture(scope="module")
 def H():
     from baseline import model_harness, ref_install
@@ -252,7 +311,7 @@ def test_patched_layer_inference_parity(name, seg, batch, dev, H):
     model.eval()
     patched = copy.deepcopy(model)
     counts = dfine_b200.patch_model(patched, layer=True)
-    assert counts["layer"] == len(model.decoder.decoder.layers)
+    assert counts["layer"] == len(model.decoder.decoder.layers) and counts["lqe"] == len(model.decoder.decoder.lqe_layers)
     images, _ = H.synthetic_batch(batch, 640, dev, seed=11)
     keys = ["pred_logits", "pred_boxes"] + (["pred_masks"] if seg else [])
     for amp, tol in ((torch.bfloat16, 1e-2), (None, 1e-5)):
@@ -262,7 +321,7 @@ def test_patched_layer_inference_parity(name, seg, batch, dev, H):
         names = set(ops.kernel_timers().keys())
         ops.enable_kernel_timers(False)
         if amp is not None:
-            assert {"gate_fwd", "ffn_out_fwd", "linear_fwd"} <= names, names
+            assert {"gate_fwd", "ffn_out_fwd", "linear_fwd", "lqe_fwd"} <= names, names
         else:
             assert not ({"gate_fwd", "ffn_out_fwd"} & names), names
         rec = {"test": "layer_inference", "model": name, "amp": str(amp)}
