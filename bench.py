@@ -923,7 +923,7 @@ class ClockSampler:
 
 def load_traffic(kernel: str):
     """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (or None)."""
-    for name in ("r3_traffic.json", "r2_traffic.json"):   # newest capture first
+    for name in ("r5_traffic.json", "r3_traffic.json", "r2_traffic.json"):   # newest capture first
         try:
             with open(os.path.join(ROOT, "profiles", name)) as f:
                 return json.load(f).get(kernel)
@@ -1216,7 +1216,7 @@ def main():
     roofline = {
         "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": load_traffic(dom), "peak_source": peak_src,
-        "traffic_source": "profiles/r3_traffic.json (ncu --set full, dram read + write per launch)",
+        "traffic_source": "profiles/r5_traffic.json (ncu --set full, dram read + write per launch)",
         "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": kms[dom],
         "msda_fwd_bwd": {"algorithmic_bytes": fwd_b + bwd_b, "ms": fb_ms,
                          "achieved": (fwd_b + bwd_b) / (fb_ms / 1e3) / 1e9,
