@@ -379,7 +379,12 @@ def msda_backward_split(memory, spec: LevelSpec, H: int, samp, attn, ref, pts_sc
 
 
 def new_records(memory: torch.Tensor, spec: LevelSpec, H: int, Lq: int) -> torch.Tensor:
-    """Workspace for the per-sample geometry records (16 bytes per sampling point)."""
+    """Workspace for the per-sample geometry records (16 bytes per sampling point).  Allocated by a forward
+    that will be differentiated: shapes the BACKWARD kernels do not take are refused here, before any
+    work is done (the forward alone accepts up to DFINE_MAX_POINTS = 32 points per head)."""
+    if spec.P > 16:
+        raise ValueError(f"dfine_msda_bwd takes at most 16 sampling points per head (got {spec.P}); the forward "
+                         "alone (no gradients) accepts up to 32")
     n = _lib.lib().dfine_msda_bwd_workspace_bytes(memory.shape[0], Lq, H, spec.P)
     return torch.empty(n, dtype=torch.uint8, device=memory.device)
 
@@ -433,6 +438,10 @@ class _MemoryHubFn(torch.autograd.Function):
         ent = _HUBS.get(ctx.key)
         if ent is not None and ent[2] is ctx.sess:
             del _HUBS[ctx.key]
+        tid = torch._C._current_graph_task_id() if hasattr(torch._C, "_current_graph_task_id") else None
+        if ctx.sess.get("task", tid) != tid:      # what is in the buffer belongs to an earlier, unfinished pass
+            ctx.sess["buf"] = None
+        ctx.sess.pop("task", None)
         buf, ctx.sess["buf"] = ctx.sess.get("buf"), None
         ev = ctx.sess.pop("event", None)
         if ev is not None and buf is not None:   # grad_value kernels ran on the side stream
@@ -463,6 +472,22 @@ def _memory_token(memory: torch.Tensor, anchor: Optional[torch.Tensor] = None):
     return token, sess
 
 
+def _new_backward_pass(sess: dict) -> None:
+    """The shared buffer belongs to ONE backward pass.  A pass that ran layer backwards without reaching the hub
+    (torch.autograd.grad(..., inputs=[query], retain_graph=True), an exception mid-backward) leaves a stale
+    sum behind: the first layer of the next pass -- recognised by the autograd engine's graph-task id -- starts a
+    fresh buffer instead of accumulating onto it."""
+    tid = torch._C._current_graph_task_id() if hasattr(torch._C, "_current_graph_task_id") else None
+    if sess.get("task") != tid or tid is None or tid < 0:
+        if sess.get("task", tid) != tid:
+            ev = sess.pop("event", None)
+            if ev is not None and sess.get("buf") is not None:
+                torch.cuda.current_stream(sess["buf"].device).wait_event(ev)
+            sess["buf"] = None
+            sess.pop("keep", None)
+        sess["task"] = tid
+
+
 def _grad_memory(ctx, memory, *args, **kw):
     """Runs dfine_msda_bwd for one layer.  With a hub session the layer's grad_value lands in
     the shared buffer (first layer writes it, later ones accumulate) and None is returned for
@@ -470,6 +495,7 @@ def _grad_memory(ctx, memory, *args, **kw):
     sess = ctx.sess
     if sess is None:
         return msda_backward_raw(memory, *args, gv_dtype=memory.dtype, **kw)
+    _new_backward_pass(sess)
     if _OVERLAP_GRAD_VALUE and kw.get("records") is not None:
         got = msda_backward_split(memory, *args, sess=sess, **kw)
         if got is not None:

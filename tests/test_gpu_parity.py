@@ -823,6 +823,48 @@ def test_shared_memory_gradient_hub(amp, overlap, dev):
     assert len(ops._HUBS) <= ops._MAX_HUBS
 
 
+def test_hub_ignores_a_pass_that_never_reached_it(dev):
+    """torch.autograd.grad(..., inputs=[query], retain_graph=True) runs the layers' backward kernels but not the
+    hub node: the sum it leaves in the shared buffer must not leak into the next backward() over the retained
+    graph (the first layer of a new pass -- a new autograd graph task -- starts a fresh buffer)."""
+    import dfine_b200
+    from dfine_b200 import ops
+    from oracle import torch_port as TP
+    torch.manual_seed(12)
+    B, Lq, C, H = 2, 40, 256, 8
+    shapes, npts = [[16, 12], [8, 6], [4, 3]], [3, 6, 3]
+    L = sum(h * w for h, w in shapes)
+    mods = []
+    for _ in range(3):
+        m = dfine_b200.MSDeformableAttention(C, H, len(shapes), npts).to(dev)
+        with torch.no_grad():
+            m.sampling_offsets.weight.normal_(0, 0.02)
+            m.attention_weights.weight.normal_(0, 0.05)
+        mods.append(m)
+    enc = torch.randn(B, L, C, device=dev)
+    qs = [torch.randn(B, Lq, C, device=dev, requires_grad=True) for _ in mods]
+    ref = torch.cat([torch.rand(B, Lq, 2, device=dev), torch.rand(B, Lq, 2, device=dev) * 0.5 + 0.05], -1)
+    gos = [torch.randn(B, Lq, C, device=dev) for _ in mods]
+
+    def run(share, probe_first):
+        old = ops.share_memory_grad(share)
+        try:
+            leaf = enc.clone().requires_grad_(True)
+            value = TP.value_views(leaf * 1.5, H, shapes)
+            outs = [m(q, ref.unsqueeze(2), value, shapes) for m, q in zip(mods, qs)]
+            if probe_first:     # layer backwards run, the hub does not
+                torch.autograd.grad(outs, qs, gos, retain_graph=True)
+                torch.autograd.grad(outs[:2], qs[:2], gos[:2], retain_graph=True)
+            torch.autograd.backward(outs, gos)
+            return leaf.grad.clone()
+        finally:
+            ops.share_memory_grad(old)
+
+    want = run(False, False)
+    assert_close(run(True, False).cpu().numpy(), want.cpu().numpy(), FP32_RTOL, "hub, plain backward")
+    assert_close(run(True, True).cpu().numpy(), want.cpu().numpy(), FP32_RTOL, "hub after autograd.grad(inputs=[query])")
+
+
 def test_many_queries_fall_back_to_reductions(dev):
     """More sampling points per (image, head, level) than the grad_value kernel can list in
     shared memory (node ids are 16-bit): the library switches to fp32 vector reductions, the

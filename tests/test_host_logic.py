@@ -289,3 +289,13 @@ def test_layerwise_grad_sync_gloo():
         for x0, x1, y0, y1 in zip(l0, l1, o0[step], o1[step]):
             np.testing.assert_allclose(y0, (x0 + x1) / 2, rtol=1e-6, atol=1e-6)
             np.testing.assert_array_equal(y0, y1)
+
+
+def test_backward_point_limit_is_refused_before_any_work():
+    """The forward takes up to 32 sampling points per head, the backward kernels 16: a differentiated forward with
+    17-32 points must fail when it allocates its records, not at loss.backward() (no GPU needed: the check
+    precedes the library call)."""
+    from dfine_b200 import ops
+    spec = ops.level_spec([[8, 8], [4, 4]], [9, 9])
+    with pytest.raises(ValueError, match="at most 16"):
+        ops.new_records(torch.zeros(1, 80, 256), spec, 8, 10)
