@@ -299,3 +299,33 @@ def test_backward_point_limit_is_refused_before_any_work():
     spec = ops.level_spec([[8, 8], [4, 4]], [9, 9])
     with pytest.raises(ValueError, match="at most 16"):
         ops.new_records(torch.zeros(1, 80, 256), spec, 8, 10)
+
+
+def test_reference_points_last_dim_2_branch_is_dead_in_the_reference_and_fails_alike():
+    """MSDeformableAttention.forward's `reference_points.shape[-1] == 2` branch (reference dfine_decoder.py:149-155,
+    inherited from RT-DETR) divides the [bs, Lq, H, P, 2] offsets by a [1, 1, 1, n_levels, 1, 2] normaliser: the
+    broadcast fails for every head / level count (probed: RuntimeError "The size of tensor a ... must match"), so
+    no configuration can reach the sampling core through it.  The mirror keeps the branch and its error behaviour
+    (same exception type, raised by the same arithmetic, before any kernel is launched); last dim 3 raises the
+    reference's ValueError."""
+    import dfine_b200
+    H, shapes, npts = 8, [[8, 8], [4, 4], [2, 2]], [3, 6, 3]
+    C, B, Lq = 128, 2, 5
+    L = sum(h * w for h, w in shapes)
+    mem, q = torch.randn(B, L, C), torch.randn(B, Lq, C)
+    value = mem.reshape(B, L, H, C // H).permute(0, 2, 3, 1).split([h * w for h, w in shapes], dim=-1)
+    ref2 = torch.rand(B, Lq, len(shapes), 2)
+    mods = [dfine_b200.MSDeformableAttention(C, H, len(shapes), npts)]
+    try:
+        from baseline import ref_install
+        if ref_install.installed():
+            ref_install.import_reference()
+            from src.d_fine.arch.dfine_decoder import MSDeformableAttention as RefMSDA
+            mods.append(RefMSDA(C, H, len(shapes), npts))
+    except ImportError:
+        pass
+    for m in mods:
+        with pytest.raises(RuntimeError, match="must match the size"):
+            m(q, ref2, value, shapes)
+        with pytest.raises(ValueError, match="Last dim of reference_points must be 2 or 4"):
+            m(q, torch.rand(B, Lq, 1, 3), value, shapes)
