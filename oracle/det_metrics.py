@@ -11,6 +11,8 @@ pieces on that path are restated here in numpy/torch:
                         descending IoU, class-aware TP / FP / FN; unmatched predictions are FPs,
                         unmatched ground truths FNs), F1 from the summed counts (:300-338)
 * mask IoU             src/dl/validator.py:269-279  (intersection / union of binary masks)
+* mask postprocess     src/dl/train.py:296-316 + src/dl/utils.py:715-786 (kept queries' mask probabilities -> half
+                        -> bilinear resize to the input size -> clamp, >= conf_thresh -> zero outside the box)
 """
 from __future__ import annotations
 
@@ -100,3 +102,25 @@ def mask_iou(a: np.ndarray, b: np.ndarray) -> float:
     a, b = a.astype(bool), b.astype(bool)
     union = np.logical_or(a, b).sum()
     return float(np.logical_and(a, b).sum() / union) if union else 0.0
+
+
+def postprocess_masks(pred_masks: torch.Tensor, preds: List[Dict[str, torch.Tensor]], size: int,
+                      conf_thresh: float = 0.5) -> List[torch.Tensor]:
+    """train.py:296-316 for square inputs without letterboxing (orig size = network input size): per image the
+    uint8 masks [N, size, size] of the kept predictions (`preds` from `postprocess`: "queries", "boxes" in
+    normalised xyxy)."""
+    out = []
+    for b, p in enumerate(preds):
+        q = p["queries"].to(pred_masks.device)
+        if q.numel() == 0:
+            out.append(torch.zeros((0, size, size), dtype=torch.uint8))
+            continue
+        mb = pred_masks[b, q].to(torch.float16).unsqueeze(0)
+        m = torch.nn.functional.interpolate(mb, size=(size, size), mode="bilinear", align_corners=False)[0]
+        m = (m.clamp(0, 1) >= conf_thresh).to(torch.uint8).cpu()
+        ys = torch.arange(size)[None, :, None]
+        xs = torch.arange(size)[None, None, :]
+        x1, y1, x2, y2 = (p["boxes"] * size).T          # utils.py:772-786 cleanup_masks
+        inside = (xs >= x1[:, None, None]) & (xs < x2[:, None, None]) & (ys >= y1[:, None, None]) & (ys < y2[:, None, None])
+        out.append(m * inside.to(m.dtype))
+    return out

@@ -560,3 +560,100 @@ def test_graphed_inference_bit_identical(name, seg, batch, dev, H):
     with pytest.raises(RuntimeError):
         patched.train()
         dfine_b200.GraphedInference(patched, x0)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# North star: "detection F1 / mask IoU must be unchanged on a fixed synthetic set" -- on the REFERENCE MODEL,
+# trained briefly on synthetic coloured rectangles so that the metric is non-trivial
+# ------------------------------------------------------------------------------------------------------------
+_COLORS = torch.tensor([[1.0, 0.1, 0.1], [0.1, 1.0, 0.1], [0.1, 0.1, 1.0], [1.0, 1.0, 0.1]])
+
+
+def _rect_batch(batch, size, device, seed, n_gt=3, nc=4):
+    """Dark noisy images with n_gt axis-aligned rectangles, colour = class; boxes, labels and rectangle masks."""
+    g = torch.Generator().manual_seed(seed)
+    images = torch.rand(batch, 3, size, size, generator=g) * 0.15
+    targets = []
+    for b in range(batch):
+        labels = torch.randint(0, nc, (n_gt,), generator=g)
+        cxcy = torch.rand(n_gt, 2, generator=g) * 0.6 + 0.2
+        wh = torch.rand(n_gt, 2, generator=g) * 0.2 + 0.12
+        m = torch.zeros(n_gt, size, size, dtype=torch.uint8)
+        for i in range(n_gt):
+            x0, x1 = int((cxcy[i, 0] - wh[i, 0] / 2) * size), int((cxcy[i, 0] + wh[i, 0] / 2) * size)
+            y0, y1 = int((cxcy[i, 1] - wh[i, 1] / 2) * size), int((cxcy[i, 1] + wh[i, 1] / 2) * size)
+            m[i, y0:y1, x0:x1] = 1
+            images[b, :, y0:y1, x0:x1] = _COLORS[labels[i]].view(3, 1, 1) * (0.8 + 0.2 * torch.rand(1, generator=g))
+        targets.append({"labels": labels.to(device), "boxes": torch.cat([cxcy, wh], -1).to(device),
+                        "masks": m.to(device)})
+    return images.to(device), targets
+
+
+def test_f1_and_mask_iou_unchanged_on_a_trained_model(dev, H):
+    """D-FINE-n-seg (4 classes, 256 x 256) is trained for 600 steps on synthetic rectangles THROUGH the patched
+    path (patch_model(layer=True): forward and backward kernels of this repo, the reference's criterion and
+    AdamW) -- it has to converge for the test to mean anything -- and then evaluated on a fixed set of 32
+    images by (a) the unmodified reference model holding the same weights, (b) the patched model, (c) the patched
+    model replayed from a CUDA graph.  The reference's metric (oracle/det_metrics.py: top-300 postprocess,
+    confidence 0.5, greedy IoU matching at 0.5, class-aware TP / FP / FN, F1; masks resized, thresholded and
+    clipped to their boxes, IoU against the ground-truth masks of the matched pairs) must come out the same:
+    identical counts and matches in fp32; under bf16 autocast at most two decisions may differ (scores within a
+    bf16 ulp of the threshold)."""
+    import dfine_b200
+    from oracle import det_metrics as DM
+    size, nc = 256, 4
+    model, loss_fn = H.build("n", dev, size, True, num_classes=nc, trained=False)
+    model.train(), loss_fn.train()
+    counts = dfine_b200.patch_model(model, layer=True)
+    assert counts["msda"] > 0 and counts["mask"] == 1
+    opt = H.build_optimizer(model, "n")
+    first = last = None
+    for it in range(600):
+        images, targets = _rect_batch(8, size, dev, 1000 + it)
+        _, _, loss = H.train_step(model, loss_fn, images, targets, None, optimizer=opt)
+        if it < 20:
+            first = float(loss.detach()) if first is None else max(first, float(loss.detach()))
+    last = float(loss.detach())
+    assert last < 0.75 * first, f"training through the patched path did not converge: loss {first:.1f} -> {last:.1f}"
+    model.eval()
+    reference = copy.deepcopy(model)
+    dfine_b200.unpatch_model(reference)
+    eval_set = [_rect_batch(4, size, dev, s) for s in range(8)]
+    graphed = dfine_b200.GraphedInference(model, eval_set[0][0], amp_dtype=None)
+
+    def metric(fn):
+        tp = fp = fn_ = 0
+        matches, ious = [], []
+        for images, targets in eval_set:
+            out = fn(images)
+            preds = DM.postprocess(out["pred_logits"], out["pred_boxes"], 0.5)
+            gts = [{"boxes": DM.box_cxcywh_to_xyxy(t["boxes"].cpu()), "labels": t["labels"].cpu()} for t in targets]
+            a, b, c, _, m = DM.f1_counts(preds, gts)
+            tp, fp, fn_ = tp + a, fp + b, fn_ + c
+            matches.append(m)
+            masks = DM.postprocess_masks(out["pred_masks"], preds, size)
+            for i, pairs in enumerate(m):
+                for p_, g_ in pairs:
+                    ious.append(DM.mask_iou(masks[i][p_].numpy(), targets[i]["masks"][g_].cpu().numpy()))
+        return {"tp": tp, "fp": fp, "fn": fn_, "f1": DM.f1_score(tp, fp, fn_), "matches": matches,
+                "mask_iou": float(np.mean(ious)) if ious else 0.0, "ious": ious}
+
+    rec = {"test": "f1_mask_iou_trained_model", "loss_first": first, "loss_last": last}
+    for amp_name, amp in (("fp32", None), ("bf16", torch.bfloat16)):
+        want = metric(lambda x: H.infer_step(reference, x, amp))
+        got = metric(lambda x: H.infer_step(model, x, amp))
+        rec[amp_name] = {k: {"f1": v["f1"], "tp": v["tp"], "fp": v["fp"], "fn": v["fn"], "mask_iou": v["mask_iou"]}
+                         for k, v in (("reference", want), ("patched", got))}
+        assert want["f1"] >= 0.3 and want["mask_iou"] >= 0.3, (amp_name, want["f1"], want["mask_iou"])
+        if amp is None:
+            assert (got["tp"], got["fp"], got["fn"]) == (want["tp"], want["fp"], want["fn"]), (got, want)
+            assert got["matches"] == want["matches"]
+            assert np.abs(np.asarray(got["ious"]) - np.asarray(want["ious"])).max() <= 1e-2   # a border pixel may flip
+            assert abs(got["mask_iou"] - want["mask_iou"]) <= 1e-3
+            g2 = metric(lambda x: graphed(x))
+            assert (g2["tp"], g2["fp"], g2["fn"]) == (got["tp"], got["fp"], got["fn"]) and g2["matches"] == got["matches"]
+            assert g2["ious"] == got["ious"], "graph replay is bit-identical to the eager patched model"
+        else:
+            assert abs(got["tp"] - want["tp"]) <= 2 and abs(got["fp"] - want["fp"]) <= 2 and abs(got["fn"] - want["fn"]) <= 2
+            assert abs(got["f1"] - want["f1"]) <= 0.03 and abs(got["mask_iou"] - want["mask_iou"]) <= 0.02
+    _log(rec)
