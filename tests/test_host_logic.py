@@ -1,6 +1,7 @@
 """CPU-side tests: the C-ABI symbol table, argument validation (no compute calls), the
 zero-copy recovery of `memory` behind value_op's views, model patching, and the
 world_size-2 (gloo) logic of bench.py."""
+import copy
 import ctypes
 import os
 import re
@@ -58,6 +59,42 @@ def test_argument_validation_without_gpu():
     assert lib.dfine_linear_wgrad(None, 0, None, 0, 16, 288, 256, None, None) == -1
     with pytest.raises(_lib.DfineB200Error):
         _lib.check(rc, "probe")
+    # the fused decoder-layer entry points: shapes / dtypes before pointers
+    L = lib.dfine_linear_fwd
+    assert L(None, 0, 0, None, 0, None, None, 1, None, 1, 0, None, 0, 288, 256, 0, None) == -2          # M = 0
+    assert L(None, 7, 0, None, 0, None, None, 1, None, 1, 0, None, 16, 288, 256, 0, None) == -3         # dtype
+    assert L(None, 0, 100, None, 0, None, None, 1, None, 1, 0, None, 16, 288, 256, 0, None) == -2       # stride < K
+    assert b"row strides" in lib.dfine_last_error()
+    assert L(None, 0, 0, None, 0, None, None, 1, None, 1, 0, None, 16, 288, 256, 0, None) == -1         # NULL x
+    assert lib.dfine_gate_fwd(None, 0, None, 0, None, None, 1, None, None, 1e-5, None, 0, 16, 100, None) == -3
+    assert b"multiple of 64" in lib.dfine_last_error()
+    assert lib.dfine_gate_fwd(None, 0, None, 0, None, None, 1, None, None, 1e-5, None, 0, 16, 512, None) == -3
+    assert lib.dfine_ffn_out_fwd(None, 0, None, None, 1, None, 0, None, None, 1e-5, None, 0, 16, 256, 100, None) == -1 \
+        or lib.dfine_ffn_out_fwd(None, 0, None, None, 1, None, 0, None, None, 1e-5, None, 0, 16, 256, 100, None) == -3
+    assert lib.dfine_lqe_fwd(None, 0, None, 0, None, None, None, None, None, 10, 80, 3, 64, 32, 0, None) == -3
+    assert b"k = 4" in lib.dfine_last_error()
+    assert lib.dfine_lqe_fwd(None, 0, None, 0, None, None, None, None, None, 10, 80, 4, 64, 32, 0, None) == -1
+    assert lib.dfine_lqe_fwd(None, 0, None, 0, None, None, None, None, None, 0, 80, 4, 64, 32, 0, None) == 0   # empty
+
+
+def test_parameter_caches_live_and_die_with_the_parameter():
+    """bf16 copies of parameters (inference) are cached on the parameter OBJECT and invalidated by in-place
+    modification; a new tensor at the same address, with the same shape and version, never sees them."""
+    from dfine_b200 import ops
+    p = torch.nn.Parameter(torch.randn(8, 8))
+    t = ops.bf16_param(p)
+    assert t.dtype == torch.bfloat16 and ops.bf16_param(p) is t
+    with torch.no_grad():
+        p.add_(1.0)
+    t2 = ops.bf16_param(p)
+    assert t2 is not t and torch.equal(t2, p.detach().bfloat16())
+    q = copy.deepcopy(p)
+    assert "_dfine_bf16" not in q.__dict__
+    with torch.no_grad():
+        q.mul_(2.0)
+    assert torch.equal(ops.bf16_param(q), q.detach().bfloat16())
+    b = torch.randn(4).bfloat16()
+    assert ops.bf16_param(b) is b
 
 
 def test_cpu_tensors_are_rejected():
