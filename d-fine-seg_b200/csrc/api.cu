@@ -34,9 +34,11 @@ int launch_mask_gemm_bwd(const void*, const void*, const void*, float*, void*, i
 int launch_colsum(const void*, int, long long, int, long long, float*, cudaStream_t);
 int launch_linear_wgrad(const void*, int64_t, const void*, int64_t, int, int, int, float*, cudaStream_t);
 int launch_multicast_add(const float*, float*, long long, float, cudaStream_t);
+int launch_ffn_fwd(const float*, int64_t, const void*, const void*, const void*, const void*, int, const float*,
+                   const float*, float, float*, int64_t, int, int, int, cudaStream_t);
 int launch_lqe(const void*, int, const void*, int, const float*, const float*, const float*, const float*, void*,
                long long, int, int, int, cudaStream_t);
-int launch_linear_fwd(const void*, int, int64_t, const float*, int64_t, const void*, const void*, int, void*, int, int64_t,
+int launch_linear_fwd(const void*, int, int64_t, const void*, int, int64_t, const void*, const void*, int, void*, int, int64_t,
                       void*, int, int, int, int, cudaStream_t);
 int launch_gate_fwd(const float*, int64_t, const float*, int64_t, const void*, const void*, int, const float*,
                     const float*, float, float*, int64_t, int, int, cudaStream_t);
@@ -426,7 +428,8 @@ static int dtype_ok(int dt, const char* what, const char* fn) {
   return 0;
 }
 
-int dfine_linear_fwd(const void* x, int x_dtype, int64_t x_row_stride, const float* x_add, int64_t xadd_row_stride,
+int dfine_linear_fwd(const void* x, int x_dtype, int64_t x_row_stride, const void* x_add, int xadd_dtype,
+                     int64_t xadd_row_stride,
                      const void* w, const void* bias, int bias_dtype, void* y, int y_dtype, int64_t y_row_stride,
                      void* x_bf16_out, int64_t M, int N, int K, int relu, void* stream) {
   const char* fn = "dfine_linear_fwd";
@@ -436,7 +439,7 @@ int dfine_linear_fwd(const void* x, int x_dtype, int64_t x_row_stride, const flo
     return DFINE_E_SHAPE;
   }
   if ((rc = dtype_ok(x_dtype, "x_dtype", fn)) || (rc = dtype_ok(bias_dtype, "bias_dtype", fn)) ||
-      (rc = dtype_ok(y_dtype, "y_dtype", fn)))
+      (rc = dtype_ok(y_dtype, "y_dtype", fn)) || (x_add && (rc = dtype_ok(xadd_dtype, "xadd_dtype", fn))))
     return rc;
   if (x_row_stride == 0) x_row_stride = K;
   if (xadd_row_stride == 0) xadd_row_stride = K;
@@ -465,7 +468,8 @@ int dfine_linear_fwd(const void* x, int x_dtype, int64_t x_row_stride, const flo
     set_error("%s: x, x_add, w, y and x_bf16_out must be 16-byte aligned", fn);
     return DFINE_E_ALIGN;
   }
-  return cuda_rc(launch_linear_fwd(x, x_dtype == DFINE_BF16, x_row_stride, x_add, xadd_row_stride, w, bias,
+  return cuda_rc(launch_linear_fwd(x, x_dtype == DFINE_BF16, x_row_stride, x_add, xadd_dtype == DFINE_BF16,
+                                   xadd_row_stride, w, bias,
                                    bias_dtype == DFINE_BF16, y, y_dtype == DFINE_BF16, y_row_stride, x_bf16_out, (int)M,
                                    N, K, relu, (cudaStream_t)stream), fn);
 }
@@ -545,6 +549,39 @@ int dfine_ffn_out_fwd(const void* h, int64_t h_row_stride, const void* w, const 
   return cuda_rc(launch_ffn_out_fwd(h, h_row_stride, w, bias, bias_dtype == DFINE_BF16, residual, res_row_stride,
                                     ln_weight, ln_bias, eps, out, out_row_stride, (int)M, C, F, (cudaStream_t)stream),
                  fn);
+}
+
+int dfine_ffn_fwd(const float* x, int64_t x_row_stride, const void* w1, const void* b1, const void* w2, const void* b2,
+                  int bias_dtype, const float* ln_weight, const float* ln_bias, float eps, float* out,
+                  int64_t out_row_stride, int64_t M, int C, int F, void* stream) {
+  const char* fn = "dfine_ffn_fwd";
+  int rc;
+  if (M <= 0 || M > 0x7fffffffLL) {
+    set_error("%s: need 0 < M < 2^31 (got %lld)", fn, (long long)M);
+    return DFINE_E_SHAPE;
+  }
+  if ((C != 128 && C != 256) || F <= 0 || (F & 127)) {
+    set_error("%s: built for C = 128 or 256 and F a multiple of 128 (got C = %d, F = %d)", fn, C, F);
+    return DFINE_E_UNSUPPORTED;
+  }
+  if ((rc = dtype_ok(bias_dtype, "bias_dtype", fn))) return rc;
+  if (x_row_stride == 0) x_row_stride = C;
+  if (out_row_stride == 0) out_row_stride = C;
+  if (x_row_stride < C || out_row_stride < C || (x_row_stride & 3) || (out_row_stride & 3)) {
+    set_error("%s: row strides (%lld, %lld) must be >= C and multiples of 4", fn, (long long)x_row_stride,
+              (long long)out_row_stride);
+    return DFINE_E_SHAPE;
+  }
+  const void* ptrs[8] = {x, w1, b1, w2, b2, ln_weight, ln_bias, out};
+  const char* names[8] = {"x", "w1", "b1", "w2", "b2", "ln_weight", "ln_bias", "out"};
+  for (int i = 0; i < 8; ++i)
+    if ((rc = require_device(ptrs[i], names[i], fn))) return rc;
+  if (!aligned16(x) || !aligned16(w1) || !aligned16(w2) || !aligned16(out) || !aligned16(b1) || !aligned16(b2)) {
+    set_error("%s: x, w1, b1, w2, b2 and out must be 16-byte aligned", fn);
+    return DFINE_E_ALIGN;
+  }
+  return cuda_rc(launch_ffn_fwd(x, x_row_stride, w1, b1, w2, b2, bias_dtype == DFINE_BF16, ln_weight, ln_bias, eps, out,
+                                out_row_stride, (int)M, C, F, (cudaStream_t)stream), fn);
 }
 
 int dfine_lqe_fwd(const void* corners, int c_dtype, const void* scores, int s_dtype, const float* w1, const float* b1,

@@ -4,7 +4,7 @@
 //   EPI_BIAS    y = act(bf16(x [+ x_add]) W^T + b)
 //               * MSDeformableAttention's concatenated sampling_offsets / attention_weights Linear
 //                 (:139-147) with the caller's  with_pos_embed  add (:245, :227-228) and autocast's
-//                 fp32 -> bf16 cast of the query folded into the operand load (x, x_add fp32);
+//                 fp32 -> bf16 cast of the query folded into the operand load (x fp32, x_add fp32 or bf16);
 //               * linear1 + ReLU of the FFN (:229-230).
 //   EPI_GATE    Gate.forward (:258-271):  g = sigmoid([x1 | x2] W^T + b);  LayerNorm(g1*x1 + g2*x2)
 //               -- torch.cat, the cast, the GEMM, sigmoid, chunk, two multiplies, the add and the
@@ -30,6 +30,8 @@
 //                               through shared memory) -> transposition through padded shared memory ->
 //                               row-contiguous 16-byte stores.
 #include <cuda.h>
+
+#include <cstdlib>
 
 #include "common.cuh"
 #include "tma_util.cuh"
@@ -60,7 +62,8 @@ enum { A_BF16 = 0, A_F32 = 1, A_F32_CAT = 2 };
 
 struct Args {
   const void* x0;        // A_F32 / A_F32_CAT: fp32 rows (A_BF16: unused, the rows come through map_a)
-  const float* x1;       // A_F32: rows added to x0 (nullable); A_F32_CAT: the second half of the cat
+  const float* x1;       // A_F32: rows added to x0 (nullable; fp32, or bf16 when x1_bf16); A_F32_CAT: the second half of the cat
+  int x1_bf16;
   int64_t x0_rs, x1_rs;  // row strides in elements
   __nv_bfloat16* a_save; // optional: the bf16 A rows [M, K] (the weight-gradient kernel's input)
   const void* bias;      // [N] fp32 or bf16
@@ -82,6 +85,17 @@ struct Args {
 
 __host__ __device__ constexpr uint32_t idesc(int n) {   // D = f32, A = B = bf16, both K-major, M = 128
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+
+// K-major SW128 operand descriptors (LBO 16 B, SBO 1024 B) built from a precomputed low word: one thread issues
+// every MMA of the CTA, so its instruction stream IS the tensor pipe's issue rate -- measured on the fused FFN
+// kernel: 148 cycles per M128 x N128 x K16 MMA with make_desc() evaluated per MMA (shift / mask / or of two
+// 64-bit descriptors), against 64 cycles of tensor work.  The tile bases are 1024-byte aligned, so advancing
+// 16 k (32 bytes) is +2 on the low word.
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3fffu) | (1u << 16); }
+__device__ __forceinline__ uint64_t desc_k(uint32_t lo, int k) {
+  constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | (2u << 29);     // SBO | version 1 | SWIZZLE_128B
+  return ((uint64_t)kHi << 32) | (uint64_t)(lo + 2u * (uint32_t)k);
 }
 
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0, int c1) {
@@ -266,7 +280,23 @@ linear_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
     else
       issue_from(reinterpret_cast<const float*>(a.x0), a.x0_rs, kk + 4 * f, v);
   };
-  auto issue_add = [&](int kb, float4 (&v)[8]) { issue_from(a.x1, a.x1_rs, kb * BLOCK_K + 4 * f, v); };
+  // the added rows: fp32, or bf16 (under autocast the reference's query_pos_head returns bf16; fp32 + bf16
+  // promotes to fp32) -- four bf16 per lane, kept as raw bits in .x / .y until they are added
+  auto issue_add = [&](int kb, float4 (&v)[8]) {
+    if (!a.x1_bf16) {
+      issue_from(a.x1, a.x1_rs, kb * BLOCK_K + 4 * f, v);
+      return;
+    }
+    const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(a.x1);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int m = mt * BLOCK_M + i * 16 + cw * 2 + rsub;
+      uint2 u = make_uint2(0u, 0u);
+      if (m < a.M) u = __ldg(reinterpret_cast<const uint2*>(src + (int64_t)m * a.x1_rs + kb * BLOCK_K + 4 * f));
+      v[i].x = __uint_as_float(u.x);
+      v[i].y = __uint_as_float(u.y);
+    }
+  };
   if (convert && warp >= 2) {                      // in flight under the barrier / TMEM set-up
     issue(0, b0);
     if (has_add) {
@@ -328,15 +358,12 @@ linear_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
         if (convert) mbar_wait(smem_u32(&full_a[stage]), phase);
         tcgen05_fence_after();
         const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-        const uint32_t sb = sa + A_BYTES;
+        // both operands K-major SW128: 8-row groups 1024 B apart; +32 B per 16 k inside the row
+        const uint32_t la = desc_lo(sa), lb0 = desc_lo(sa + A_BYTES), lb1 = desc_lo(sa + A_BYTES + a.nc * 128);
 #pragma unroll
         for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          // both operands K-major SW128: 8-row groups 1024 B apart; +32 B per 16 k inside the row
-          const uint64_t da = make_desc(sa + k * UMMA_K * 2, 16, 1024);
-          for (int j = 0; j < a.n_mma; ++j) {
-            const uint64_t db = make_desc(sb + j * a.nc * 128 + k * UMMA_K * 2, 16, 1024);
-            umma_bf16(tmem_base + j * a.nc, da, db, id, (kb | k) != 0 ? 1u : 0u);
-          }
+          umma_bf16(tmem_base, desc_k(la, k), desc_k(lb0, k), id, (kb | k) != 0 ? 1u : 0u);
+          if (a.n_mma > 1) umma_bf16(tmem_base + a.nc, desc_k(la, k), desc_k(lb1, k), id, (kb | k) != 0 ? 1u : 0u);
         }
         umma_commit(smem_u32(&empty_bar[stage]));
         if (++stage == a.stages) {
@@ -379,7 +406,15 @@ linear_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
       };
       auto add_into = [&](float4 (&v)[8], const float4 (&p)[8]) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { v[i].x += p[i].x; v[i].y += p[i].y; v[i].z += p[i].z; v[i].w += p[i].w; }
+        for (int i = 0; i < 8; ++i) {
+          if (a.x1_bf16) {
+            const uint32_t u0 = __float_as_uint(p[i].x), u1 = __float_as_uint(p[i].y);
+            v[i].x += __uint_as_float(u0 << 16); v[i].y += __uint_as_float(u0 & 0xffff0000u);
+            v[i].z += __uint_as_float(u1 << 16); v[i].w += __uint_as_float(u1 & 0xffff0000u);
+          } else {
+            v[i].x += p[i].x; v[i].y += p[i].y; v[i].z += p[i].z; v[i].w += p[i].w;
+          }
+        }
       };
       if (has_add) {
         for (int kb = 0; kb < k_blocks; kb += 2) {
@@ -513,10 +548,409 @@ linear_fused_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
         tmem_ld_32x32(taddr + c0, r);
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          v[j] = (__uint_as_float(r[j]) - mean) * rstd * __ldg(a.ln_w + c0 + j) + __ldg(a.ln_b + c0 + j);
+        for (int j8 = 0; j8 < 32; j8 += 8) {
+          float gw[8], gb[8];
+          load_bias8(a.ln_w, 0, c0 + j8, gw);
+          load_bias8(a.ln_b, 0, c0 + j8, gb);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j8 + j] = (__uint_as_float(r[j8 + j]) - mean) * rstd * gw[j] + gb[j];
+        }
         store_rows(v, a.y, a.y_rs, 0, m0, c0, a.M, stg, lane);
       }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+  }
+}
+
+// =====================================================================================================
+// The whole FFN of a decoder layer in ONE kernel (reference dfine_decoder.py:229-230, :251-253):
+//     out = LayerNorm(clamp(x + (relu(x W1^T + b1) W2^T + b2), -65504, 65504))
+// The hidden rows never leave the SM.  One CTA per 128 rows; the hidden dimension is processed in chunks of 128:
+//     GEMM1(j): D1[j % 2] (128 x 128, TMEM) = X (128 x C, bf16, resident in smem) . W1[128 j .. , :]^T
+//     chunk epilogue (warps 2..9): D1 -> + b1 -> ReLU -> bf16 -> H in smem, in the UMMA K-major swizzle layout
+//     GEMM2(j): D2 (128 x C, TMEM) += H (128 x 128) . W2[:, 128 j ..]^T
+// The MMA warp issues GEMM1(j + 1) before GEMM2(j), so the tensor pipe works on the next chunk while the epilogue
+// warps turn the current one into the second GEMM's operand; D1 is double-buffered, the weights stream
+// through a ring of 16-KB units ([128 rows][64 k] boxes of W1 / W2: 1 MB per CTA at C = 256, F = 1024, from L2).
+// TMEM: D1 2 x 128 columns + D2 C columns <= 512.  Same autocast(bfloat16) rounding points as the two-kernel
+// route: X, the hidden rows and linear2's result are rounded to bf16, accumulation, residual, LayerNorm fp32.
+// =====================================================================================================
+constexpr int FF_CHUNK = 128;                      // hidden units per chunk (UMMA N of GEMM1, K of GEMM2)
+constexpr int FF_UNIT_BYTES = 128 * 128;           // one [128 rows][64 k] bf16 box
+constexpr int FF_RING = 6;          // even: the two 128-row halves of a W2 k-block sit in adjacent units
+constexpr int FF_H_BYTES = BLOCK_M * FF_CHUNK * 2; // 32 KiB (single buffer: the shared memory goes to the weight ring)
+
+struct FfnArgs {
+  const float* x;          // [M, C] fp32: the FFN's input and the residual
+  int64_t x_rs;
+  const void* b1;          // [F]
+  const void* b2;          // [C]
+  int b_bf16;
+  const float* ln_w;
+  const float* ln_b;
+  float eps;
+  float* out;              // [M, C] fp32
+  int64_t out_rs;
+  int M, C, F;
+  int rotate;
+};
+
+#ifdef DFINE_FFN_PROF
+// per-CTA cycle counters of the MMA thread: {total, waiting for weight units, waiting for D1 to be drained, waiting
+// for H, issuing}, and of epilogue thread (warp 2, lane 0): {waiting d1_full, waiting h_empty, working}
+__device__ long long g_ffn_prof[256][8];
+#define FFN_T() clock64()
+#else
+#define FFN_T() 0ll
+#endif
+
+__global__ void __launch_bounds__(THREADS, 1)
+ffn_fused_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2, const FfnArgs a) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int kb1 = a.C / BLOCK_K;                   // k-blocks of GEMM1 (2 or 4)
+  const int nh = a.C / 128;                        // 128-column halves of D2 (1 or 2)
+  const int chunks = a.F / FF_CHUNK;
+  const int rot = a.rotate ? (int)(blockIdx.x % chunks) : 0;   // experiment: de-synchronise the CTAs' weight streams
+  unsigned char* smem_a = smem;                                    // [kb1][A_BYTES] resident X
+  unsigned char* smem_h = smem_a + kb1 * A_BYTES;                  // [FF_H_BYTES] hidden chunk (A operand of GEMM2)
+  unsigned char* smem_w = smem_h + FF_H_BYTES;                     // [FF_RING][FF_UNIT_BYTES]; the final epilogue's staging
+  float* smem_red = reinterpret_cast<float*>(smem_w + FF_RING * FF_UNIT_BYTES);
+  float* smem_b1 = smem_red + RED_BYTES / 4;                       // [F] linear1's bias, float32
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b1 + a.F);
+  uint64_t* w_full = bars;                 // [FF_RING]
+  uint64_t* w_empty = bars + FF_RING;      // [FF_RING]
+  uint64_t* a_full = bars + 2 * FF_RING;   // [1]  X converted (8 warps)
+  uint64_t* d1_full = a_full + 1;          // [2]  GEMM1 of a chunk retired
+  uint64_t* d1_empty = d1_full + 2;        // [2]  chunk epilogue has read D1 (8 warps)
+  uint64_t* h_full = d1_empty + 2;         // [2]  H written (8 warps)
+  uint64_t* h_empty = h_full + 2;          // [2]  GEMM2 of a chunk retired
+  uint64_t* d2_full = h_empty + 2;         // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d2_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int mt = blockIdx.x;
+  const int cw = warp - 2;
+
+  // X rows: half a warp per row, 16 lanes x float4 = one 64-wide k-block; loads of the first two k-blocks in flight
+  // under the set-up
+  const int rsub = lane >> 4, f = lane & 15;
+  float4 xa[8], xb[8];
+  auto issue = [&](int kb, float4 (&v)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int m = mt * BLOCK_M + i * 16 + cw * 2 + rsub;
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < a.M) v[i] = __ldg(reinterpret_cast<const float4*>(a.x + (int64_t)m * a.x_rs + kb * BLOCK_K + 4 * f));
+    }
+  };
+  if (warp >= 2) {
+    issue(0, xa);
+    issue(1, xb);
+  }
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < FF_RING; ++i) {
+      mbar_init(smem_u32(&w_full[i]), 1);
+      mbar_init(smem_u32(&w_empty[i]), 1);
+    }
+    mbar_init(smem_u32(a_full), CONV_WARPS);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&d1_full[i]), 1);
+      mbar_init(smem_u32(&d1_empty[i]), CONV_WARPS / 2);
+      mbar_init(smem_u32(&h_full[i]), CONV_WARPS / 2);
+      mbar_init(smem_u32(&h_empty[i]), 1);
+    }
+    mbar_init(smem_u32(d2_full), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_d2 = tmem_base + 2 * FF_CHUNK;
+
+  if (warp == 0) {
+    // ===================== TMA producer: weight units in the order the MMA warp consumes them =====================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w1) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w2) : "memory");
+      int slot = 0;
+      uint32_t phase = 0;
+      auto put = [&](const CUtensorMap* map, int c0, int c1) {
+        mbar_wait(smem_u32(&w_empty[slot]), phase ^ 1);
+        const uint32_t fb = smem_u32(&w_full[slot]);
+        mbar_expect_tx(fb, FF_UNIT_BYTES);
+        tma_load_2d(map, smem_u32(smem_w + slot * FF_UNIT_BYTES), fb, c0, c1);
+        if (++slot == FF_RING) {
+          slot = 0;
+          phase ^= 1;
+        }
+      };
+      auto g1 = [&](int j) {
+        for (int kb = 0; kb < kb1; ++kb) put(&map_w1, kb * BLOCK_K, ((j + rot) % chunks) * FF_CHUNK);
+      };
+      auto g2 = [&](int j) {
+        for (int kk = 0; kk < FF_CHUNK / BLOCK_K; ++kk)
+          for (int h = 0; h < nh; ++h) put(&map_w2, ((j + rot) % chunks) * FF_CHUNK + kk * BLOCK_K, h * 128);
+      };
+      g1(0);
+      for (int j = 0; j < chunks; ++j) {
+        if (j + 1 < chunks) g1(j + 1);
+        g2(j);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t phase = 0;
+      const uint32_t id128 = idesc(128);
+      const uint32_t la0 = desc_lo(smem_u32(smem_a)), lh0 = desc_lo(smem_u32(smem_h));
+      long long t_w = 0, t_d1 = 0, t_h = 0;
+      const long long t_begin = FFN_T();
+      auto take = [&]() -> uint32_t {       // next weight unit (its smem address); released by `release`
+        const long long t0 = FFN_T();
+        mbar_wait(smem_u32(&w_full[slot]), phase);
+        t_w += FFN_T() - t0;
+        tcgen05_fence_after();
+        return smem_u32(smem_w + slot * FF_UNIT_BYTES);
+      };
+      auto release = [&]() {
+        umma_commit(smem_u32(&w_empty[slot]));
+        if (++slot == FF_RING) {
+          slot = 0;
+          phase ^= 1;
+        }
+      };
+      int slot_held = 0;
+      auto release_later = [&]() {          // keep the unit, move on to its neighbour (never wraps: even slot)
+        slot_held = slot;
+        ++slot;
+      };
+      auto release_both = [&]() {
+        umma_commit(smem_u32(&w_empty[slot_held]));
+        release();
+      };
+      const uint32_t id256 = idesc(256);
+      auto gemm1 = [&](int j) {
+        const int b = j & 1, use = j >> 1;
+        const long long t0 = FFN_T();
+        mbar_wait(smem_u32(&d1_empty[b]), (use & 1) ^ 1);     // the chunk epilogue drained this accumulator
+        t_d1 += FFN_T() - t0;
+        tcgen05_fence_after();
+        for (int kb = 0; kb < kb1; ++kb) {
+          const uint32_t lb = desc_lo(take());
+          const uint32_t la = la0 + (uint32_t)kb * (A_BYTES >> 4);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_bf16(tmem_base + b * FF_CHUNK, desc_k(la, k), desc_k(lb, k), id128, (kb | k) != 0 ? 1u : 0u);
+          release();
+        }
+        umma_commit(smem_u32(&d1_full[b]));
+      };
+      auto gemm2 = [&](int j) {
+        const long long t0 = FFN_T();
+        mbar_wait(smem_u32(&h_full[0]), j & 1);               // the hidden chunk is in smem
+        t_h += FFN_T() - t0;
+        tcgen05_fence_after();
+        for (int kk = 0; kk < FF_CHUNK / BLOCK_K; ++kk) {
+          const uint32_t la = lh0 + (uint32_t)kk * (A_BYTES >> 4);
+          if (nh == 2) {
+            // C = 256: the two units of this k-block are adjacent (even ring, every group of units is even): ONE
+            // N = 256 MMA per k-step reads the A operand once -- cta_group::1 MMAs are bound by operand delivery
+            // from shared memory (measured: 137 cycles per N = 128 MMA against 64 of tensor work)
+            const uint32_t lb = desc_lo(take());
+            release_later();
+            take();
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_bf16(tmem_d2, desc_k(la, k), desc_k(lb, k), id256, (j | kk | k) != 0 ? 1u : 0u);
+            release_both();
+          } else {
+            const uint32_t lb = desc_lo(take());
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_bf16(tmem_d2, desc_k(la, k), desc_k(lb, k), id128, (j | kk | k) != 0 ? 1u : 0u);
+            release();
+          }
+        }
+        umma_commit(smem_u32(&h_empty[0]));
+      };
+      mbar_wait(smem_u32(a_full), 0);
+      tcgen05_fence_after();
+      gemm1(0);
+      for (int j = 0; j < chunks; ++j) {
+        if (j + 1 < chunks) gemm1(j + 1);
+        gemm2(j);
+      }
+      umma_commit(smem_u32(d2_full));
+#ifdef DFINE_FFN_PROF
+      if (blockIdx.x < 256) {
+        g_ffn_prof[blockIdx.x][0] = FFN_T() - t_begin;
+        g_ffn_prof[blockIdx.x][1] = t_w;
+        g_ffn_prof[blockIdx.x][2] = t_d1;
+        g_ffn_prof[blockIdx.x][3] = t_h;
+      }
+#endif
+    }
+  } else {
+    // ===================== X -> bf16, resident A operand =====================
+    auto put_a = [&](int kb, const float4 (&v)[8]) {
+      unsigned char* sa = smem_a + kb * A_BYTES;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = i * 16 + cw * 2 + rsub;
+        const __nv_bfloat162 p0 = __floats2bfloat162_rn(v[i].x, v[i].y), p1 = __floats2bfloat162_rn(v[i].z, v[i].w);
+        *reinterpret_cast<uint2*>(sa + r * 128 + ((((f >> 1) ^ (r & 7)) << 4) | ((f & 1) << 3))) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
+      }
+    };
+    for (int kb = 0; kb < kb1; kb += 2) {
+      put_a(kb, xa);
+      if (kb + 2 < kb1) issue(kb + 2, xa);
+      put_a(kb + 1, xb);
+      if (kb + 3 < kb1) issue(kb + 3, xb);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(a_full));
+
+    // ===================== chunk epilogues: D1 -> relu(. + b1) -> bf16 -> H =====================
+    // The two groups of four warps alternate chunks (group g owns D1[g] / H[g]): a group has two chunk periods for
+    // its epilogue, so the tensor pipe does not wait for the TMEM -> registers -> smem round trip.
+    for (int i = threadIdx.x - 64; i < a.F; i += 32 * CONV_WARPS) smem_b1[i] = load_scalar(a.b1, i, a.b_bf16);
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * CONV_WARPS) : "memory");
+    const int wq = warp & 3, member = cw >> 2;
+    const int row = wq * 32 + lane;                // row of the tile held by this thread
+    const uint32_t tq = (uint32_t)(wq * 32) << 16;
+    long long e_d1 = 0, e_h = 0;
+    const long long e_begin = FFN_T();
+    for (int j = member; j < chunks; j += 2) {
+      const int b = member, use = j >> 1;
+      long long t0 = FFN_T();
+      mbar_wait(smem_u32(&d1_full[b]), use & 1);
+      e_d1 += FFN_T() - t0;
+      tcgen05_fence_after();
+      t0 = FFN_T();
+      mbar_wait(smem_u32(&h_empty[0]), (j & 1) ^ 1);            // GEMM2 of the previous chunk has read the H buffer
+      e_h += FFN_T() - t0;
+#pragma unroll
+      for (int part = 0; part < 4; ++part) {
+        const int c0 = part * 32;                               // column inside the chunk
+        unsigned char* hb = smem_h + (part >> 1) * A_BYTES;     // k-block of H holding these columns
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + tq + b * FF_CHUNK + c0, r);
+        const float* bj = smem_b1 + ((j + rot) % chunks) * FF_CHUNK + c0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {                           // 8 values = one 16-byte chunk of the row
+          const float4 b0 = *reinterpret_cast<const float4*>(bj + 8 * q), b1v = *reinterpret_cast<const float4*>(bj + 8 * q + 4);
+          const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1v.x, b1v.y, b1v.z, b1v.w};
+          uint32_t pk[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float v0 = fmaxf(__uint_as_float(r[8 * q + 2 * i]) + bv[2 * i], 0.f);
+            const float v1 = fmaxf(__uint_as_float(r[8 * q + 2 * i + 1]) + bv[2 * i + 1], 0.f);
+            const __nv_bfloat162 p = __floats2bfloat162_rn(v0, v1);
+            pk[i] = *reinterpret_cast<const uint32_t*>(&p);
+          }
+          const int cc = (part & 1) * 4 + q;                    // 16-byte chunk index inside the 128-byte row
+          *reinterpret_cast<uint4*>(hb + row * 128 + ((cc ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+      tcgen05_fence_before();
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(smem_u32(&d1_empty[b]));
+        mbar_arrive(smem_u32(&h_full[0]));
+      }
+    }
+
+#ifdef DFINE_FFN_PROF
+    if (warp == 2 && lane == 0 && blockIdx.x < 256) {
+      g_ffn_prof[blockIdx.x][4] = FFN_T() - e_begin;
+      g_ffn_prof[blockIdx.x][5] = e_d1;
+      g_ffn_prof[blockIdx.x][6] = e_h;
+    }
+#endif
+    // ===================== final epilogue: + b2 -> bf16 -> + x -> clamp -> LayerNorm =====================
+    const int m0 = mt * BLOCK_M + wq * 32;
+    const int C = a.C;
+    const int cbeg = member * (C / 2), cend = cbeg + C / 2;
+    float* stg = reinterpret_cast<float*>(smem_w) + cw * 32 * STG_ROW;   // the weight ring is idle by now
+    float4 ta[8];
+    fetch_rows(a.x, a.x_rs, m0, cbeg, a.M, lane, ta);
+    mbar_wait(smem_u32(d2_full), 0);
+    tcgen05_fence_after();
+    const uint32_t taddr = tmem_d2 + tq;
+    float sum = 0.f;
+    for (int c0 = cbeg; c0 < cend; c0 += 32) {
+      uint32_t r[32];
+      float xv[32], v[32];
+      tmem_ld_32x32(taddr + c0, r);
+      stage_rows(ta, stg, lane, xv);
+      if (c0 + 32 < cend) fetch_rows(a.x, a.x_rs, m0, c0 + 32, a.M, lane, ta);
+#pragma unroll
+      for (int j8 = 0; j8 < 32; j8 += 8) {
+        float bv[8];
+        load_bias8(a.b2, a.b_bf16, c0 + j8, bv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float t = bf16_round(__uint_as_float(r[j8 + j]) + bv[j]);
+          v[j8 + j] = fminf(fmaxf(xv[j8 + j] + t, -65504.f), 65504.f);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        sum += v[j];
+        r[j] = __float_as_uint(v[j]);
+      }
+      tmem_st_32x32(taddr + c0, r);
+    }
+    smem_red[member * BLOCK_M + row] = sum;
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * CONV_WARPS) : "memory");
+    const float mean = (smem_red[row] + smem_red[BLOCK_M + row]) / (float)C;
+    float sq = 0.f;
+    for (int c0 = cbeg; c0 < cend; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32(taddr + c0, r);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float d = __uint_as_float(r[j]) - mean;
+        sq = fmaf(d, d, sq);
+      }
+    }
+    smem_red[2 * BLOCK_M + member * BLOCK_M + row] = sq;
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * CONV_WARPS) : "memory");
+    const float var = (smem_red[2 * BLOCK_M + row] + smem_red[3 * BLOCK_M + row]) / (float)C;
+    const float rstd = rsqrtf(var + a.eps);
+    for (int c0 = cbeg; c0 < cend; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32(taddr + c0, r);
+      float v[32];
+#pragma unroll
+      for (int j8 = 0; j8 < 32; j8 += 8) {
+        float gw[8], gb[8];
+        load_bias8(a.ln_w, 0, c0 + j8, gw);
+        load_bias8(a.ln_b, 0, c0 + j8, gb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j8 + j] = (__uint_as_float(r[j8 + j]) - mean) * rstd * gw[j] + gb[j];
+      }
+      store_rows(v, a.out, a.out_rs, 0, m0, c0, a.M, stg, lane);
     }
   }
 
@@ -597,13 +1031,40 @@ static int launch(Args a, const void* w, const void* a_bf16, int64_t a_rs, cudaS
   return (int)cudaGetLastError();
 }
 
+
+static int launch_ffn(const FfnArgs& a, const void* w1, const void* w2, cudaStream_t s) {
+  const char* fn = "dfine_ffn_fwd";
+  if ((a.C != 128 && a.C != 256) || a.F % FF_CHUNK || a.F <= 0 || a.M <= 0) {
+    set_error("%s: built for C = 128 or 256 and F a multiple of 128 (got C = %d, F = %d)", fn, a.C, a.F);
+    return DFINE_E_UNSUPPORTED;
+  }
+  alignas(64) CUtensorMap map_w1, map_w2;
+  int rc;
+  if ((rc = encode_2d(&map_w1, w1, (uint64_t)a.C, (uint64_t)a.F, (uint64_t)a.C * 2, 128, "linear1.weight"))) return rc;
+  if ((rc = encode_2d(&map_w2, w2, (uint64_t)a.F, (uint64_t)a.C, (uint64_t)a.F * 2, 128, "linear2.weight"))) return rc;
+  const int smem = (a.C / BLOCK_K) * A_BYTES + FF_H_BYTES + FF_RING * FF_UNIT_BYTES + RED_BYTES + a.F * 4 + MISC_BYTES;
+  if (smem > SMEM_LIMIT) {
+    set_error("%s: F = %d needs %d bytes of shared memory", fn, a.F, smem);
+    return DFINE_E_UNSUPPORTED;
+  }
+  static_assert(FF_RING * FF_UNIT_BYTES >= STG_BYTES, "the final epilogue stages through the idle weight ring");
+  static PerDeviceOnce configured;
+  if (!configured.done()) {
+    const cudaError_t e = cudaFuncSetAttribute(ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    if (e != cudaSuccess) return (int)e;
+    configured.mark();
+  }
+  ffn_fused_kernel<<<(unsigned)((a.M + BLOCK_M - 1) / BLOCK_M), THREADS, smem, s>>>(map_w1, map_w2, a);
+  return (int)cudaGetLastError();
+}
+
 }  // namespace lf
 
-int launch_linear_fwd(const void* x, int x_bf16, int64_t x_rs, const float* x_add, int64_t xadd_rs, const void* w,
+int launch_linear_fwd(const void* x, int x_bf16, int64_t x_rs, const void* x_add, int xadd_bf16, int64_t xadd_rs, const void* w,
                       const void* bias, int bias_bf16, void* y, int y_bf16, int64_t y_rs, void* x_bf16_out, int M,
                       int N, int K, int relu, cudaStream_t s) {
   lf::Args a{};
-  a.x0 = x; a.x1 = x_add; a.x0_rs = x_rs; a.x1_rs = xadd_rs;
+  a.x0 = x; a.x1 = reinterpret_cast<const float*>(x_add); a.x1_bf16 = xadd_bf16; a.x0_rs = x_rs; a.x1_rs = xadd_rs;
   a.a_save = reinterpret_cast<__nv_bfloat16*>(x_bf16_out);
   a.bias = bias; a.bias_bf16 = bias_bf16;
   a.y = y; a.y_rs = y_rs; a.y_bf16 = y_bf16; a.relu = relu;
@@ -640,3 +1101,22 @@ int launch_ffn_out_fwd(const void* h, int64_t h_rs, const void* w, const void* b
 }
 
 }  // namespace dfine
+
+namespace dfine {
+int launch_ffn_fwd(const float* x, int64_t x_rs, const void* w1, const void* b1, const void* w2, const void* b2,
+                   int bias_bf16, const float* ln_w, const float* ln_b, float eps, float* out, int64_t out_rs, int M,
+                   int C, int F, cudaStream_t s) {
+  lf::FfnArgs a{};
+  a.x = x; a.x_rs = x_rs; a.b1 = b1; a.b2 = b2; a.b_bf16 = bias_bf16;
+  a.ln_w = ln_w; a.ln_b = ln_b; a.eps = eps; a.out = out; a.out_rs = out_rs;
+  a.M = M; a.C = C; a.F = F;
+  a.rotate = getenv("DFINE_FFN_ROTATE") != nullptr;
+  return lf::launch_ffn(a, w1, w2, s);
+}
+}  // namespace dfine
+
+#ifdef DFINE_FFN_PROF
+extern "C" __attribute__((visibility("default"))) int dfine_debug_ffn_prof(void* dst) {
+  return (int)cudaMemcpyFromSymbol(dst, dfine::lf::g_ffn_prof, sizeof(dfine::lf::g_ffn_prof));
+}
+#endif

@@ -47,12 +47,14 @@ _SIGNATURES = {
     "dfine_fdr_bwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_int, c_int64, c_int, c_void_p]),
     "dfine_linear_wgrad": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p]),
-    "dfine_linear_fwd": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_int,
+    "dfine_linear_fwd": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_int,
                                  c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p]),
     "dfine_gate_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                c_float, c_void_p, c_int64, c_int64, c_int, c_void_p]),
     "dfine_ffn_out_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p,
                                   c_float, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]),
+    "dfine_ffn_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_float,
+                              c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]),
     "dfine_lqe_fwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                               c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "dfine_multicast_add": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_void_p]),

@@ -219,8 +219,9 @@ def _layer_forward(self, target, reference_points, value, spatial_shapes, attn_m
 
     Self-attention and norm1 are the reference's modules.  The cross-attention receives the positional embedding
     separately (the add happens inside the fused Linear).  In inference under bf16 autocast the rest of the layer
-    is three launches: Gate (cat + Linear + sigmoid + mix + LayerNorm), linear1 + ReLU, linear2 + residual +
-    clamp + norm3; in training the reference modules run (autograd)."""
+    is two launches: Gate (cat + Linear + sigmoid + mix + LayerNorm) and the FFN (linear1 + ReLU + linear2 +
+    residual + clamp + norm3 in one kernel; two kernels for widths the fused one does not take); in training the
+    reference modules run (autograd)."""
     q = k = self.with_pos_embed(target, query_pos_embed)
     target2, _ = self.self_attn(q, k, value=target, attn_mask=attn_mask)
     target = target + self.dropout1(target2)
@@ -236,9 +237,12 @@ def _layer_forward(self, target, reference_points, value, spatial_shapes, attn_m
         g = self.gateway
         target = ops.gate_fwd(target.contiguous(), target2.float().contiguous(), ops.bf16_param(g.gate.weight),
                               ops.bf16_param(g.gate.bias), g.norm.weight, g.norm.bias, g.norm.eps)
-        h = ops.linear_fwd(target, ops.bf16_param(self.linear1.weight), ops.bf16_param(self.linear1.bias), relu=True)
-        return ops.ffn_out_fwd(h, ops.bf16_param(self.linear2.weight), ops.bf16_param(self.linear2.bias), target,
-                               self.norm3.weight, self.norm3.bias, self.norm3.eps)
+        w1, b1 = ops.bf16_param(self.linear1.weight), ops.bf16_param(self.linear1.bias)
+        w2, b2 = ops.bf16_param(self.linear2.weight), ops.bf16_param(self.linear2.bias)
+        if ops.ffn_fwd_supported(target, w1.shape[0]):      # the whole FFN in one launch (hidden rows stay on the SM)
+            return ops.ffn_fwd(target, w1, b1, w2, b2, self.norm3.weight, self.norm3.bias, self.norm3.eps)
+        h = ops.linear_fwd(target, w1, b1, relu=True)
+        return ops.ffn_out_fwd(h, w2, b2, target, self.norm3.weight, self.norm3.bias, self.norm3.eps)
 
     target = self.gateway(target, self.dropout2(target2))
     target2 = self.forward_ffn(target)

@@ -623,7 +623,7 @@ class _LinearFn(torch.autograd.Function):
 
 
 def linear_fwd_supported(x: torch.Tensor, N: int, x_add: Optional[torch.Tensor] = None) -> bool:
-    """Shapes / dtypes dfine_linear_fwd takes (include/dfine_b200.h): x float32 (optionally + float32 x_add) or
+    """Shapes / dtypes dfine_linear_fwd takes (include/dfine_b200.h): x float32 (optionally + float32 / bfloat16 x_add) or
     bfloat16, rows of K = x.shape[-1] elements with K % 64 == 0, N splitting into equal tiles of <= 512 columns."""
     if os.environ.get("DFINE_LINEAR_FWD", "1") == "0":     # A/B switch: cast kernel + cuBLAS GEMM
         return False
@@ -633,7 +633,7 @@ def linear_fwd_supported(x: torch.Tensor, N: int, x_add: Optional[torch.Tensor] 
         return False
     if not (x.is_cuda and x.dtype in _DT and x.is_contiguous() and x.data_ptr() % 16 == 0):
         return False
-    if x_add is not None and not (x.dtype == torch.float32 and x_add.dtype == torch.float32 and x_add.is_cuda
+    if x_add is not None and not (x.dtype == torch.float32 and x_add.dtype in _DT and x_add.is_cuda
                                   and x_add.shape == x.shape and x_add.is_contiguous()
                                   and x_add.data_ptr() % 16 == 0):
         return False
@@ -657,7 +657,8 @@ def linear_fwd(x: torch.Tensor, w_bf16: torch.Tensor, bias: torch.Tensor, x_add:
     y = torch.empty((*x.shape[:-1], N), dtype=out_dtype, device=x.device)
     xs = torch.empty((M, K), dtype=torch.bfloat16, device=x.device) if save_input and x.dtype == torch.float32 else None
     with torch.cuda.device_of(x), _timed("linear_fwd", x):
-        rc = _lib.lib().dfine_linear_fwd(x.data_ptr(), _DT[x.dtype], K, _ptr(x_add), K, w_bf16.data_ptr(),
+        rc = _lib.lib().dfine_linear_fwd(x.data_ptr(), _DT[x.dtype], K, _ptr(x_add),
+                                         _DT[x_add.dtype] if x_add is not None else F32, K, w_bf16.data_ptr(),
                                          bias.data_ptr(), _dt(bias, "bias"), y.data_ptr(), _DT[out_dtype], N,
                                          _ptr(xs), M, N, K, int(bool(relu)), _stream(x))
     check(rc, "dfine_linear_fwd")
@@ -705,6 +706,39 @@ def ffn_out_fwd(h: torch.Tensor, w_bf16: torch.Tensor, bias: torch.Tensor, resid
                                           residual.data_ptr(), C, ln_weight.data_ptr(), ln_bias.data_ptr(), float(eps),
                                           out.data_ptr(), C, M, C, F, _stream(h))
     check(rc, "dfine_ffn_out_fwd")
+    return out
+
+
+def ffn_fwd_supported(x: torch.Tensor, F: int) -> bool:
+    if os.environ.get("DFINE_FFN_FUSED", "1") == "0":      # A/B switch: dfine_linear_fwd(relu) + dfine_ffn_out_fwd
+        return False
+    return (x.is_cuda and x.dtype == torch.float32 and x.shape[-1] in (128, 256) and F % 128 == 0 and F > 0
+            and x.numel() > 0)
+
+
+def ffn_fwd(x: torch.Tensor, w1_bf16: torch.Tensor, b1: torch.Tensor, w2_bf16: torch.Tensor, b2: torch.Tensor,
+            ln_weight: torch.Tensor, ln_bias: torch.Tensor, eps: float) -> torch.Tensor:
+    """LayerNorm(clamp(x + linear2(relu(linear1(x))), -65504, 65504)) under bf16 autocast as ONE launch
+    (dfine_ffn_fwd: the hidden rows stay on the SM).  x float32 [..., C]; w1_bf16 [F, C], w2_bf16 [C, F] bfloat16;
+    b1 [F], b2 [C] in one dtype (float32 / bfloat16)."""
+    _require_cuda(x, w1_bf16, b1, w2_bf16, b2, ln_weight, ln_bias)
+    C = x.shape[-1]
+    F = w1_bf16.shape[0]
+    if (x.dtype != torch.float32 or w1_bf16.dtype != torch.bfloat16 or w2_bf16.dtype != torch.bfloat16
+            or tuple(w1_bf16.shape) != (F, C) or tuple(w2_bf16.shape) != (C, F) or b1.dtype != b2.dtype
+            or not w1_bf16.is_contiguous() or not w2_bf16.is_contiguous() or b1.numel() != F or b2.numel() != C):
+        raise ValueError("ffn_fwd: need float32 x [..., C], bfloat16 w1 [F, C] and w2 [C, F], biases of one dtype")
+    if not ffn_fwd_supported(x, F):
+        raise ValueError(f"ffn_fwd: unsupported shape C = {C}, F = {F} (C in (128, 256), F a multiple of 128)")
+    xc = x.contiguous()
+    M = xc.numel() // C
+    out = torch.empty_like(xc)
+    with torch.cuda.device_of(xc), _timed("ffn_fwd", xc):
+        rc = _lib.lib().dfine_ffn_fwd(xc.data_ptr(), C, w1_bf16.data_ptr(), b1.contiguous().data_ptr(),
+                                      w2_bf16.data_ptr(), b2.contiguous().data_ptr(), _dt(b1, "bias"),
+                                      ln_weight.data_ptr(), ln_bias.data_ptr(), float(eps), out.data_ptr(), C, M, C, F,
+                                      _stream(xc))
+    check(rc, "dfine_ffn_fwd")
     return out
 
 

@@ -187,7 +187,8 @@ DFINE_API int dfine_linear_wgrad(const void* grad_y, int64_t gy_row_stride, cons
  *   (:245, :227-228), autocast's fp32 -> bf16 cast of the query, the concatenated sampling_offsets /
  *   attention_weights GEMM and its bias; for the FFN (:229-230): linear1 + ReLU.
  *     x          x_dtype [M, K] (x_row_stride elements between rows, 0 = K)
- *     x_add      float32 [M, K] or NULL (query_pos_embed); float32 x only
+ *     x_add      xadd_dtype [M, K] or NULL (query_pos_embed: bf16 under autocast, float32 otherwise; the sum is
+ *                formed in float32 as torch's type promotion does); float32 x only
  *     w          bf16 [N, K] contiguous (nn.Linear layout; dfine_pack_linear writes it)
  *     bias       bias_dtype [N]
  *     y          y_dtype [M, N] (y_row_stride, 0 = N)
@@ -207,7 +208,7 @@ DFINE_API int dfine_linear_wgrad(const void* grad_y, int64_t gy_row_stride, cons
  *
  * C a multiple of 64, <= 256; F a multiple of 64.  Forward only (inference; training keeps the
  * reference modules and their autograd).  DFINE_E_UNSUPPORTED for other shapes. */
-DFINE_API int dfine_linear_fwd(const void* x, int x_dtype, int64_t x_row_stride, const float* x_add,
+DFINE_API int dfine_linear_fwd(const void* x, int x_dtype, int64_t x_row_stride, const void* x_add, int xadd_dtype,
                      int64_t xadd_row_stride, const void* w, const void* bias, int bias_dtype, void* y, int y_dtype,
                      int64_t y_row_stride, void* x_bf16_out, int64_t M, int N, int K, int relu, void* stream);
 DFINE_API int dfine_gate_fwd(const float* x1, int64_t x1_row_stride, const float* x2, int64_t x2_row_stride,
@@ -216,6 +217,17 @@ DFINE_API int dfine_gate_fwd(const float* x1, int64_t x1_row_stride, const float
 DFINE_API int dfine_ffn_out_fwd(const void* h, int64_t h_row_stride, const void* w, const void* bias, int bias_dtype,
                       const float* residual, int64_t res_row_stride, const float* ln_weight, const float* ln_bias,
                       float eps, float* out, int64_t out_row_stride, int64_t M, int C, int F, void* stream);
+
+/* The whole FFN of a decoder layer in one launch (the hidden rows never leave the SM):
+ *     out = LayerNorm(clamp(x + (relu(x w1^T + b1) w2^T + b2), -65504, 65504))
+ * replaces forward_ffn, the residual add, the clamp and norm3 of TransformerDecoderLayer.forward
+ * (dfine_decoder.py:229-230, :251-253) under torch.autocast(bfloat16); same rounding points as
+ * dfine_linear_fwd(relu) + dfine_ffn_out_fwd.  x, out float32 [M, C]; w1 bf16 [F, C]; w2 bf16 [C, F]; b1 [F],
+ * b2 [C] (bias_dtype).  Built for C = 128 or 256, F a multiple of 128; DFINE_E_UNSUPPORTED otherwise
+ * (use the two-kernel route).  Forward only. */
+DFINE_API int dfine_ffn_fwd(const float* x, int64_t x_row_stride, const void* w1, const void* b1, const void* w2,
+                  const void* b2, int bias_dtype, const float* ln_weight, const float* ln_bias, float eps, float* out,
+                  int64_t out_row_stride, int64_t M, int C, int F, void* stream);
 
 /* LQE head, forward (inference): out = scores + reg_conf(cat(topk(softmax(pred_corners), k), mean(topk)))
  * replaces LQE.forward (dfine_decoder.py:307-313; MLP :33-46): softmax over the reg_max+1 bins of the 4

@@ -87,6 +87,13 @@ def test_linear_fwd_matches_autocast_linear(M, N, K, pos, relu, out_dtype, dev):
     else:
         same = _bf16_close(y, want, "linear_fwd")
     _log({"test": "linear_fwd", "M": M, "N": N, "K": K, "bit_identical": same})
+    if pos:     # positional rows in bf16 (what query_pos_head returns under autocast): fp32 + bf16 promotes to fp32
+        pb = p.bfloat16()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            want_b = F.linear(x + pb, w, b)
+        yb, xsb = ops.linear_fwd(x, w.bfloat16(), b.bfloat16(), x_add=pb, out_dtype=torch.bfloat16, save_input=True)
+        assert torch.equal(xsb, (x + pb).bfloat16())
+        _bf16_close(yb, want_b, "linear_fwd (bf16 positional rows)")
     # bf16 input rows (TMA-loaded A operand) give the same result as the in-kernel conversion
     y2 = ops.linear_fwd((x + p if pos else x).bfloat16(), w.bfloat16(), b.bfloat16(), relu=relu, out_dtype=out_dtype)
     assert torch.equal(y2, y)
@@ -230,6 +237,16 @@ def test_ffn_tail_matches_reference_ops(M, C, Fd, dev):
     e2 = _scale_err(got2, want)
     _log({"test": "ffn_tail", "M": M, "C": C, "F": Fd, "tail_err": e, "chained_err": e2})
     assert e <= 1e-2 and e2 <= 1e-2, (e, e2)
+    # the whole FFN in one launch (hidden rows stay on the SM): same rounding points, so it agrees with the
+    # two-kernel route except where an accumulation-order ulp flips a bf16 rounding
+    if ops.ffn_fwd_supported(t, Fd):
+        got3 = ops.ffn_fwd(t, l1.weight.detach().bfloat16(), l1.bias.detach().bfloat16(), l2.weight.detach().bfloat16(),
+                           l2.bias.detach().bfloat16(), norm.weight.detach(), norm.bias.detach(), norm.eps)
+        e3, e32 = _scale_err(got3, want), _scale_err(got3, got2)
+        same = float(((got3 - got2).abs() <= 1e-5 * got2.abs().max()).float().mean())
+        _log({"test": "ffn_fused", "M": M, "C": C, "F": Fd, "err_vs_reference": e3, "err_vs_two_kernels": e32,
+              "within_1e-5_of_two_kernels": same})
+        assert e3 <= 1e-2 and e32 <= 1e-2 and same >= 0.99, (e3, e32, same)
 
 
 def _ref_lqe(scores, pred_corners, l1, l2, k=4, reg_max=32):
@@ -321,9 +338,9 @@ def test_patched_layer_inference_parity(name, seg, batch, dev, H):
         names = set(ops.kernel_timers().keys())
         ops.enable_kernel_timers(False)
         if amp is not None:
-            assert {"gate_fwd", "ffn_out_fwd", "linear_fwd", "lqe_fwd"} <= names, names
+            assert {"gate_fwd", "ffn_fwd", "linear_fwd", "lqe_fwd"} <= names, names
         else:
-            assert not ({"gate_fwd", "ffn_out_fwd"} & names), names
+            assert not ({"gate_fwd", "ffn_out_fwd", "ffn_fwd"} & names), names
         rec = {"test": "layer_inference", "model": name, "amp": str(amp)}
         for k in keys:
             assert got[k].shape == want[k].shape and got[k].dtype == want[k].dtype, k

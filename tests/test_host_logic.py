@@ -61,11 +61,11 @@ def test_argument_validation_without_gpu():
         _lib.check(rc, "probe")
     # the fused decoder-layer entry points: shapes / dtypes before pointers
     L = lib.dfine_linear_fwd
-    assert L(None, 0, 0, None, 0, None, None, 1, None, 1, 0, None, 0, 288, 256, 0, None) == -2          # M = 0
-    assert L(None, 7, 0, None, 0, None, None, 1, None, 1, 0, None, 16, 288, 256, 0, None) == -3         # dtype
-    assert L(None, 0, 100, None, 0, None, None, 1, None, 1, 0, None, 16, 288, 256, 0, None) == -2       # stride < K
+    assert L(None, 0, 0, None, 0, 0, None, None, 1, None, 1, 0, None, 0, 288, 256, 0, None) == -2          # M = 0
+    assert L(None, 7, 0, None, 0, 0, None, None, 1, None, 1, 0, None, 16, 288, 256, 0, None) == -3         # dtype
+    assert L(None, 0, 100, None, 0, 0, None, None, 1, None, 1, 0, None, 16, 288, 256, 0, None) == -2       # stride < K
     assert b"row strides" in lib.dfine_last_error()
-    assert L(None, 0, 0, None, 0, None, None, 1, None, 1, 0, None, 16, 288, 256, 0, None) == -1         # NULL x
+    assert L(None, 0, 0, None, 0, 0, None, None, 1, None, 1, 0, None, 16, 288, 256, 0, None) == -1         # NULL x
     assert lib.dfine_gate_fwd(None, 0, None, 0, None, None, 1, None, None, 1e-5, None, 0, 16, 100, None) == -3
     assert b"multiple of 64" in lib.dfine_last_error()
     assert lib.dfine_gate_fwd(None, 0, None, 0, None, None, 1, None, None, 1e-5, None, 0, 16, 512, None) == -3
