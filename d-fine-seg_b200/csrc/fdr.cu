@@ -125,8 +125,8 @@ fdr_kernel(const void* __restrict__ corners, int c_bf16, const float* __restrict
 // reg_max + 1 <= 40 (every shipped config: 33 bins): the kernel above is instruction-issue bound (ncu, config 3:
 // 310 warp instructions per box, issue-active 69 %, DRAM 6 %).  This variant lets a warp take kBoxes consecutive
 // boxes: the W(n) table, reg_scale and the index arithmetic are set up once, the loads of all boxes are in flight
-// together, element types are compile-time, exp / reciprocal use the SFU approximations (softmax terms within
-// 2 ulp), and the box decode runs once per warp with one box per lane instead of once per box on lane 0.
+// together, element types are compile-time, exp / reciprocal use the SFU approximations for bf16 logits (softmax
+// terms within 2 ulp), and the box decode runs once per warp with one box per lane instead of once per box on lane 0.
 // ---------------------------------------------------------------------------------------------------
 template <typename T> __device__ __forceinline__ float fdr_ld(const T* p);
 template <> __device__ __forceinline__ float fdr_ld<float>(const float* p) { return __ldg(p); }
@@ -177,12 +177,14 @@ fdr_fast_kernel(const CT* __restrict__ corners, const float* __restrict__ ref_in
     float sum = 0.f;
 #pragma unroll
     for (int t = 0; t < BPL; ++t) {
-      x[b][t] = __expf(x[b][t] - m);           // exp(-inf) = 0 for the padding bins
+      // float32 logits (non-AMP runs, 1e-5 tolerances): libm exp and an IEEE division, as the generic kernel;
+      // bf16 logits: the SFU approximations (2 ulp) are far below the inputs' own resolution
+      x[b][t] = sizeof(CT) == 4 ? expf(x[b][t] - m) : __expf(x[b][t] - m);   // exp(-inf) = 0 for the padding bins
       sum += x[b][t];
     }
 #pragma unroll
     for (int o = 4; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float inv = __fdividef(1.0f, sum);
+    const float inv = sizeof(CT) == 4 ? 1.0f / sum : __fdividef(1.0f, sum);
     float dd = 0.f;
 #pragma unroll
     for (int t = 0; t < BPL; ++t) {
