@@ -17,5 +17,6 @@ for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 2):
     ops.gate_fwd(x, x2, wg, bg, lnw, lnb, 1e-5)
     h = ops.linear_fwd(x, w1, b1, relu=True)
     ops.ffn_out_fwd(h, w2, b2, x, lnw, lnb, 1e-5)
+    ops.ffn_fwd(x, w1, b1, w2, b2, lnw, lnb, 1e-5)
 torch.cuda.synchronize()
 print("ok")
