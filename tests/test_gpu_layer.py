@@ -208,7 +208,8 @@ def test_gate_fwd_matches_reference_gate(M, C, dev):
     assert frac_small >= 0.9, frac_small
 
 
-@pytest.mark.parametrize("M,C,Fd", [(1500, 256, 1024), (16000, 256, 1024), (700, 128, 512), (97, 64, 64)])
+@pytest.mark.parametrize("M,C,Fd", [(1500, 256, 1024), (16000, 256, 1024), (700, 128, 512), (97, 64, 64), (97, 128, 256),
+                                     (300, 256, 2048)])
 def test_ffn_tail_matches_reference_ops(M, C, Fd, dev):
     """linear1 + ReLU (dfine_linear_fwd) and linear2 + residual + clamp + norm3 (dfine_ffn_out_fwd) against
     TransformerDecoderLayer.forward's last three lines (dfine_decoder.py:251-253) under bf16 autocast."""
