@@ -449,7 +449,10 @@ def secondary_kernel_legs(device, peak: float, reps: int = 10):
         res = {}
         ms = timed(lambda: ops.msda_forward_raw(mem, spec, H, raw, attn_view, ref, nps, 0.5, True, torch.float32,
                                                 samp_rs=rs, attn_rs=rs, records=rec))
-        res["msda_fwd"] = {"ms": ms, "algorithmic_bytes": fwd_bytes, "frac": fwd_bytes / (ms / 1e3) / 1e9 / peak}
+        res["msda_fwd"] = {"ms": ms, "algorithmic_bytes": fwd_bytes, "frac": fwd_bytes / (ms / 1e3) / 1e9 / peak,
+                           "note": "SURVEY's formula charges the whole `memory` tensor once; the gather touches a subset "
+                                   "of it (ncu at config 3: 112.8 MB read of 156 MB algorithmic), so this fraction is an "
+                                   "upper-bound reading of the kernel's DRAM efficiency, most of all at large B x L"}
         if cf["bwd"]:
             go = torch.randn(B, Lq, H * c, device=device, generator=g)
             g_raw = torch.empty_like(raw)
