@@ -312,3 +312,21 @@ def ffn_tail(hidden, w2, b2, residual, ln_w, ln_b, eps: float) -> np.ndarray:
     autocast(bfloat16): linear2 (bf16 result) + residual in float32, clamp to +-65504, norm3."""
     t2 = linear_bf16(hidden, w2, b2)
     return layer_norm(np.clip(np.asarray(residual, np.float32) + t2, -65504.0, 65504.0), ln_w, ln_b, eps)
+
+
+def lqe_fwd(scores, corners, w1, b1, w2, b2, k: int = 4, reg_max: int = 32, emulate_bf16: bool = False) -> np.ndarray:
+    """LQE.forward (reference dfine_decoder.py:307-313; MLP :33-46): softmax over the reg_max+1 bins of the four
+    edges, the k largest probabilities per edge and their mean, reg_conf = Linear(4(k+1), H) -> ReLU -> Linear(H, 1),
+    broadcast add to the scores.  emulate_bf16: the rounding points of autocast(bfloat16) (statistics, parameters
+    and each Linear's result rounded to bf16; the sum with the bf16 scores rounded once)."""
+    sc = np.asarray(scores, np.float32)
+    x = np.asarray(corners, np.float32).reshape(*sc.shape[:-1], 4, reg_max + 1).astype(np.float64)
+    e = np.exp(x - x.max(-1, keepdims=True))
+    prob = (e / e.sum(-1, keepdims=True)).astype(np.float32)
+    top = -np.sort(-prob, axis=-1)[..., :k]
+    stat = np.concatenate([top, top.mean(-1, keepdims=True, dtype=np.float32)], -1).reshape(*sc.shape[:-1], 4 * (k + 1))
+    r = bf16_round if emulate_bf16 else (lambda a: np.asarray(a, np.float32))
+    h = r((r(stat).astype(np.float64) @ r(w1).astype(np.float64).T + r(b1).astype(np.float64)).astype(np.float32))
+    h = np.maximum(h, 0.0)
+    q = r((h.astype(np.float64) @ r(w2).astype(np.float64).T + r(b2).astype(np.float64)).astype(np.float32))
+    return r(sc + q)

@@ -19,6 +19,7 @@ Reference entry points exercised (all imported, nothing restated here):
   src/d_fine/arch/dfine_decoder.py:937  DFINETransformer._mask_logits_from_h
   src/d_fine/dfine_criterion.py:273-312  DFINECriterion._focal_loss_mask / _dice_loss
   src/d_fine/arch/dfine_decoder.py:180-256  TransformerDecoderLayer (with_pos_embed, forward_ffn, norm3), :258-271 Gate
+  src/d_fine/arch/dfine_decoder.py:298-313  LQE
 """
 from __future__ import annotations
 
@@ -351,6 +352,33 @@ def case_layer(ref):
         ln3_eps=np.float32(layer.norm3.eps), hidden_bf16=h(hid[0]), ffn_out=f(ffn_out[0]))
 
 
+def case_lqe(ref):
+    """LQE.forward (dfine_decoder.py:307-313) of the reference's LQE(4, 64, 2, 32): float32, and under CPU
+    autocast(bfloat16) with bf16 scores / corners (what the decoder hands it under AMP; note that torch's CPU
+    autocast keeps softmax / topk / mean in bf16 where CUDA autocast computes the softmax in float32).  Engineered
+    rows: a uniform distribution (all ties), saturated logits, a one-hot."""
+    g = torch.Generator().manual_seed(61)
+    B, L, nc, reg_max = 2, 45, 7, 32
+    lqe = ref.LQE(4, 64, 2, reg_max)
+    with torch.no_grad():
+        for p_ in lqe.parameters():
+            p_.copy_(bf16r(torch.randn(p_.shape, generator=g) * 0.3))     # (the output layer is zero-initialised)
+    pc = bf16r(torch.randn(B, L, 4 * (reg_max + 1), generator=g) * 3.0)
+    pc[0, 0] = 0.0
+    pc[0, 1, :33] = 80.0
+    pc[0, 2, 5] = 60.0
+    sc = bf16r(torch.randn(B, L, nc, generator=g))
+    with torch.no_grad():
+        out32 = lqe(sc, pc)
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            out16 = lqe(sc.bfloat16(), pc.bfloat16())
+    assert out32.dtype == torch.float32 and out16.dtype == torch.bfloat16
+    f = lambda t: t.detach().float().numpy().copy()
+    l1, l2 = lqe.reg_conf.layers
+    return "lqe", dict(scores=f(sc), corners=f(pc), w1=f(l1.weight), b1=f(l1.bias), w2=f(l2.weight), b2=f(l2.bias),
+                       out_f32=f(out32), out_bf16=f(out16))
+
+
 def _criterion_class():
     from src.d_fine.dfine_criterion import DFINECriterion  # noqa: E402
     return DFINECriterion
@@ -364,7 +392,7 @@ def load_reference(path: str):
         core=au.deformable_attention_core_func_v2, weighting_function=au.weighting_function,
         distance2bbox=au.distance2bbox, MSDeformableAttention=dd.MSDeformableAttention,
         Integral=dd.Integral, TransformerDecoder=dd.TransformerDecoder,
-        TransformerDecoderLayer=dd.TransformerDecoderLayer,
+        TransformerDecoderLayer=dd.TransformerDecoderLayer, LQE=dd.LQE,
         DFINETransformer=dd.DFINETransformer, DFINECriterion=_criterion_class())
 
 
@@ -392,6 +420,7 @@ def main() -> None:
         case_mask_bwd(ref),
         case_mask_loss(ref),
         case_layer(ref),
+        case_lqe(ref),
     ]
     for name, arrs in cases:
         if a.only and name not in a.only.split(","):

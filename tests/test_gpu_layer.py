@@ -309,6 +309,24 @@ def test_lqe_fwd_matches_reference_ops(B, L, nc, amp, dev):
     _log({"test": "lqe_fwd", "B": B, "L": L, "nc": nc, "amp": amp, "bit_identical": same})
 
 
+def test_lqe_kernel_matches_reference_golden_and_oracle(dev):
+    """tests/golden/lqe.npz: outputs of the reference's own LQE class (float32 and autocast bf16)."""
+    import numpy as np
+    from dfine_b200 import ops
+    from oracle import cpu_oracle as O
+    from util import golden
+    g = golden("lqe")
+    T = lambda a, dt=torch.float32: torch.from_numpy(np.ascontiguousarray(a)).to(dev).to(dt)
+    w = [T(g[k]) for k in ("w1", "b1", "w2", "b2")]
+    got = ops.lqe_fwd(T(g["scores"]), T(g["corners"]), *w)
+    assert _scale_err(got, T(g["out_f32"])) <= 1e-5
+    assert _scale_err(got, T(O.lqe_fwd(g["scores"], g["corners"], g["w1"], g["b1"], g["w2"], g["b2"]))) <= 1e-5
+    got = ops.lqe_fwd(T(g["scores"], torch.bfloat16), T(g["corners"], torch.bfloat16), *w, emulate_bf16=True)
+    assert _scale_err(got.float(), T(g["out_bf16"])) <= 1e-2      # CPU autocast keeps softmax in bf16: bf16 tolerance
+    _bf16_close(got, T(O.lqe_fwd(g["scores"], g["corners"], g["w1"], g["b1"], g["w2"], g["b2"], emulate_bf16=True)),
+                "lqe (bf16) vs oracle")
+
+
 @pytest.fixture(scope="module")
 def H():
     from baseline import model_harness, ref_install

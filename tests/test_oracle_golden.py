@@ -186,3 +186,15 @@ def test_gate_and_ffn_tail_match_reference_autocast():
     assert (np.abs(got - g["gate_out"]) <= 1e-5 * np.abs(g["gate_out"]).max()).mean() >= 0.999
     got = O.ffn_tail(g["hidden"], g["w2"], g["b2"], g["target"], g["ln3_w"], g["ln3_b"], float(g["ln3_eps"]))
     assert_close(got, g["ffn_out"], FP32_RTOL, "ffn tail")       # row 0 went through the clamp of :253
+
+
+def test_lqe_matches_reference():
+    # reference: LQE.forward, dfine_decoder.py:307-313 (float32, and CPU autocast(bfloat16))
+    g = golden("lqe")
+    args = (g["scores"], g["corners"], g["w1"], g["b1"], g["w2"], g["b2"])
+    assert_close(O.lqe_fwd(*args), g["out_f32"], FP32_RTOL, "lqe float32")
+    # torch's CPU autocast keeps softmax / topk / mean in bf16 (CUDA autocast runs softmax in float32, which is what
+    # the oracle's emulate_bf16 and the kernel restate): the CPU fixture pins the bf16 route to the north star's
+    # bf16 tolerance only; the CUDA policy is checked against the reference's ops on the GPU itself
+    # (tests/test_gpu_layer.py::test_lqe_fwd_matches_reference_ops)
+    assert_close(O.lqe_fwd(*args, emulate_bf16=True), g["out_bf16"], 1e-2, "lqe autocast (CPU policy)")
