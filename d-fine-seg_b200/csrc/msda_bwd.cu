@@ -111,7 +111,7 @@ msda_bwd_kernel(const MsdaParams p) {
     if (item_ok) load_go<VPL>(p.grad_out, ((size_t)b * n_items + item) * p.c + sub * VPL, p.go_bf16, go);
     const int h = p.h_shift >= 0 ? (item & (p.H - 1)) : item % p.H;
 
-#pragma unroll 1
+#pragma unroll 3
     for (int pt0 = 0; pt0 < P; pt0 += SPI) {
       const int pt = pt0 + ps;
       const bool live = item_ok && pt < P;
