@@ -10,6 +10,8 @@ into ``param.grad``.  Plain ``torch.distributed`` plumbing -- no kernels of ours
 """
 from __future__ import annotations
 
+import os
+
 from typing import Iterable, List, Optional, Sequence
 
 import torch
@@ -149,8 +151,8 @@ class NvlsGradExchange:
 
         begin_step():  zero the local replica; barrier A   (on a forked side stream: hidden under the step)
         ... backward: dfine_linear_wgrad per layer into the local blocks ...
-        end_step():    dfine_multicast_add (1.2 MB, one launch); barrier B -> every replica holds the rank
-                       average (DDP's result, reference src/dl/train.py:161-166)
+        end_step():    dfine_multicast_add (1.2 MB, one launch; layer-wise variant: block_ready); barrier B ->
+                       every replica holds the rank average (DDP's result, reference src/dl/train.py:161-166)
 
     All of it is capturable in a CUDA graph.  Raises if the device / fabric has no multicast support."""
 
@@ -176,6 +178,14 @@ class NvlsGradExchange:
         self.local = torch.zeros(self.total, dtype=torch.float32, device=device)   # this rank's own gradients
         self._next = 0
         self._side = None
+        # layer-wise (DFINE_NVLS_LAYERWISE=1, off by default): a layer's block is added into the replicas on the
+        # side stream as soon as its weight-gradient kernel is done, under the backward of the remaining layers.
+        # Measured at N = 2 inside the step (bench.py, DFINE_NVLS_PROBE): exchange off 0.951 ms; coupling only
+        # (barrier A + join) 0.958; + the 1.18-MB add 0.982 (the add alone takes 3.9 us on an idle pair of GPUs);
+        # + barrier B 0.988.  Layer-wise adds: 0.991 vs 0.995 in the same run -- the 24 us are not the add's own
+        # duration on the critical path but what the reductions cost the kernels running beside them.
+        self.layerwise = os.environ.get("DFINE_NVLS_LAYERWISE", "0") == "1"
+        self._added = 0
         self.buf.zero_()
         self.handle.barrier(channel=0)
 
@@ -184,13 +194,15 @@ class NvlsGradExchange:
         """Zero the local replica and meet the other ranks (barrier A) on a side stream forked from the
         current one: both run under the step's forward / backward kernels; end_step() joins."""
         self._next = 0
+        self._added = 0
         dev = self.local.device
         if self._side is None:
             self._side = torch.cuda.Stream(dev)
         self._side.wait_stream(torch.cuda.current_stream(dev))    # after the last reader of the replica
         with torch.cuda.stream(self._side):
             self.buf.zero_()
-            self.handle.barrier(channel=0)
+            if "begin" not in os.environ.get("DFINE_NVLS_PROBE", ""):
+                self.handle.barrier(channel=0)
 
     def end_step(self) -> None:
         from . import _lib
@@ -198,11 +210,17 @@ class NvlsGradExchange:
             raise RuntimeError(f"NvlsGradExchange.end_step: {self._next} of {len(self.slots)} gradient blocks "
                                "were produced (every rank must produce all of them)")
         torch.cuda.current_stream(self.local.device).wait_stream(self._side)   # every replica is zero
-        with torch.cuda.device_of(self.local):
-            rc = _lib.lib().dfine_multicast_add(self.local.data_ptr(), self.mc_ptr, self.total, self.scale,
-                                                torch.cuda.current_stream(self.local.device).cuda_stream)
-        _lib.check(rc, "dfine_multicast_add")
-        self.handle.barrier(channel=1)
+        skip = os.environ.get("DFINE_NVLS_PROBE", "")     # timing probes only (results are wrong with them)
+        if "add" not in skip and self._added < len(self.slots):
+            # whatever was not added layer by layer (everything when layerwise is off)
+            o = self.offsets[self._added]
+            with torch.cuda.device_of(self.local):
+                rc = _lib.lib().dfine_multicast_add(self.local.data_ptr() + 4 * o, self.mc_ptr + 4 * o, self.total - o,
+                                                    self.scale, torch.cuda.current_stream(self.local.device).cuda_stream)
+            _lib.check(rc, "dfine_multicast_add")
+            self._added = len(self.slots)
+        if "barrier" not in skip:
+            self.handle.barrier(channel=1)
 
     # -- called by ops.linear_wgrad --------------------------------------------------------------
     def next_block(self, n_floats: int):
@@ -214,6 +232,26 @@ class NvlsGradExchange:
         self._next += 1
         o = self.offsets[k]
         return self.local[o:o + n_floats], self.buf[o:o + n_floats]
+
+    def block_ready(self) -> None:
+        """Called by ops.linear_wgrad right after the weight-gradient kernel of the block handed out last was
+        enqueued on the current stream: (layer-wise mode) fork its multicast add onto the side stream."""
+        from . import _lib
+        k = self._next - 1
+        if not self.layerwise or k != self._added or "add" in os.environ.get("DFINE_NVLS_PROBE", ""):
+            return
+        dev = self.local.device
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        o = self.offsets[k]
+        n = (self.slots[k] + 3) & ~3
+        with torch.cuda.stream(self._side):          # after barrier A (same stream): every replica is zero
+            self._side.wait_event(ev)
+            with torch.cuda.device_of(self.local):
+                rc = _lib.lib().dfine_multicast_add(self.local.data_ptr() + 4 * o, self.mc_ptr + 4 * o, n, self.scale,
+                                                    self._side.cuda_stream)
+            _lib.check(rc, "dfine_multicast_add")
+        self._added = k + 1
 
     def __enter__(self):
         from . import ops

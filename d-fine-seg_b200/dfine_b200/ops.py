@@ -901,6 +901,7 @@ def linear_wgrad(gy: torch.Tensor, x: torch.Tensor):
             rc = _lib.lib().dfine_linear_wgrad(gy.data_ptr(), gy.stride(0), x.data_ptr(), x.stride(0), M, N, K,
                                                buf.data_ptr(), _stream(gy))
         check(rc, "dfine_linear_wgrad")
+        ex.block_ready()
         return out[:N * K].view(N, K), out[N * K:]
     buf = torch.empty(N * K + N, dtype=torch.float32, device=gy.device)
     with torch.cuda.device_of(gy), _timed("linear_wgrad", gy):
